@@ -1,0 +1,235 @@
+/*
+ * optmc.h -- C ABI of liboptmc.so, the B200 (sm_100a) Monte Carlo engine that
+ * replaces the numba hot path of Diljit22/optpricing.
+ *
+ * The reference has no FFI today: its "operator API" for this path is the set
+ * of Python functions below, and every entry point here names the one it
+ * replaces (paths relative to /root/reference/src/optpricing/techniques/).
+ * INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (optmc_last_error
+ *     gives the text); nothing throws across the ABI;
+ *   - one process drives one GPU: a ctx is bound to one device; calls on one
+ *     ctx are not re-entrant; distinct ctx objects are independent;
+ *   - *_dev pointers are device memory owned by the caller (in the Python
+ *     host layer: torch tensors); `stream` is a cudaStream_t passed as void*
+ *     (NULL = the legacy default stream).  The library itself allocates only a
+ *     few KB of scratch at ctx creation;
+ *   - functions whose name ends in _async only enqueue work on `stream`; the
+ *     others synchronise the stream once before returning and write their
+ *     results to host memory.
+ *   - all floating point is IEEE binary64.
+ */
+#ifndef OPTMC_H
+#define OPTMC_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct optmc_ctx optmc_ctx;
+
+/* Dispatch order of monte_carlo.py:130-197 / american_monte_carlo.py:87-150 */
+enum optmc_model_kind {
+    OPTMC_BSM = 0,       /* kernels/mc_kernels.py:18-34   path_kernels.py:17-35   */
+    OPTMC_HESTON = 1,    /* mc_kernels.py:43-79           path_kernels.py:43-77   */
+    OPTMC_MERTON = 2,    /* mc_kernels.py:88-118          path_kernels.py:85-121  */
+    OPTMC_BATES = 3,     /* mc_kernels.py:127-177         path_kernels.py:130-180 */
+    OPTMC_SABR = 4,      /* mc_kernels.py:186-218         path_kernels.py:189-217 */
+    OPTMC_SABR_JUMP = 5, /* mc_kernels.py:227-276         path_kernels.py:225-274 */
+    OPTMC_KOU = 6        /* mc_kernels.py:285-329         path_kernels.py:277-324 */
+};
+
+/* The reference's kernel_params dict (monte_carlo.py:128-197), flattened.
+   Fields a model does not use are ignored. */
+typedef struct optmc_model {
+    int32_t kind;       /* enum optmc_model_kind */
+    int32_t reserved;
+    double r, q;        /* risk-free rate, dividend yield */
+    double sigma;       /* BSM, Merton, Kou */
+    double v0;          /* Heston/Bates initial variance; SABR initial vol */
+    double kappa, theta, rho, vol_of_vol; /* Heston/Bates; rho also SABR */
+    double alpha, beta; /* SABR */
+    double lambda, mu_j, sigma_j;         /* Merton, Bates, SABR-jump */
+    double p_up, eta1, eta2;              /* Kou */
+} optmc_model;
+
+/* How the two Brownian drivers of a variance model are mixed (Philox mode). */
+enum optmc_correlation {
+    /* dw1 = rho*a + rho_bar*b, dw2 = a, then the kernel's own
+       rho*dw1 + rho_bar*dw2: what MonteCarloTechnique does
+       (monte_carlo.py:222-231 followed by mc_kernels.py:67). */
+    OPTMC_CORR_REFERENCE_EUROPEAN = 0,
+    /* dw1 = a, dw2 = b (american_monte_carlo.py:181-185): corr(dW_S, dW_v) = rho */
+    OPTMC_CORR_INDEPENDENT_DRAWS = 1
+};
+
+/* One simulation job (monte_carlo.py:199-215). */
+typedef struct optmc_sim {
+    double s0;            /* Stock.spot */
+    double maturity;      /* Option.maturity; dt = maturity / n_steps */
+    int64_t n_draws;      /* draws of the WHOLE job: n_paths/2 if antithetic else n_paths
+                             (num_draws, monte_carlo.py:210) */
+    int64_t draw_offset;  /* first draw this call simulates (multi-GPU partition) */
+    int64_t n_local;      /* draws this call simulates: [draw_offset, draw_offset+n_local) */
+    int32_t n_steps;
+    int32_t antithetic;   /* 1: each draw also yields its negated partner */
+    uint64_t seed;        /* Philox4x32-10 key; the stream of draw g depends only on (seed, g) */
+    int32_t correlation;  /* enum optmc_correlation */
+    int32_t reserved;
+} optmc_sim;
+
+/* Per contract, over this call's samples (a sample = one draw: the mean of the
+   antithetic pair when antithetic, else one path; payoff p and control c = S_T
+   are undiscounted):
+     m[0] = n samples   m[1] = sum p   m[2] = sum p^2
+     m[3] = sum c       m[4] = sum c^2 m[5] = sum p*c
+   Sums over disjoint draw ranges (ranks) add. */
+#define OPTMC_NMOM 6
+
+int optmc_version(void);
+int optmc_ctx_create(int device, optmc_ctx **out);
+void optmc_ctx_destroy(optmc_ctx *ctx);
+const char *optmc_last_error(const optmc_ctx *ctx); /* ctx may be NULL: last create error */
+
+/*
+ * European pricing, on-device RNG.  Replaces the whole of
+ * MonteCarloTechnique._simulate_sde_path + payoff + mean
+ * (monte_carlo.py:199-257 and :110-115): no increments are materialised.
+ * Writes OPTMC_NMOM doubles per contract.
+ *   optmc_european_async: moments_dev is device memory; nothing is synchronised.
+ *   optmc_european:       moments_host is host memory; returns after one sync.
+ * terminal_dev (optional, may be NULL): receives S_T, n_local doubles for the
+ * draws followed (if antithetic) by n_local doubles for their partners -- the
+ * order of np.concatenate([ST, ST_anti]) (monte_carlo.py:255).
+ */
+int optmc_european_async(optmc_ctx *ctx, const optmc_model *model, const optmc_sim *sim,
+                         int32_t n_contracts, const double *strikes,
+                         const int32_t *is_call, double *moments_dev,
+                         double *terminal_dev, void *stream);
+int optmc_european(optmc_ctx *ctx, const optmc_model *model, const optmc_sim *sim,
+                   int32_t n_contracts, const double *strikes, const int32_t *is_call,
+                   double *moments_host, double *terminal_dev, void *stream);
+
+/*
+ * Fed-draw kernels: the drop-in for the 7 terminal kernels of mc_kernels.py and
+ * the 7 path kernels of path_kernels.py, same inputs in the same C-order
+ * layouts, all in device memory:
+ *   dw1_dev        double[n_paths][n_steps]   (`dw` for one-factor models)
+ *   dw2_dev        double[n_paths][n_steps]   (two-factor models, else NULL)
+ *   counts_dev     int64 [n_paths][n_steps]   (jump models, else NULL)
+ *   jumps_dev      double[n_jumps]  jump sizes in the order the reference pulls
+ *                  them from its RNG: by step, then path, then jump
+ *                  (Merton/Bates/Kou: additive log-jumps; SABR-jump: the
+ *                  N(mu_j, sigma_j) draws, exponentiated here)
+ *   x0             log_s0, or s0 for the SABR kinds (monte_carlo.py:217-220)
+ *   sign           +1.0, or -1.0 for the antithetic second pass
+ *                  (monte_carlo.py:247-254) without touching the buffers
+ *   terminal_dev   double[n_paths] log S_T (S_T for SABR kinds) or NULL
+ *   paths_dev      double[n_paths][n_steps+1] spot matrix or NULL
+ *   path_sum_mode  1: jumps of one path-step are summed, then added
+ *                  (path_kernels.py, kou_kernel); 0: added one by one
+ *   workspace_dev  optmc_fed_workspace_bytes() bytes, 8-byte aligned
+ */
+int64_t optmc_fed_workspace_bytes(int32_t kind, int64_t n_paths, int32_t n_steps);
+int optmc_fed_async(optmc_ctx *ctx, const optmc_model *model, double x0, double dt,
+                    int64_t n_paths, int32_t n_steps, const double *dw1_dev,
+                    const double *dw2_dev, const int64_t *counts_dev,
+                    const double *jumps_dev, int64_t n_jumps, double sign,
+                    int32_t path_sum_mode, double *terminal_dev, double *paths_dev,
+                    void *workspace_dev, int64_t workspace_bytes, void *stream);
+
+/*
+ * Strike sweep over stored terminal spots: moments for n_contracts payoffs of
+ * the same maturity from one simulation (BASELINE config 3).  terminal_dev is
+ * laid out as optmc_european writes it.
+ */
+int optmc_payoff_sweep_async(optmc_ctx *ctx, const double *terminal_dev, int64_t n_local,
+                             int32_t antithetic, int32_t n_contracts,
+                             const double *strikes, const int32_t *is_call,
+                             double *moments_dev, void *stream);
+
+/*
+ * Longstaff-Schwartz, replacing AmericanMonteCarloTechnique.price
+ * (american_monte_carlo.py:52-73).
+ *
+ * Path store: step-major, store_dev[(i-1) * ld + j] = spot of local path j at
+ * date i (i = 1..n_steps), j < n_paths_local = n_local * (antithetic ? 2 : 1),
+ * partners at j + n_local; ld >= n_paths_local, a multiple of 2.
+ *
+ *   optmc_lsmc_paths_async   simulate (Philox) and fill the store; replaces
+ *                            _simulate_full_sde_paths (:152-207) + path_kernels.py
+ *   optmc_lsmc_load_async    fill the store from a reference-layout matrix
+ *                            paths_dev[n_paths][n_steps+1] (column 0 ignored)
+ *   optmc_lsmc_begin_async   cashflow = payoff at T      (american_mc_kernels.py:48-51)
+ *   optmc_lsmc_gram_async    date i: cashflow *= exp(-r dt); accumulate the
+ *                            in-the-money power sums sum x^k (k <= 2d) and
+ *                            sum y x^k (k <= d) of the shifted variable
+ *                            x = S/K - 1 into gram_dev   (:54-69; the X'X and
+ *                            X'y of :72 are read off these sums)
+ *   optmc_lsmc_decide_async  solve the normal equations from gram_dev (after
+ *                            any cross-rank all-reduce) and exercise where
+ *                            intrinsic > fitted continuation (:72-80); a
+ *                            rank-deficient or non-positive-definite system
+ *                            skips the date like the bare `except` of :81-82
+ *   optmc_lsmc_finish_async  out_dev[0..2] = n, sum cf*disc, sum (cf*disc)^2 (:84)
+ *   optmc_lsmc               all of the above for one GPU, one sync, host result
+ *
+ * gram_dev: OPTMC_LSMC_GRAM doubles per date:
+ *   [0] n_itm, [1..2d] sum x^k, then [16 + k] sum y x^k (k = 0..d).  degree <= 7.
+ */
+#define OPTMC_LSMC_GRAM 24
+#define OPTMC_LSMC_MAX_DEGREE 7
+
+int optmc_lsmc_paths_async(optmc_ctx *ctx, const optmc_model *model, const optmc_sim *sim,
+                           double *store_dev, int64_t ld, void *stream);
+int optmc_lsmc_load_async(optmc_ctx *ctx, const double *paths_dev, int64_t n_paths,
+                          int32_t n_steps, double *store_dev, int64_t ld, void *stream);
+int optmc_lsmc_begin_async(optmc_ctx *ctx, const double *store_dev, int64_t ld,
+                           int64_t n_paths, int32_t n_steps, double strike,
+                           int32_t is_call, double *cashflow_dev, void *stream);
+int optmc_lsmc_gram_async(optmc_ctx *ctx, const double *store_dev, int64_t ld,
+                          int64_t n_paths, int32_t date, double strike, int32_t is_call,
+                          double discount, int32_t degree, double *cashflow_dev,
+                          double *gram_dev, void *stream);
+int optmc_lsmc_decide_async(optmc_ctx *ctx, const double *store_dev, int64_t ld,
+                            int64_t n_paths, int32_t date, double strike, int32_t is_call,
+                            int32_t degree, const double *gram_dev, double *cashflow_dev,
+                            void *stream);
+int optmc_lsmc_finish_async(optmc_ctx *ctx, int64_t n_paths, double discount,
+                            const double *cashflow_dev, double *out_dev, void *stream);
+int optmc_lsmc(optmc_ctx *ctx, const double *store_dev, int64_t ld, int64_t n_paths,
+               int32_t n_steps, double strike, int32_t is_call, double r, double dt,
+               int32_t degree, double *cashflow_dev, double *gram_dev, double *out_host,
+               void *stream);
+
+/*
+ * Diagnostics used by the tests and by bench.py's roofline.
+ *   optmc_philox_raw     out_dev[4*i..] = Philox4x32-10(counter = (lo(i), hi(i), c2, c3), key = seed)
+ *   optmc_normals        out_dev[2*i], out_dev[2*i+1] = the two N(0,1) the engine
+ *                        derives for (draw i, step `step`)
+ *   optmc_fp64_peak      runs a register-resident DFMA loop on every SM for
+ *                        ~`iters` iterations and returns fp64 FMA instructions
+ *                        per second (thread-level): the measured denominator of
+ *                        the fp64-pipe roofline
+ */
+int optmc_philox_raw(optmc_ctx *ctx, uint64_t seed, int64_t n, uint32_t c2, uint32_t c3,
+                     uint32_t *out_dev, void *stream);
+int optmc_normals(optmc_ctx *ctx, uint64_t seed, int64_t n, int32_t step, double *out_dev,
+                  void *stream);
+int optmc_fp64_peak(optmc_ctx *ctx, int64_t iters, double *fma_per_sec, double *elapsed_ms);
+
+/* Tunables: "normals_impl" (0 = CUDA math library Box-Muller, 1 = hand-written,
+   default 1), "euro_blocks_per_sm" (0 = occupancy API decides). */
+int optmc_set_int(optmc_ctx *ctx, const char *key, int64_t value);
+
+/* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
+int64_t optmc_launch_count(const optmc_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPTMC_H */

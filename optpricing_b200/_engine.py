@@ -1,0 +1,374 @@
+"""
+ctypes binding of liboptmc.so (include/optmc.h) plus the per-process engine
+object the techniques share.
+
+PyTorch is plumbing here: it owns device buffers (``torch.empty(..., device=)``)
+and the stream; every kernel is in liboptmc.so.  There is no CPU fallback: if
+the library is missing or no B200 is visible, constructing the engine raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liboptmc.so")
+
+KIND_CODES = {"bsm": 0, "heston": 1, "merton": 2, "bates": 3, "sabr": 4, "sabr_jump": 5, "kou": 6}
+TWO_FACTOR = ("heston", "bates", "sabr", "sabr_jump")
+JUMP_KINDS = ("merton", "bates", "sabr_jump", "kou")
+SABR_KINDS = ("sabr", "sabr_jump")
+CORR_REFERENCE_EUROPEAN = 0
+CORR_INDEPENDENT_DRAWS = 1
+NMOM = 6
+LSMC_GRAM = 24
+
+c_void_p, c_int, c_i32, c_i64, c_u32, c_u64, c_double = (
+    ctypes.c_void_p, ctypes.c_int, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32,
+    ctypes.c_uint64, ctypes.c_double)
+_dp = ctypes.POINTER(c_double)
+_ip = ctypes.POINTER(c_i32)
+
+
+class OptmcModel(ctypes.Structure):
+    """struct optmc_model (include/optmc.h)."""
+    _fields_ = [("kind", c_i32), ("reserved", c_i32), ("r", c_double), ("q", c_double),
+                ("sigma", c_double), ("v0", c_double), ("kappa", c_double), ("theta", c_double),
+                ("rho", c_double), ("vol_of_vol", c_double), ("alpha", c_double),
+                ("beta", c_double), ("lambda_", c_double), ("mu_j", c_double),
+                ("sigma_j", c_double), ("p_up", c_double), ("eta1", c_double),
+                ("eta2", c_double)]
+
+
+class OptmcSim(ctypes.Structure):
+    """struct optmc_sim (include/optmc.h)."""
+    _fields_ = [("s0", c_double), ("maturity", c_double), ("n_draws", c_i64),
+                ("draw_offset", c_i64), ("n_local", c_i64), ("n_steps", c_i32),
+                ("antithetic", c_i32), ("seed", c_u64), ("correlation", c_i32),
+                ("reserved", c_i32)]
+
+
+# every symbol include/optmc.h declares: (name, restype, argtypes)
+SIGNATURES = [
+    ("optmc_version", c_int, []),
+    ("optmc_ctx_create", c_int, [c_int, ctypes.POINTER(c_void_p)]),
+    ("optmc_ctx_destroy", None, [c_void_p]),
+    ("optmc_last_error", ctypes.c_char_p, [c_void_p]),
+    ("optmc_european_async", c_int, [c_void_p, ctypes.POINTER(OptmcModel),
+                                     ctypes.POINTER(OptmcSim), c_i32, _dp, _ip, c_void_p,
+                                     c_void_p, c_void_p]),
+    ("optmc_european", c_int, [c_void_p, ctypes.POINTER(OptmcModel), ctypes.POINTER(OptmcSim),
+                               c_i32, _dp, _ip, _dp, c_void_p, c_void_p]),
+    ("optmc_fed_workspace_bytes", c_i64, [c_i32, c_i64, c_i32]),
+    ("optmc_fed_async", c_int, [c_void_p, ctypes.POINTER(OptmcModel), c_double, c_double, c_i64,
+                                c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_double,
+                                c_i32, c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
+    ("optmc_payoff_sweep_async", c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i32, _dp, _ip,
+                                         c_void_p, c_void_p]),
+    ("optmc_lsmc_paths_async", c_int, [c_void_p, ctypes.POINTER(OptmcModel),
+                                       ctypes.POINTER(OptmcSim), c_void_p, c_i64, c_void_p]),
+    ("optmc_lsmc_load_async", c_int, [c_void_p, c_void_p, c_i64, c_i32, c_void_p, c_i64,
+                                      c_void_p]),
+    ("optmc_lsmc_begin_async", c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i32, c_double, c_i32,
+                                       c_void_p, c_void_p]),
+    ("optmc_lsmc_gram_async", c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i32, c_double, c_i32,
+                                      c_double, c_i32, c_void_p, c_void_p, c_void_p]),
+    ("optmc_lsmc_decide_async", c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i32, c_double,
+                                        c_i32, c_i32, c_void_p, c_void_p, c_void_p]),
+    ("optmc_lsmc_finish_async", c_int, [c_void_p, c_i64, c_double, c_void_p, c_void_p,
+                                        c_void_p]),
+    ("optmc_lsmc", c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i32, c_double, c_i32, c_double,
+                           c_double, c_i32, c_void_p, c_void_p, _dp, c_void_p]),
+    ("optmc_philox_raw", c_int, [c_void_p, c_u64, c_i64, c_u32, c_u32, c_void_p, c_void_p]),
+    ("optmc_normals", c_int, [c_void_p, c_u64, c_i64, c_i32, c_void_p, c_void_p]),
+    ("optmc_fp64_peak", c_int, [c_void_p, c_i64, _dp, _dp]),
+    ("optmc_set_int", c_int, [c_void_p, ctypes.c_char_p, c_i64]),
+    ("optmc_launch_count", c_i64, [c_void_p]),
+]
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library() -> ctypes.CDLL:
+    """dlopen liboptmc.so and bind every declared symbol.  Needs no GPU."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EngineError(
+                f"{LIB_PATH} is missing: build it with `python -m optpricing_b200.build` "
+                "(there is no CPU fallback)")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, restype, argtypes in SIGNATURES:
+            fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+    return _lib
+
+
+def make_model(kind: str, params: dict, r: float, q: float, v0=None) -> OptmcModel:
+    """
+    Flatten the reference's ``kernel_params`` (monte_carlo.py:128-197) into
+    struct optmc_model.  ``v0`` follows the reference: kwarg first, then
+    params["v0"] (Heston/Bates) or params["alpha"] (SABR).
+    """
+    m = OptmcModel()
+    m.kind = KIND_CODES[kind]
+    m.r, m.q = float(r), float(q)
+    p = params
+    if kind in ("bsm", "merton", "kou"):
+        m.sigma = float(p["sigma"])
+    if kind in ("heston", "bates"):
+        m.kappa, m.theta, m.rho, m.vol_of_vol = (float(p["kappa"]), float(p["theta"]),
+                                                 float(p["rho"]), float(p["vol_of_vol"]))
+        m.v0 = float(v0 if v0 is not None else p.get("v0"))
+    if kind in SABR_KINDS:
+        m.alpha, m.beta, m.rho = float(p["alpha"]), float(p["beta"]), float(p["rho"])
+        m.v0 = float(v0 if v0 is not None else p.get("alpha"))
+    if kind in ("merton", "bates", "sabr_jump"):
+        m.lambda_, m.mu_j, m.sigma_j = float(p["lambda"]), float(p["mu_j"]), float(p["sigma_j"])
+    if kind == "kou":
+        m.lambda_, m.p_up, m.eta1, m.eta2 = (float(p["lambda"]), float(p["p_up"]),
+                                             float(p["eta1"]), float(p["eta2"]))
+    return m
+
+
+class Engine:
+    """One liboptmc context on one CUDA device, plus torch-owned device buffers."""
+
+    def __init__(self, device: int | None = None):
+        import torch
+
+        self.torch = torch
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise EngineError("no CUDA device visible: the optpricing_b200 engine needs a B200 "
+                              "(there is no CPU fallback)")
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        ctx = c_void_p()
+        rc = self.lib.optmc_ctx_create(self.device_index, ctypes.byref(ctx))
+        if rc != 0:
+            raise EngineError("optmc_ctx_create: " + self.lib.optmc_last_error(None).decode())
+        self.ctx = ctx
+        self._buffers = {}
+
+    # -- plumbing -----------------------------------------------------------
+    def _check(self, rc, what):
+        if rc != 0:
+            raise EngineError(f"{what}: {self.lib.optmc_last_error(self.ctx).decode()}")
+
+    def stream(self):
+        return c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def buffer(self, name, n, dtype=None):
+        """A cached device buffer of at least n elements (grown, never shrunk)."""
+        torch = self.torch
+        dtype = dtype or torch.float64
+        t = self._buffers.get(name)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = torch.empty(max(int(n), 1), dtype=dtype, device=self.device)
+            self._buffers[name] = t
+        return t
+
+    def set_int(self, key: str, value: int):
+        self._check(self.lib.optmc_set_int(self.ctx, key.encode(), int(value)), "optmc_set_int")
+
+    def launch_count(self) -> int:
+        return int(self.lib.optmc_launch_count(self.ctx))
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.optmc_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    # -- European, device RNG ----------------------------------------------
+    def make_sim(self, s0, maturity, n_draws, n_steps, antithetic, seed, correlation,
+                 draw_offset=0, n_local=None) -> OptmcSim:
+        s = OptmcSim()
+        s.s0, s.maturity = float(s0), float(maturity)
+        s.n_draws = int(n_draws)
+        s.draw_offset = int(draw_offset)
+        s.n_local = int(n_draws - draw_offset if n_local is None else n_local)
+        s.n_steps = int(n_steps)
+        s.antithetic = 1 if antithetic else 0
+        s.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        s.correlation = int(correlation)
+        return s
+
+    @staticmethod
+    def _contracts(strikes, is_call):
+        k = np.ascontiguousarray(np.atleast_1d(strikes), dtype=np.float64)
+        c = np.ascontiguousarray(np.broadcast_to(np.atleast_1d(is_call), k.shape), dtype=np.int32)
+        return k, c, k.ctypes.data_as(_dp), c.ctypes.data_as(_ip)
+
+    def european(self, model: OptmcModel, sim: OptmcSim, strikes, is_call, terminal=None):
+        """optmc_european: host moments array (n_contracts, 6) after one sync."""
+        k, c, kp, cp = self._contracts(strikes, is_call)
+        out = np.empty((k.size, NMOM))
+        tptr = c_void_p(terminal.data_ptr()) if terminal is not None else None
+        if k.size > 1 and terminal is None:
+            terminal = self.buffer("terminal", sim.n_local * (2 if sim.antithetic else 1))
+            tptr = c_void_p(terminal.data_ptr())
+        self._check(self.lib.optmc_european(self.ctx, ctypes.byref(model), ctypes.byref(sim),
+                                            k.size, kp, cp, out.ctypes.data_as(_dp), tptr,
+                                            self.stream()), "optmc_european")
+        return out
+
+    def european_async(self, model, sim, strikes, is_call, moments, terminal=None):
+        """optmc_european_async into the torch tensor ``moments`` (n_contracts*6 f64)."""
+        k, c, kp, cp = self._contracts(strikes, is_call)
+        tptr = c_void_p(terminal.data_ptr()) if terminal is not None else None
+        self._check(self.lib.optmc_european_async(self.ctx, ctypes.byref(model),
+                                                  ctypes.byref(sim), k.size, kp, cp,
+                                                  c_void_p(moments.data_ptr()), tptr,
+                                                  self.stream()), "optmc_european_async")
+
+    def payoff_sweep(self, terminal, n_local, antithetic, strikes, is_call):
+        k, c, kp, cp = self._contracts(strikes, is_call)
+        mom = self.buffer("sweep_moments", k.size * NMOM)
+        self._check(self.lib.optmc_payoff_sweep_async(self.ctx, c_void_p(terminal.data_ptr()),
+                                                      int(n_local), 1 if antithetic else 0,
+                                                      k.size, kp, cp, c_void_p(mom.data_ptr()),
+                                                      self.stream()), "optmc_payoff_sweep_async")
+        return mom[: k.size * NMOM].cpu().numpy().reshape(k.size, NMOM)
+
+    # -- fed-draw kernels ---------------------------------------------------
+    def fed(self, kind, model: OptmcModel, x0, dt, dw1, dw2=None, counts=None, jumps=None,
+            sign=1.0, path_sum_mode=0, want_terminal=True, want_paths=False):
+        """
+        Run the fed kernel on host (numpy) or device (torch) inputs laid out as
+        the reference passes them; returns numpy arrays (terminal, paths).
+        """
+        torch = self.torch
+
+        def dev(a, dtype):
+            if a is None:
+                return None
+            if isinstance(a, torch.Tensor):
+                return a.to(device=self.device, dtype=dtype).contiguous()
+            return torch.from_numpy(np.ascontiguousarray(a)).to(device=self.device, dtype=dtype)
+
+        d1 = dev(dw1, torch.float64)
+        n_paths, n_steps = d1.shape
+        d2 = dev(dw2, torch.float64)
+        cn = dev(counts, torch.int64)
+        jb = dev(jumps, torch.float64)
+        term = torch.empty(n_paths, dtype=torch.float64, device=self.device) if want_terminal else None
+        paths = (torch.empty((n_paths, n_steps + 1), dtype=torch.float64, device=self.device)
+                 if want_paths else None)
+        ws_bytes = int(self.lib.optmc_fed_workspace_bytes(KIND_CODES[kind], n_paths, n_steps))
+        ws = torch.empty(max(ws_bytes // 8, 1), dtype=torch.int64, device=self.device)
+        ptr = lambda t: c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+        self._check(self.lib.optmc_fed_async(
+            self.ctx, ctypes.byref(model), float(x0), float(dt), n_paths, n_steps, ptr(d1),
+            ptr(d2), ptr(cn), ptr(jb), 0 if jb is None else jb.numel(), float(sign),
+            int(path_sum_mode), ptr(term), ptr(paths), ptr(ws), ws.numel() * 8, self.stream()),
+            "optmc_fed_async")
+        return (term.cpu().numpy() if term is not None else None,
+                paths.cpu().numpy() if paths is not None else None)
+
+    # -- Longstaff-Schwartz ---------------------------------------------------
+    def lsmc_store(self, n_paths, n_steps):
+        ld = (int(n_paths) + 1) // 2 * 2
+        return self.buffer("lsmc_store", ld * int(n_steps)), ld
+
+    def lsmc_fill_paths(self, model, sim, store, ld):
+        self._check(self.lib.optmc_lsmc_paths_async(self.ctx, ctypes.byref(model),
+                                                    ctypes.byref(sim), c_void_p(store.data_ptr()),
+                                                    ld, self.stream()), "optmc_lsmc_paths_async")
+
+    def lsmc_load(self, paths_dev, n_paths, n_steps, store, ld):
+        self._check(self.lib.optmc_lsmc_load_async(self.ctx, c_void_p(paths_dev.data_ptr()),
+                                                   n_paths, n_steps, c_void_p(store.data_ptr()),
+                                                   ld, self.stream()), "optmc_lsmc_load_async")
+
+    def lsmc(self, store, ld, n_paths, n_steps, strike, is_call, r, dt, degree):
+        """Single-GPU induction: returns (n, sum, sum_sq) of discounted cashflows."""
+        cash = self.buffer("lsmc_cash", n_paths)
+        gram = self.buffer("lsmc_gram", LSMC_GRAM)
+        out = np.empty(3)
+        self._check(self.lib.optmc_lsmc(self.ctx, c_void_p(store.data_ptr()), ld, n_paths,
+                                        n_steps, float(strike), 1 if is_call else 0, float(r),
+                                        float(dt), int(degree), c_void_p(cash.data_ptr()),
+                                        c_void_p(gram.data_ptr()), out.ctypes.data_as(_dp),
+                                        self.stream()), "optmc_lsmc")
+        return out
+
+    def lsmc_distributed(self, store, ld, n_paths, n_steps, strike, is_call, r, dt, degree,
+                         all_reduce):
+        """
+        The same induction with one ``all_reduce(tensor)`` of the 24-double Gram
+        vector per exercise date and one of (n, sum, sum_sq) at the end
+        (SURVEY 8 e2).  ``all_reduce`` sums a device tensor in place across ranks.
+        """
+        import math
+
+        L, ctx, st = self.lib, self.ctx, self.stream()
+        cash = self.buffer("lsmc_cash", n_paths)
+        gram = self.buffer("lsmc_gram", LSMC_GRAM)
+        out = self.buffer("lsmc_out", 3)
+        disc = math.exp(-r * dt)
+        sp, cp, gp = (c_void_p(store.data_ptr()), c_void_p(cash.data_ptr()),
+                      c_void_p(gram.data_ptr()))
+        ic = 1 if is_call else 0
+        self._check(L.optmc_lsmc_begin_async(ctx, sp, ld, n_paths, n_steps, float(strike), ic,
+                                             cp, st), "optmc_lsmc_begin_async")
+        for i in range(n_steps - 1, 0, -1):
+            self._check(L.optmc_lsmc_gram_async(ctx, sp, ld, n_paths, i, float(strike), ic, disc,
+                                                int(degree), cp, gp, st), "optmc_lsmc_gram_async")
+            all_reduce(gram[:LSMC_GRAM])
+            self._check(L.optmc_lsmc_decide_async(ctx, sp, ld, n_paths, i, float(strike), ic,
+                                                  int(degree), gp, cp, st),
+                        "optmc_lsmc_decide_async")
+        self._check(L.optmc_lsmc_finish_async(ctx, n_paths, disc, cp, c_void_p(out.data_ptr()),
+                                              st), "optmc_lsmc_finish_async")
+        all_reduce(out[:3])
+        return out[:3].cpu().numpy()
+
+    # -- diagnostics ----------------------------------------------------------
+    def philox_raw(self, seed, n, c2=0, c3=0):
+        out = self.torch.empty(4 * n, dtype=self.torch.int32, device=self.device)
+        self._check(self.lib.optmc_philox_raw(self.ctx, int(seed), n, c2, c3,
+                                              c_void_p(out.data_ptr()), self.stream()),
+                    "optmc_philox_raw")
+        return out.cpu().numpy().view(np.uint32).reshape(n, 4)
+
+    def normals(self, seed, n, step=0):
+        out = self.torch.empty(2 * n, dtype=self.torch.float64, device=self.device)
+        self._check(self.lib.optmc_normals(self.ctx, int(seed), n, step, c_void_p(out.data_ptr()),
+                                           self.stream()), "optmc_normals")
+        return out.cpu().numpy()
+
+    def fp64_peak(self, iters=1 << 16):
+        rate, ms = c_double(), c_double()
+        self._check(self.lib.optmc_fp64_peak(self.ctx, int(iters), ctypes.byref(rate),
+                                             ctypes.byref(ms)), "optmc_fp64_peak")
+        return rate.value, ms.value
+
+
+_engines = {}
+_lock = threading.Lock()
+
+
+def get_engine(device: int | None = None) -> Engine:
+    """The process-wide engine for ``device`` (default: torch's current device)."""
+    import torch
+
+    if not torch.cuda.is_available():
+        raise EngineError("no CUDA device visible: the optpricing_b200 engine needs a B200 "
+                          "(there is no CPU fallback)")
+    idx = torch.cuda.current_device() if device is None else int(device)
+    with _lock:
+        eng = _engines.get(idx)
+        if eng is None:
+            eng = _engines[idx] = Engine(idx)
+    return eng

@@ -1,0 +1,180 @@
+// fed.cuh -- fed-draw kernels: the drop-in for the reference's 7 terminal
+// kernels (mc_kernels.py) and 7 path kernels (path_kernels.py), consuming the
+// reference's own C-order buffers.  Used for bit-level parity (<= 1e-12) and
+// for the technique's rng_mode="numpy" compatibility mode.
+//
+// Layout problem: the reference's dw[n_paths][n_steps] is path-major, so a
+// thread-per-path walk is a stride-n_steps access.  Each block stages a tile of
+// FED_P paths x FED_T steps through shared memory: global reads and writes are
+// coalesced row segments, per-thread reads come from padded shared rows.
+//
+// Jump sizes arrive as one flat buffer in the order the reference pulls them
+// from its RNG: by step, then path, then jump.  The offset of (path p, step i)
+// is base[i][block] + (exclusive prefix of counts over the block's paths at
+// step i); base comes from k_fed_block_totals + k_scan_exclusive.
+#pragma once
+#include "models.cuh"
+
+namespace optmc {
+
+constexpr int FED_P = 64;   // paths per block (= threads)
+constexpr int FED_T = 32;   // steps per tile
+constexpr int FED_LD = FED_T + 1;
+
+struct FedArgs {
+    Consts c;
+    int64_t n_paths;
+    int n_steps;
+    const double *dw1, *dw2;
+    const int64_t *counts;
+    const double *jumps;
+    int64_t n_jumps;
+    double sign;
+    int sum_mode;
+    double *terminal;
+    double *paths;          // [n_paths][n_steps+1] or null
+    int64_t *base;          // [n_steps][n_blocks] exclusive offsets (jump models)
+    int64_t n_blocks;
+};
+
+constexpr size_t fed_smem_bytes() {
+    return sizeof(double) * 2 * FED_P * FED_LD + sizeof(int) * 2 * FED_P * FED_LD;
+}
+
+// Coalesced load of a [FED_P][tile_len] tile of a row-major [n][n_steps] array.
+template <class T, class U>
+__device__ __forceinline__ void load_tile(U (*dst)[FED_LD], const T *src, int64_t row0,
+                                          int64_t n_rows, int n_steps, int t0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int rr = warp; rr < FED_P; rr += FED_P / 32) {
+        int64_t row = row0 + rr;
+        int col = t0 + lane;
+        U val = U(0);
+        if (row < n_rows && col < n_steps) val = (U)src[(size_t)row * n_steps + col];
+        dst[rr][lane] = val;
+    }
+}
+
+// Per-block, per-step jump totals: tot[i * n_blocks + b].
+__global__ void __launch_bounds__(FED_P) k_fed_block_totals(const int64_t *counts, int64_t n_paths,
+                                                            int n_steps, int64_t n_blocks,
+                                                            int64_t *tot) {
+    __shared__ int cnt[FED_P][FED_LD];
+    const int64_t row0 = (int64_t)blockIdx.x * FED_P;
+    for (int t0 = 0; t0 < n_steps; t0 += FED_T) {
+        load_tile<int64_t, int>(cnt, counts, row0, n_paths, n_steps, t0);
+        __syncthreads();
+        if (threadIdx.x < FED_T && t0 + threadIdx.x < n_steps) {
+            int64_t s = 0;
+            for (int rr = 0; rr < FED_P; ++rr) s += cnt[rr][threadIdx.x];
+            tot[(size_t)(t0 + threadIdx.x) * n_blocks + blockIdx.x] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// In-place exclusive scan of n int64 values by one block (n is small: one
+// entry per 64 paths per step).
+__global__ void __launch_bounds__(1024) k_scan_exclusive(int64_t *a, int64_t n) {
+    __shared__ int64_t sums[1024];
+    const int t = threadIdx.x;
+    const int64_t chunk = (n + 1023) / 1024;
+    const int64_t lo = min(n, (int64_t)t * chunk), hi = min(n, lo + chunk);
+    int64_t s = 0;
+    for (int64_t i = lo; i < hi; ++i) s += a[i];
+    sums[t] = s;
+    __syncthreads();
+    if (t == 0) {
+        int64_t run = 0;
+        for (int i = 0; i < 1024; ++i) {
+            int64_t v = sums[i];
+            sums[i] = run;
+            run += v;
+        }
+    }
+    __syncthreads();
+    int64_t run = sums[t];
+    for (int64_t i = lo; i < hi; ++i) {
+        int64_t v = a[i];
+        a[i] = run;
+        run += v;
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(FED_P) k_fed(const FedArgs A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double(*t1)[FED_LD] = reinterpret_cast<double(*)[FED_LD]>(smem_raw);
+    double(*t2)[FED_LD] = t1 + FED_P;
+    int(*cnt)[FED_LD] = reinterpret_cast<int(*)[FED_LD]>(t2 + FED_P);
+    int(*pre)[FED_LD] = cnt + FED_P;
+
+    constexpr bool TWO = kind_two_factor(KIND);
+    constexpr bool JUMPS = kind_jumps(KIND);
+    const Consts &c = A.c;
+    const int tid = threadIdx.x;
+    const int64_t row0 = (int64_t)blockIdx.x * FED_P;
+    const int64_t p = row0 + tid;
+    const bool live = p < A.n_paths;
+    const size_t pld = (size_t)A.n_steps + 1;
+
+    State s;
+    s.x = c.x0;
+    s.v = c.v0;
+    if (A.paths && live)
+        A.paths[(size_t)p * pld] = kind_sabr(KIND) ? c.x0 : exp(c.x0);   // path_kernels.py:28
+
+    for (int t0 = 0; t0 < A.n_steps; t0 += FED_T) {
+        const int tile_len = min(FED_T, A.n_steps - t0);
+        load_tile<double, double>(t1, A.dw1, row0, A.n_paths, A.n_steps, t0);
+        if constexpr (TWO) load_tile<double, double>(t2, A.dw2, row0, A.n_paths, A.n_steps, t0);
+        if constexpr (JUMPS) load_tile<int64_t, int>(cnt, A.counts, row0, A.n_paths, A.n_steps, t0);
+        __syncthreads();
+        if constexpr (JUMPS) {
+            if (tid < FED_T) {
+                int run = 0;
+                for (int rr = 0; rr < FED_P; ++rr) {
+                    pre[rr][tid] = run;
+                    run += cnt[rr][tid];
+                }
+            }
+            __syncthreads();
+        }
+        for (int j = 0; j < tile_len; ++j) {
+            double z1, cz = 0.0;
+            if constexpr (TWO)
+                mix_fed(KIND, A.sign * t1[tid][j], A.sign * t2[tid][j], c, z1, cz);
+            else
+                z1 = A.sign * t1[tid][j];
+            step_diffusion<KIND>(s, z1, cz, c);
+            if constexpr (JUMPS) {
+                int n = cnt[tid][j];
+                if (n > 0) {
+                    const double *jb =
+                        A.jumps + A.base[(size_t)(t0 + j) * A.n_blocks + blockIdx.x] + pre[tid][j];
+                    if (KIND != OPTMC_SABR_JUMP && A.sum_mode) {
+                        double acc = 0.0;                       // np.sum(slice), path_kernels.py:116
+                        for (int k = 0; k < n; ++k) acc += jb[k];
+                        s.x += acc;
+                    } else {
+                        for (int k = 0; k < n; ++k) apply_jump<KIND>(s, jb[k]);
+                    }
+                }
+            }
+            if (A.paths) t1[tid][j] = kind_sabr(KIND) ? s.x : exp(s.x);   // path_kernels.py:34
+        }
+        if (A.paths) {
+            __syncthreads();
+            const int lane = tid & 31, warp = tid >> 5;
+            for (int rr = warp; rr < FED_P; rr += FED_P / 32) {
+                int64_t row = row0 + rr;
+                if (row < A.n_paths && lane < tile_len)
+                    A.paths[(size_t)row * pld + 1 + t0 + lane] = t1[rr][lane];
+            }
+        }
+        __syncthreads();
+    }
+    if (A.terminal && live) A.terminal[p] = s.x;
+}
+
+}  // namespace optmc

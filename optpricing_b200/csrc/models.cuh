@@ -1,0 +1,138 @@
+// models.cuh -- per-step recurrences of the seven SDE models.
+//
+// One set of step functions serves both the fed-draw kernels (parity with the
+// numba originals to <= 1e-12) and the Philox kernels (throughput): what is
+// parity-checked is what is benchmarked.  Reference lines per function below
+// are relative to /root/reference/src/optpricing/techniques/kernels/.
+#pragma once
+#include <cmath>
+#include <cstdint>
+
+#include "../../include/optmc.h"
+#include "philox.cuh"
+
+namespace optmc {
+
+// Everything a kernel needs, precomputed once on the host in the reference's
+// own expression order (so drift/compensator constants match its doubles).
+struct Consts {
+    int kind;
+    int beta_mode;            // SABR: 0 general pow, 1 beta==1, 2 beta==0, 3 beta==0.5
+    double x0;                // log_s0, or s0 for SABR kinds        (monte_carlo.py:217-220)
+    double v0;
+    double dt, sqrt_dt;
+    double r, q;
+    // one-factor log models
+    double sigma;
+    double drift;             // (r - q - 0.5 sigma^2 - compensator) dt   (mc_kernels.py:29,104,304)
+    // Heston / Bates
+    double rqc;               // r - q - compensator
+    double rqc_dt;            // rqc * dt
+    double neg_half_dt;       // -0.5 dt
+    double kappa_theta_dt;    // kappa theta dt
+    double neg_kappa_dt;      // -kappa dt
+    double xi;                // vol_of_vol
+    // SABR
+    double alpha, beta;
+    double neg_half_alpha2_dt;
+    // correlation of the kernel itself (mc_kernels.py:59,67)
+    double rho, rho_bar;
+    // Philox mode: (z1, cz) = M (a, b) for iid N(0,1) a, b; sqrt(dt) and, for
+    // Heston/Bates, vol_of_vol are folded in (see make_consts).
+    double m11, m12, m21, m22;
+    // jumps
+    double lam_dt;            // lambda dt (per Poisson draw; x2 when two steps share a draw)
+    double mu_j, sigma_j;
+    double p_up, inv_eta1, inv_eta2;
+    uint32_t p_up_bits;
+};
+
+__host__ __device__ constexpr bool kind_two_factor(int k) {
+    return k == OPTMC_HESTON || k == OPTMC_BATES || k == OPTMC_SABR || k == OPTMC_SABR_JUMP;
+}
+__host__ __device__ constexpr bool kind_jumps(int k) {
+    return k == OPTMC_MERTON || k == OPTMC_BATES || k == OPTMC_SABR_JUMP || k == OPTMC_KOU;
+}
+__host__ __device__ constexpr bool kind_sabr(int k) {
+    return k == OPTMC_SABR || k == OPTMC_SABR_JUMP;
+}
+
+// max(a, 0) on the integer pipe (keeps the fp64 pipe for arithmetic).
+// -0.0 and negatives -> +0.0.
+__device__ __forceinline__ double relu64(double a) {
+    int hi = __double2hiint(a), lo = __double2loint(a);
+    int keep = ~(hi >> 31);
+    return __hiloint2double(hi & keep, lo & keep);
+}
+
+struct State {
+    double x;  // log S (S for SABR kinds)
+    double v;  // variance (Heston/Bates) or vol (SABR); unused otherwise
+};
+
+// bsm_kernel mc_kernels.py:30-32; merton :105-106; kou :306-307 (diffusion part)
+__device__ __forceinline__ void step_one_factor(State &s, double dw, const Consts &c) {
+    s.x += fma(c.sigma, dw, c.drift);
+}
+
+// heston_kernel mc_kernels.py:62-77, bates_kernel :151-164.
+// z1 = dw1; czx = vol_of_vol * (rho*dw1 + rho_bar*dw2).
+__device__ __forceinline__ void step_heston(State &s, double z1, double czx, const Consts &c) {
+    double vp = relu64(s.v);                       // v_pos = max(v, 0)
+    double sq = sqrt_nonneg(vp);                   // v_sqrt
+    s.x += fma(sq, z1, fma(vp, c.neg_half_dt, c.rqc_dt));
+    double vn = fma(sq, czx, fma(vp, c.neg_kappa_dt, s.v + c.kappa_theta_dt));
+    s.v = relu64(vn);                              // v = max(v, 0)
+}
+
+__device__ __forceinline__ double sabr_pow(double s_pos, const Consts &c) {
+    switch (c.beta_mode) {
+        case 1: return s_pos;
+        case 2: return 1.0;
+        case 3: return sqrt_nonneg(s_pos);
+        default: return pow(s_pos, c.beta);
+    }
+}
+
+// sabr_kernel mc_kernels.py:204-216, sabr_jump_kernel :251-258.
+// z1 = dw1; cz = rho*dw1 + rho_bar*dw2.
+__device__ __forceinline__ void step_sabr(State &s, double z1, double cz, const Consts &c) {
+    double s_pos = fmax(s.x, 1e-8);
+    double v_pos = relu64(s.v);
+    s.x += fma(v_pos * sabr_pow(s_pos, c), z1, c.rqc_dt * s_pos);
+    s.v = s.v * exp(fma(c.alpha, cz, c.neg_half_alpha2_dt));
+}
+
+// Fed mode: the kernel's own correlation step applied to the given increments.
+__device__ __forceinline__ void mix_fed(int kind, double dw1, double dw2, const Consts &c,
+                                        double &z1, double &cz) {
+    z1 = dw1;
+    cz = fma(c.rho, dw1, c.rho_bar * dw2);          // mc_kernels.py:67
+    if (kind == OPTMC_HESTON || kind == OPTMC_BATES) cz *= c.xi;
+}
+
+template <int KIND>
+__device__ __forceinline__ void step_diffusion(State &s, double z1, double cz, const Consts &c) {
+    if constexpr (KIND == OPTMC_HESTON || KIND == OPTMC_BATES)
+        step_heston(s, z1, cz, c);
+    else if constexpr (kind_sabr(KIND))
+        step_sabr(s, z1, cz, c);
+    else
+        step_one_factor(s, z1, c);
+}
+
+// Apply one jump of size J (Merton/Bates/Kou: additive in log space,
+// mc_kernels.py:115,174,323; SABR-jump: multiplicative on S, :274).
+template <int KIND>
+__device__ __forceinline__ void apply_jump(State &s, double J) {
+    if constexpr (KIND == OPTMC_SABR_JUMP)
+        s.x *= exp(J);
+    else
+        s.x += J;
+}
+
+__device__ __forceinline__ double terminal_spot(int kind, const State &s) {
+    return kind_sabr(kind) ? s.x : exp(s.x);        // monte_carlo.py:257
+}
+
+}  // namespace optmc

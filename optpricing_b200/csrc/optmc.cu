@@ -1,0 +1,697 @@
+// optmc.cu -- C ABI of liboptmc.so (see include/optmc.h for the contract and
+// the reference lines each entry point replaces).  Host side only: argument
+// checks, constant folding in the reference's expression order, launch
+// geometry.  All arithmetic on paths happens in the kernels included below.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/optmc.h"
+#include "european.cuh"
+#include "fed.cuh"
+#include "lsmc.cuh"
+
+using namespace optmc;
+
+struct optmc_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int normals_impl = 1;       // 0: CUDA math library, 1: hand-written (philox.cuh)
+    int euro_blocks_per_sm = 0; // 0: occupancy API decides
+    int64_t launches = 0;
+    unsigned char *scratch = nullptr;  // device
+    size_t scratch_bytes = 0;
+    double *moments_dev = nullptr;     // SWEEP_MAX * OPTMC_NMOM
+    double *moments_host = nullptr;    // pinned
+    unsigned int *ticket = nullptr;    // device, zero between launches
+    std::string err;
+};
+
+static std::string g_create_err;
+
+#define CK(call)                                                                        \
+    do {                                                                                \
+        cudaError_t e_ = (call);                                                        \
+        if (e_ != cudaSuccess) {                                                        \
+            char b_[512];                                                               \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                     __FILE__, __LINE__);                                               \
+            ctx->err = b_;                                                              \
+            return -1;                                                                  \
+        }                                                                               \
+    } while (0)
+
+#define FAIL(msg)          \
+    do {                   \
+        ctx->err = (msg);  \
+        return -2;         \
+    } while (0)
+
+static constexpr size_t SCRATCH_BYTES = 8u << 20;
+static constexpr int MAX_GRID = 148 * 16 * 2;   // partial rows the scratch is carved for
+
+extern "C" int optmc_version(void) { return 100; }
+
+extern "C" const char *optmc_last_error(const optmc_ctx *ctx) {
+    return ctx ? ctx->err.c_str() : g_create_err.c_str();
+}
+
+extern "C" int64_t optmc_launch_count(const optmc_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int optmc_ctx_create(int device, optmc_ctx **out) {
+    if (!out) return -2;
+    *out = nullptr;
+    optmc_ctx *ctx = new optmc_ctx();
+    auto fail = [&](cudaError_t e, const char *what) {
+        g_create_err = std::string(what) + ": " + cudaGetErrorString(e);
+        delete ctx;
+        return -1;
+    };
+    cudaError_t e;
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return fail(e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return fail(e, "cudaGetDeviceProperties");
+    if (prop.major != 10) {
+        g_create_err = "liboptmc is built for sm_100a (B200) only; device is sm_" +
+                       std::to_string(prop.major) + std::to_string(prop.minor);
+        delete ctx;
+        return -3;
+    }
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->scratch_bytes = SCRATCH_BYTES;
+    if ((e = cudaMalloc(&ctx->scratch, SCRATCH_BYTES)) != cudaSuccess) return fail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&ctx->moments_dev, sizeof(double) * SWEEP_MAX * OPTMC_NMOM)) != cudaSuccess)
+        return fail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&ctx->ticket, 64)) != cudaSuccess) return fail(e, "cudaMalloc");
+    if ((e = cudaMemset(ctx->ticket, 0, 64)) != cudaSuccess) return fail(e, "cudaMemset");
+    if ((e = cudaHostAlloc(&ctx->moments_host, sizeof(double) * SWEEP_MAX * OPTMC_NMOM,
+                           cudaHostAllocDefault)) != cudaSuccess)
+        return fail(e, "cudaHostAlloc");
+    if ((e = cudaFuncSetAttribute(k_fed<OPTMC_BSM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)fed_smem_bytes())) != cudaSuccess)
+        return fail(e, "cudaFuncSetAttribute");
+#define FED_ATTR(K)                                                                      \
+    cudaFuncSetAttribute(k_fed<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                         (int)fed_smem_bytes())
+    FED_ATTR(OPTMC_HESTON); FED_ATTR(OPTMC_MERTON); FED_ATTR(OPTMC_BATES);
+    FED_ATTR(OPTMC_SABR); FED_ATTR(OPTMC_SABR_JUMP); FED_ATTR(OPTMC_KOU);
+#undef FED_ATTR
+    *out = ctx;
+    return 0;
+}
+
+extern "C" void optmc_ctx_destroy(optmc_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->scratch);
+    cudaFree(ctx->moments_dev);
+    cudaFree(ctx->ticket);
+    cudaFreeHost(ctx->moments_host);
+    delete ctx;
+}
+
+extern "C" int optmc_set_int(optmc_ctx *ctx, const char *key, int64_t value) {
+    if (!ctx || !key) return -2;
+    if (!strcmp(key, "normals_impl")) {
+        if (value != 0 && value != 1) FAIL("normals_impl must be 0 or 1");
+        ctx->normals_impl = (int)value;
+    } else if (!strcmp(key, "euro_blocks_per_sm")) {
+        if (value < 0 || value > 16) FAIL("euro_blocks_per_sm out of range");
+        ctx->euro_blocks_per_sm = (int)value;
+    } else {
+        FAIL(std::string("unknown option ") + key);
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// constants, in the reference's expression order
+// ---------------------------------------------------------------------------
+static int make_consts(optmc_ctx *ctx, const optmc_model *m, double x0, double dt, int correlation,
+                       Consts *out) {
+    Consts c;
+    memset(&c, 0, sizeof c);
+    if (m->kind < OPTMC_BSM || m->kind > OPTMC_KOU) FAIL("unknown model kind");
+    if (!(dt > 0.0)) FAIL("dt must be positive");
+    c.kind = m->kind;
+    c.x0 = x0;
+    c.v0 = m->v0;
+    c.dt = dt;
+    c.sqrt_dt = std::sqrt(dt);
+    c.r = m->r;
+    c.q = m->q;
+    double comp = 0.0;
+    if (m->kind == OPTMC_MERTON || m->kind == OPTMC_BATES || m->kind == OPTMC_SABR_JUMP)
+        comp = m->lambda * (std::exp(m->mu_j + 0.5 * m->sigma_j * m->sigma_j) - 1);  // mc_kernels.py:103
+    if (m->kind == OPTMC_KOU)
+        comp = m->lambda * ((m->p_up * m->eta1 / (m->eta1 - 1)) +
+                            ((1 - m->p_up) * m->eta2 / (m->eta2 + 1)) - 1);          // :301-303
+    c.sigma = m->sigma;
+    c.drift = (m->r - m->q - 0.5 * m->sigma * m->sigma - comp) * dt;                 // :29,104,304
+    c.rqc = m->r - m->q - comp;
+    c.rqc_dt = c.rqc * dt;
+    c.neg_half_dt = -0.5 * dt;
+    c.kappa_theta_dt = m->kappa * m->theta * dt;
+    c.neg_kappa_dt = -m->kappa * dt;
+    c.xi = m->vol_of_vol;
+    c.alpha = m->alpha;
+    c.beta = m->beta;
+    c.neg_half_alpha2_dt = -0.5 * m->alpha * m->alpha * dt;
+    c.beta_mode = m->beta == 1.0 ? 1 : m->beta == 0.0 ? 2 : m->beta == 0.5 ? 3 : 0;
+    c.rho = m->rho;
+    c.rho_bar = std::sqrt(1 - m->rho * m->rho);                                      // :59
+    const double sd = c.sqrt_dt, rho = c.rho, rb = c.rho_bar;
+    if (correlation == OPTMC_CORR_REFERENCE_EUROPEAN) {
+        // dw1 = rho a + rho_bar b, dw2 = a (monte_carlo.py:230-231); kernel: rho dw1 + rho_bar dw2
+        c.m11 = sd * rho;
+        c.m12 = sd * rb;
+        c.m21 = sd * (rho * rho + rb);
+        c.m22 = sd * rho * rb;
+    } else if (correlation == OPTMC_CORR_INDEPENDENT_DRAWS) {
+        c.m11 = sd;
+        c.m12 = 0.0;
+        c.m21 = sd * rho;
+        c.m22 = sd * rb;
+    } else {
+        FAIL("unknown correlation mode");
+    }
+    if (m->kind == OPTMC_HESTON || m->kind == OPTMC_BATES) {
+        c.m21 *= c.xi;
+        c.m22 *= c.xi;
+    }
+    c.lam_dt = m->lambda * dt;
+    c.mu_j = m->mu_j;
+    c.sigma_j = m->sigma_j;
+    c.p_up = m->p_up;
+    if (m->kind == OPTMC_KOU) {
+        c.inv_eta1 = 1.0 / m->eta1;
+        c.inv_eta2 = 1.0 / m->eta2;
+        double pb = std::floor(m->p_up * 4294967296.0);
+        c.p_up_bits = (uint32_t)std::min(std::max(pb, 0.0), 4294967295.0);
+    }
+    *out = c;
+    return 0;
+}
+
+static void poisson_consts(EuroArgs &A) {
+    for (int two = 0; two < 2; ++two) {
+        double mu = A.c.lam_dt * (two + 1);
+        double p0 = std::exp(-mu);
+        A.pois_mu[two] = mu;
+        A.pois_p0[two] = p0;
+        A.pois_p0_bits[two] = (uint32_t)std::min(std::floor(p0 * 4294967296.0), 4294967295.0);
+    }
+}
+
+static int check_sim(optmc_ctx *ctx, const optmc_sim *s) {
+    if (!(s->s0 > 0.0)) FAIL("s0 must be positive");
+    if (!(s->maturity > 0.0)) FAIL("maturity must be positive");
+    if (s->n_steps < 1) FAIL("n_steps must be >= 1");
+    if (s->n_local < 0 || s->draw_offset < 0 || s->n_draws < 0) FAIL("negative draw counts");
+    if (s->draw_offset + s->n_local > s->n_draws) FAIL("draw range exceeds n_draws");
+    return 0;
+}
+
+template <class K>
+static int euro_grid(optmc_ctx *ctx, K kernel, int64_t n_local) {
+    int per_sm = ctx->euro_blocks_per_sm;
+    if (per_sm <= 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, EURO_THREADS, 0) !=
+                cudaSuccess || per_sm < 1)
+            per_sm = 1;
+    }
+    int64_t need = (n_local + EURO_THREADS - 1) / EURO_THREADS;
+    int64_t cap = (int64_t)ctx->sm_count * per_sm;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(std::min(need, cap), MAX_GRID));
+}
+
+// KIND x ANTI x NIMPL dispatch
+#define DISPATCH_KIND(KIND_VAR, MACRO)                         \
+    switch (KIND_VAR) {                                        \
+        case OPTMC_BSM: MACRO(OPTMC_BSM); break;               \
+        case OPTMC_HESTON: MACRO(OPTMC_HESTON); break;         \
+        case OPTMC_MERTON: MACRO(OPTMC_MERTON); break;         \
+        case OPTMC_BATES: MACRO(OPTMC_BATES); break;           \
+        case OPTMC_SABR: MACRO(OPTMC_SABR); break;             \
+        case OPTMC_SABR_JUMP: MACRO(OPTMC_SABR_JUMP); break;   \
+        case OPTMC_KOU: MACRO(OPTMC_KOU); break;               \
+        default: FAIL("unknown model kind");                   \
+    }
+
+template <int KIND, bool ANTI, int NIMPL>
+static int launch_euro_t(optmc_ctx *ctx, EuroArgs &A, cudaStream_t st, int *grid_out) {
+    auto kern = k_european<KIND, ANTI, NIMPL>;
+    int grid = euro_grid(ctx, kern, A.n_local);
+    kern<<<grid, EURO_THREADS, 0, st>>>(A);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    *grid_out = grid;
+    return 0;
+}
+
+template <int KIND>
+static int launch_euro_k(optmc_ctx *ctx, EuroArgs &A, bool anti, cudaStream_t st, int *grid) {
+    if (ctx->normals_impl == 0)
+        return anti ? launch_euro_t<KIND, true, 0>(ctx, A, st, grid)
+                    : launch_euro_t<KIND, false, 0>(ctx, A, st, grid);
+    return anti ? launch_euro_t<KIND, true, 1>(ctx, A, st, grid)
+                : launch_euro_t<KIND, false, 1>(ctx, A, st, grid);
+}
+
+static int fill_euro_args(optmc_ctx *ctx, const optmc_model *model, const optmc_sim *sim,
+                          EuroArgs *A) {
+    if (!model || !sim) FAIL("null model or sim");
+    int rc = check_sim(ctx, sim);
+    if (rc) return rc;
+    double dt = sim->maturity / sim->n_steps;                                 // monte_carlo.py:209
+    double x0 = kind_sabr(model->kind) ? sim->s0 : std::log(sim->s0);          // :217-220
+    memset(A, 0, sizeof *A);
+    rc = make_consts(ctx, model, x0, dt, sim->correlation, &A->c);
+    if (rc) return rc;
+    poisson_consts(*A);
+    A->seed = sim->seed;
+    A->draw_offset = sim->draw_offset;
+    A->n_local = sim->n_local;
+    A->n_steps = sim->n_steps;
+    return 0;
+}
+
+static int sweep_launch(optmc_ctx *ctx, const double *terminal_dev, int64_t n_local, int antithetic,
+                        int n_contracts, const double *strikes, const int32_t *is_call,
+                        double *moments_dev, cudaStream_t st) {
+    if (n_contracts < 1) FAIL("n_contracts must be >= 1");
+    if (!terminal_dev || !strikes || !is_call || !moments_dev) FAIL("null pointer");
+    double *partials = reinterpret_cast<double *>(ctx->scratch);
+    const int gx = (int)std::max<int64_t>(
+        1, std::min<int64_t>((n_local + 255) / 256, (int64_t)ctx->sm_count * 2));
+    for (int c0 = 0; c0 < n_contracts; c0 += SWEEP_MAX) {
+        SweepArgs S;
+        memset(&S, 0, sizeof S);
+        S.terminal = terminal_dev;
+        S.n_local = n_local;
+        S.antithetic = antithetic;
+        S.n_contracts = std::min(SWEEP_MAX, n_contracts - c0);
+        for (int k = 0; k < S.n_contracts; ++k) {
+            S.strikes[k] = strikes[c0 + k];
+            S.is_call[k] = is_call[c0 + k] ? 1 : 0;
+        }
+        S.partials = partials;
+        k_payoff_sweep<<<dim3(gx, S.n_contracts), 256, 0, st>>>(S);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        k_finish_sweep<<<S.n_contracts, 256, 0, st>>>(partials, gx, (double)n_local,
+                                                       moments_dev + (size_t)c0 * OPTMC_NMOM);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    return 0;
+}
+
+extern "C" int optmc_european_async(optmc_ctx *ctx, const optmc_model *model, const optmc_sim *sim,
+                                    int32_t n_contracts, const double *strikes,
+                                    const int32_t *is_call, double *moments_dev,
+                                    double *terminal_dev, void *stream) {
+    if (!ctx) return -2;
+    CK(cudaSetDevice(ctx->device));
+    if (n_contracts < 1 || !strikes || !is_call || !moments_dev) FAIL("bad contract arguments");
+    if (n_contracts > 1 && !terminal_dev)
+        FAIL("terminal_dev is required when n_contracts > 1 (strike sweep)");
+    EuroArgs A;
+    int rc = fill_euro_args(ctx, model, sim, &A);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    A.strike = strikes[0];
+    A.is_call = is_call[0] ? 1 : 0;
+    A.partials = reinterpret_cast<double *>(ctx->scratch);
+    A.terminal = terminal_dev;
+    int grid = 0;
+    const bool anti = sim->antithetic != 0;
+    if (sim->n_local > 0) {
+#define GO(K) rc = launch_euro_k<K>(ctx, A, anti, st, &grid)
+        DISPATCH_KIND(model->kind, GO)
+#undef GO
+        if (rc) return rc;
+    }
+    if (n_contracts == 1) {
+        k_finish_moments<<<1, 256, 0, st>>>(A.partials, grid, (double)sim->n_local, moments_dev);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        return 0;
+    }
+    return sweep_launch(ctx, terminal_dev, sim->n_local, anti ? 1 : 0, n_contracts, strikes,
+                        is_call, moments_dev, st);
+}
+
+extern "C" int optmc_european(optmc_ctx *ctx, const optmc_model *model, const optmc_sim *sim,
+                              int32_t n_contracts, const double *strikes, const int32_t *is_call,
+                              double *moments_host, double *terminal_dev, void *stream) {
+    if (!ctx) return -2;
+    if (!moments_host) FAIL("moments_host is null");
+    if (n_contracts > SWEEP_MAX) FAIL("optmc_european handles at most 64 contracts per call");
+    int rc = optmc_european_async(ctx, model, sim, n_contracts, strikes, is_call, ctx->moments_dev,
+                                  terminal_dev, stream);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t bytes = sizeof(double) * OPTMC_NMOM * (size_t)n_contracts;
+    CK(cudaMemcpyAsync(ctx->moments_host, ctx->moments_dev, bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(moments_host, ctx->moments_host, bytes);
+    return 0;
+}
+
+extern "C" int optmc_payoff_sweep_async(optmc_ctx *ctx, const double *terminal_dev, int64_t n_local,
+                                        int32_t antithetic, int32_t n_contracts,
+                                        const double *strikes, const int32_t *is_call,
+                                        double *moments_dev, void *stream) {
+    if (!ctx) return -2;
+    CK(cudaSetDevice(ctx->device));
+    return sweep_launch(ctx, terminal_dev, n_local, antithetic, n_contracts, strikes, is_call,
+                        moments_dev, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------
+// fed-draw kernels
+// ---------------------------------------------------------------------------
+extern "C" int64_t optmc_fed_workspace_bytes(int32_t kind, int64_t n_paths, int32_t n_steps) {
+    if (!kind_jumps(kind) || n_paths <= 0 || n_steps <= 0) return 8;
+    int64_t n_blocks = (n_paths + FED_P - 1) / FED_P;
+    return n_blocks * (int64_t)n_steps * (int64_t)sizeof(int64_t);
+}
+
+extern "C" int optmc_fed_async(optmc_ctx *ctx, const optmc_model *model, double x0, double dt,
+                               int64_t n_paths, int32_t n_steps, const double *dw1_dev,
+                               const double *dw2_dev, const int64_t *counts_dev,
+                               const double *jumps_dev, int64_t n_jumps, double sign,
+                               int32_t path_sum_mode, double *terminal_dev, double *paths_dev,
+                               void *workspace_dev, int64_t workspace_bytes, void *stream) {
+    if (!ctx) return -2;
+    CK(cudaSetDevice(ctx->device));
+    if (!model) FAIL("null model");
+    if (n_paths < 0 || n_steps < 1) FAIL("bad n_paths / n_steps");
+    if (!dw1_dev) FAIL("dw1_dev is null");
+    if (kind_two_factor(model->kind) && !dw2_dev) FAIL("dw2_dev is required for two-factor models");
+    if (kind_jumps(model->kind) && !counts_dev) FAIL("counts_dev is required for jump models");
+    if (kind_jumps(model->kind) && n_jumps > 0 && !jumps_dev) FAIL("jumps_dev is null");
+    if (!terminal_dev && !paths_dev) FAIL("no output requested");
+    if (n_paths == 0) return 0;
+    FedArgs A;
+    memset(&A, 0, sizeof A);
+    int rc = make_consts(ctx, model, x0, dt, OPTMC_CORR_INDEPENDENT_DRAWS, &A.c);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    A.n_paths = n_paths;
+    A.n_steps = n_steps;
+    A.dw1 = dw1_dev;
+    A.dw2 = dw2_dev;
+    A.counts = counts_dev;
+    A.jumps = jumps_dev;
+    A.n_jumps = n_jumps;
+    A.sign = sign;
+    A.sum_mode = path_sum_mode;
+    A.terminal = terminal_dev;
+    A.paths = paths_dev;
+    A.n_blocks = (n_paths + FED_P - 1) / FED_P;
+    if (A.n_blocks > 0x7fffffffLL) FAIL("too many paths for one fed call");
+    if (kind_jumps(model->kind)) {
+        int64_t need = optmc_fed_workspace_bytes(model->kind, n_paths, n_steps);
+        if (!workspace_dev || workspace_bytes < need) FAIL("fed workspace too small");
+        A.base = reinterpret_cast<int64_t *>(workspace_dev);
+        k_fed_block_totals<<<(unsigned)A.n_blocks, FED_P, 0, st>>>(counts_dev, n_paths, n_steps,
+                                                                   A.n_blocks, A.base);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        k_scan_exclusive<<<1, 1024, 0, st>>>(A.base, A.n_blocks * (int64_t)n_steps);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+#define GO(K) k_fed<K><<<(unsigned)A.n_blocks, FED_P, fed_smem_bytes(), st>>>(A)
+    DISPATCH_KIND(model->kind, GO)
+#undef GO
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Longstaff-Schwartz
+// ---------------------------------------------------------------------------
+template <int KIND, bool ANTI, int NIMPL>
+static int launch_paths_t(optmc_ctx *ctx, EuroArgs &A, double *store, int64_t ld, cudaStream_t st) {
+    auto kern = k_lsmc_paths<KIND, ANTI, NIMPL>;
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EURO_THREADS, 0) != cudaSuccess ||
+        per_sm < 1)
+        per_sm = 1;
+    int64_t need = (A.n_local + EURO_THREADS - 1) / EURO_THREADS;
+    int grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)ctx->sm_count * per_sm));
+    kern<<<grid, EURO_THREADS, 0, st>>>(A, store, ld);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+template <int KIND>
+static int launch_paths_k(optmc_ctx *ctx, EuroArgs &A, bool anti, double *store, int64_t ld,
+                          cudaStream_t st) {
+    if (ctx->normals_impl == 0)
+        return anti ? launch_paths_t<KIND, true, 0>(ctx, A, store, ld, st)
+                    : launch_paths_t<KIND, false, 0>(ctx, A, store, ld, st);
+    return anti ? launch_paths_t<KIND, true, 1>(ctx, A, store, ld, st)
+                : launch_paths_t<KIND, false, 1>(ctx, A, store, ld, st);
+}
+
+extern "C" int optmc_lsmc_paths_async(optmc_ctx *ctx, const optmc_model *model,
+                                      const optmc_sim *sim, double *store_dev, int64_t ld,
+                                      void *stream) {
+    if (!ctx) return -2;
+    CK(cudaSetDevice(ctx->device));
+    if (!store_dev) FAIL("store_dev is null");
+    EuroArgs A;
+    int rc = fill_euro_args(ctx, model, sim, &A);
+    if (rc) return rc;
+    const bool anti = sim->antithetic != 0;
+    if (ld < sim->n_local * (anti ? 2 : 1)) FAIL("ld smaller than the local path count");
+    if (sim->n_local == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+#define GO(K) rc = launch_paths_k<K>(ctx, A, anti, store_dev, ld, st)
+    DISPATCH_KIND(model->kind, GO)
+#undef GO
+    return rc;
+}
+
+extern "C" int optmc_lsmc_load_async(optmc_ctx *ctx, const double *paths_dev, int64_t n_paths,
+                                     int32_t n_steps, double *store_dev, int64_t ld, void *stream) {
+    if (!ctx) return -2;
+    CK(cudaSetDevice(ctx->device));
+    if (!paths_dev || !store_dev) FAIL("null pointer");
+    if (n_paths < 1 || n_steps < 1 || ld < n_paths) FAIL("bad shape");
+    dim3 grid((unsigned)((n_paths + 31) / 32), (unsigned)((n_steps + 31) / 32));
+    k_lsmc_load<<<grid, 256, 0, (cudaStream_t)stream>>>(paths_dev, n_paths, n_steps, store_dev, ld);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int lsmc_grid(const optmc_ctx *ctx, int64_t n) {
+    int64_t need = (n + LSMC_THREADS - 1) / LSMC_THREADS;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)ctx->sm_count * 8));
+}
+
+extern "C" int optmc_lsmc_begin_async(optmc_ctx *ctx, const double *store_dev, int64_t ld,
+                                      int64_t n_paths, int32_t n_steps, double strike,
+                                      int32_t is_call, double *cashflow_dev, void *stream) {
+    if (!ctx) return -2;
+    CK(cudaSetDevice(ctx->device));
+    if (!store_dev || !cashflow_dev) FAIL("null pointer");
+    if (n_paths < 1 || n_steps < 1 || ld < n_paths) FAIL("bad shape");
+    k_lsmc_begin<<<lsmc_grid(ctx, n_paths), LSMC_THREADS, 0, (cudaStream_t)stream>>>(
+        store_dev + (size_t)(n_steps - 1) * ld, n_paths, strike, is_call, cashflow_dev);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int optmc_lsmc_gram_async(optmc_ctx *ctx, const double *store_dev, int64_t ld,
+                                     int64_t n_paths, int32_t date, double strike, int32_t is_call,
+                                     double discount, int32_t degree, double *cashflow_dev,
+                                     double *gram_dev, void *stream) {
+    if (!ctx) return -2;
+    CK(cudaSetDevice(ctx->device));
+    if (!store_dev || !cashflow_dev || !gram_dev) FAIL("null pointer");
+    if (degree < 1 || degree > OPTMC_LSMC_MAX_DEGREE) FAIL("degree must be in 1..7");
+    if (date < 1 || n_paths < 1 || ld < n_paths) FAIL("bad shape");
+    const double *row = store_dev + (size_t)(date - 1) * ld;
+    double *partials = reinterpret_cast<double *>(ctx->scratch);
+    int grid = lsmc_grid(ctx, n_paths);
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemsetAsync(gram_dev, 0, sizeof(double) * OPTMC_LSMC_GRAM, st));
+#define GRAM(D)                                                                               \
+    case D:                                                                                   \
+        k_lsmc_gram<D><<<grid, LSMC_THREADS, 0, st>>>(row, n_paths, strike, 1.0 / strike,     \
+                                                      is_call, discount, cashflow_dev,        \
+                                                      partials, ctx->ticket, gram_dev);       \
+        break;
+    switch (degree) { GRAM(1) GRAM(2) GRAM(3) GRAM(4) GRAM(5) GRAM(6) GRAM(7) }
+#undef GRAM
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int optmc_lsmc_decide_async(optmc_ctx *ctx, const double *store_dev, int64_t ld,
+                                       int64_t n_paths, int32_t date, double strike,
+                                       int32_t is_call, int32_t degree, const double *gram_dev,
+                                       double *cashflow_dev, void *stream) {
+    if (!ctx) return -2;
+    CK(cudaSetDevice(ctx->device));
+    if (!store_dev || !cashflow_dev || !gram_dev) FAIL("null pointer");
+    if (degree < 1 || degree > OPTMC_LSMC_MAX_DEGREE) FAIL("degree must be in 1..7");
+    if (date < 1 || n_paths < 1 || ld < n_paths) FAIL("bad shape");
+    const double *row = store_dev + (size_t)(date - 1) * ld;
+    k_lsmc_decide<<<lsmc_grid(ctx, n_paths), LSMC_THREADS, 0, (cudaStream_t)stream>>>(
+        row, n_paths, strike, 1.0 / strike, is_call, degree, gram_dev, cashflow_dev);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int optmc_lsmc_finish_async(optmc_ctx *ctx, int64_t n_paths, double discount,
+                                       const double *cashflow_dev, double *out_dev, void *stream) {
+    if (!ctx) return -2;
+    CK(cudaSetDevice(ctx->device));
+    if (!cashflow_dev || !out_dev || n_paths < 1) FAIL("bad arguments");
+    double *partials = reinterpret_cast<double *>(ctx->scratch);
+    int grid = lsmc_grid(ctx, n_paths);
+    cudaStream_t st = (cudaStream_t)stream;
+    k_lsmc_finish<<<grid, LSMC_THREADS, 0, st>>>(cashflow_dev, n_paths, discount, partials);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    k_lsmc_finish2<<<1, 256, 0, st>>>(partials, grid, (double)n_paths, out_dev);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int optmc_lsmc(optmc_ctx *ctx, const double *store_dev, int64_t ld, int64_t n_paths,
+                          int32_t n_steps, double strike, int32_t is_call, double r, double dt,
+                          int32_t degree, double *cashflow_dev, double *gram_dev, double *out_host,
+                          void *stream) {
+    if (!ctx) return -2;
+    if (!out_host) FAIL("out_host is null");
+    const double disc = std::exp(-r * dt);                       // american_mc_kernels.py:54
+    int rc = optmc_lsmc_begin_async(ctx, store_dev, ld, n_paths, n_steps, strike, is_call,
+                                    cashflow_dev, stream);
+    if (rc) return rc;
+    for (int i = n_steps - 1; i >= 1; --i) {                     // :53
+        rc = optmc_lsmc_gram_async(ctx, store_dev, ld, n_paths, i, strike, is_call, disc, degree,
+                                   cashflow_dev, gram_dev, stream);
+        if (rc) return rc;
+        rc = optmc_lsmc_decide_async(ctx, store_dev, ld, n_paths, i, strike, is_call, degree,
+                                     gram_dev, cashflow_dev, stream);
+        if (rc) return rc;
+    }
+    rc = optmc_lsmc_finish_async(ctx, n_paths, disc, cashflow_dev, ctx->moments_dev, stream);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(ctx->moments_host, ctx->moments_dev, 3 * sizeof(double),
+                       cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(out_host, ctx->moments_host, 3 * sizeof(double));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// diagnostics
+// ---------------------------------------------------------------------------
+__global__ void k_philox_raw(uint64_t seed, int64_t n, uint32_t c2, uint32_t c3, uint32_t *out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 w = philox_draw(seed, (uint64_t)i, c2, c3);
+    reinterpret_cast<uint4 *>(out)[i] = w;
+}
+
+template <int NIMPL>
+__global__ void k_normals(uint64_t seed, int64_t n, int step, double *out) {
+    __shared__ LogTable tab;
+    if constexpr (NIMPL != 0) {
+        fill_log_table(&tab);
+        __syncthreads();
+    }
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 w = philox_draw(seed, (uint64_t)i, (uint32_t)step, 0u);
+    double a, b;
+    normal_pair<NIMPL>(w.x, w.y, w.z, a, b, &tab);
+    out[2 * i] = a;
+    out[2 * i + 1] = b;
+}
+
+__global__ void __launch_bounds__(256) k_fp64_peak(int64_t iters, double seed, double *sink) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3;
+    double a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 0.999999, c = 1e-7;
+    for (int64_t i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 12345.678) sink[0] = s;   // never true; keeps the loop alive
+}
+
+extern "C" int optmc_philox_raw(optmc_ctx *ctx, uint64_t seed, int64_t n, uint32_t c2, uint32_t c3,
+                                uint32_t *out_dev, void *stream) {
+    if (!ctx) return -2;
+    CK(cudaSetDevice(ctx->device));
+    if (n < 1 || !out_dev) FAIL("bad arguments");
+    k_philox_raw<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(seed, n, c2, c3,
+                                                                                out_dev);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int optmc_normals(optmc_ctx *ctx, uint64_t seed, int64_t n, int32_t step,
+                             double *out_dev, void *stream) {
+    if (!ctx) return -2;
+    CK(cudaSetDevice(ctx->device));
+    if (n < 1 || !out_dev) FAIL("bad arguments");
+    unsigned grid = (unsigned)((n + 255) / 256);
+    if (ctx->normals_impl == 0)
+        k_normals<0><<<grid, 256, 0, (cudaStream_t)stream>>>(seed, n, step, out_dev);
+    else
+        k_normals<1><<<grid, 256, 0, (cudaStream_t)stream>>>(seed, n, step, out_dev);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int optmc_fp64_peak(optmc_ctx *ctx, int64_t iters, double *fma_per_sec,
+                               double *elapsed_ms) {
+    if (!ctx) return -2;
+    CK(cudaSetDevice(ctx->device));
+    if (iters < 1 || !fma_per_sec) FAIL("bad arguments");
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const int grid = ctx->sm_count * 8;
+    double *sink = reinterpret_cast<double *>(ctx->scratch);
+    k_fp64_peak<<<grid, 256>>>(std::max<int64_t>(iters / 16, 1), 1.0, sink);   // warm-up
+    CK(cudaEventRecord(e0));
+    k_fp64_peak<<<grid, 256>>>(iters, 1.0, sink);
+    CK(cudaEventRecord(e1));
+    ctx->launches += 2;
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *fma_per_sec = (double)grid * 256.0 * 8.0 * (double)iters / (ms * 1e-3);
+    if (elapsed_ms) *elapsed_ms = ms;
+    return 0;
+}

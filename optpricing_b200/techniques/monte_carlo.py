@@ -1,0 +1,263 @@
+"""
+MonteCarloTechnique on the B200 engine: a drop-in for
+/root/reference/src/optpricing/techniques/monte_carlo.py.
+
+Public surface, defaults and error messages follow the reference
+(monte_carlo.py:36-116); what changed is underneath:
+
+* ``rng_mode="philox"`` (default).  ``price`` makes ONE call into liboptmc.so:
+  Philox normals / Poisson / jump sizes are generated in registers, the payoff
+  moments come back as 48 bytes.  No increments are materialised, so 2^24 x 252
+  runs in milliseconds where the reference cannot even allocate its arrays.  The
+  Philox key is one draw from ``self.rng``, hence ``seed=`` reproducibility,
+  stream advance per ``price`` call and common random numbers under ``crn`` all
+  behave as in the reference (greek_mixin.py:63-64 keys CRN on ``self.rng``).
+* ``rng_mode="numpy"``.  The reference's own draw sequence
+  (monte_carlo.py:222-240) on the host, fed to the GPU fed-draw kernels: prices
+  equal the reference's bit for bit up to 1e-12 for the same ``seed`` (and the
+  same ``np.random.seed`` for jump sizes).  Host-RNG bound; for parity and audits.
+* ``correlation="reference"`` reproduces the reference's European "double
+  correlation" of the two Brownian drivers (monte_carlo.py:230-231 followed by
+  mc_kernels.py:67); ``"independent"`` gives corr(dW_S, dW_v) = rho.
+* ``control_variate=True`` adds the discounted-terminal-spot control, whose mean
+  under the simulated discrete scheme is known in closed form.
+* Under an initialised ``torch.distributed`` group the draws are partitioned by
+  rank (disjoint Philox counters) and the moments are all-reduced once.
+"""
+from __future__ import annotations
+
+import math
+from typing import Any
+
+import numpy as np
+
+from optpricing_b200 import _engine
+from optpricing_b200.atoms import is_call as _is_call
+from optpricing_b200.models import model_kind
+
+from .base import BaseTechnique, GreekMixin, IVMixin, PricingResult
+from .kernels import mc_kernels
+
+_KERNELS = {
+    "bsm": mc_kernels.bsm_kernel, "heston": mc_kernels.heston_kernel,
+    "merton": mc_kernels.merton_kernel, "bates": mc_kernels.bates_kernel,
+    "sabr": mc_kernels.sabr_kernel, "sabr_jump": mc_kernels.sabr_jump_kernel,
+    "kou": mc_kernels.kou_kernel, "dupire": mc_kernels.dupire_kernel,
+}
+
+
+def shard_draws(n_draws: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous partition of draw ids [0, n_draws) -> (offset, count) of ``rank``."""
+    lo = n_draws * rank // world
+    hi = n_draws * (rank + 1) // world
+    return lo, hi - lo
+
+
+def control_mean(kind: str, params: dict, S0: float, r: float, q: float, T: float,
+                 n_steps: int) -> float:
+    """
+    E[S_T] under the *discrete* scheme the kernels simulate.  The log-Euler
+    models are exact one-step martingales (jump compensators match E[e^J]), so
+    E[S_T] = S0 e^{(r-q)T}; SABR is Euler on S itself (mc_kernels.py:211,257).
+    """
+    dt = T / n_steps
+    if kind == "sabr":
+        return S0 * (1.0 + (r - q) * dt) ** n_steps
+    if kind == "sabr_jump":
+        k = math.exp(params["mu_j"] + 0.5 * params["sigma_j"] ** 2) - 1.0
+        lam = params["lambda"]
+        return S0 * ((1.0 + (r - q - lam * k) * dt) * math.exp(lam * k * dt)) ** n_steps
+    return S0 * math.exp((r - q) * T)
+
+
+def summarize(moments, r: float, T: float, c_mean: float) -> dict:
+    """Price, standard error and control-variate estimate from (n, Sp, Spp, Sc, Scc, Spc)."""
+    n, sp, spp, sc, scc, spc = (float(x) for x in moments)
+    disc = math.exp(-r * T)
+    mp, mc = sp / n, sc / n
+    var_p = max(spp / n - mp * mp, 0.0) * (n / (n - 1.0) if n > 1 else 1.0)
+    out = {"n_samples": n, "price": disc * mp, "stderr": disc * math.sqrt(var_p / n),
+           "control_mean": mc, "control_expected": c_mean}
+    var_c = scc / n - mc * mc
+    cov = spc / n - mp * mc
+    out["control_stderr"] = math.sqrt(max(var_c, 0.0) / max(n - 1.0, 1.0))
+    if var_c > 0.0:
+        beta = cov / var_c
+        resid = max(var_p - beta * cov * (n / (n - 1.0) if n > 1 else 1.0), 0.0)
+        out.update(cv_beta=beta, cv_price=disc * (mp - beta * (mc - c_mean)),
+                   cv_stderr=disc * math.sqrt(resid / n))
+    return out
+
+
+class DeviceTerminal:
+    """What the Philox path hands from the simulator to ``price``: the payoff
+    moments of the hinted contract instead of a host array of terminal spots."""
+
+    def __init__(self, moments, kind, seed):
+        self.moments, self.kind, self.seed = moments, kind, seed
+
+
+class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
+    def __init__(self, *, n_paths: int = 20_000, n_steps: int = 100, antithetic: bool = True,
+                 seed: int | None = None, rng_mode: str = "philox",
+                 correlation: str = "reference", control_variate: bool = False,
+                 distributed: bool | None = None):
+        if antithetic and n_paths % 2 != 0:
+            n_paths += 1                       # monte_carlo.py:58-59
+        if rng_mode not in ("philox", "numpy"):
+            raise ValueError("rng_mode must be 'philox' or 'numpy'")
+        if correlation not in ("reference", "independent"):
+            raise ValueError("correlation must be 'reference' or 'independent'")
+        self.n_paths = n_paths
+        self.n_steps = n_steps
+        self.antithetic = antithetic
+        self.rng = np.random.default_rng(seed)
+        self.rng_mode = rng_mode
+        self.correlation = correlation
+        self.control_variate = control_variate
+        self.distributed = distributed
+        self.last_stats: dict = {}
+        self._hint = None
+
+    # ------------------------------------------------------------------ price
+    def price(self, option, stock, model, rate, **kwargs: Any) -> PricingResult:
+        if not (model.supports_sde or getattr(model, "is_pure_levy", False)):
+            raise TypeError(f"Model '{model.name}' does not support simulation.")
+        S0, K, T = stock.spot, option.strike, option.maturity
+        r, q = rate.get_rate(T), stock.dividend
+        call = _is_call(option)
+
+        if getattr(model, "has_exact_sampler", False):      # CEV: model's own sampler (:103-104)
+            ST = model.sample_terminal_spot(S0, r, T, self.n_paths)
+        elif getattr(model, "is_pure_levy", False):         # VG/NIG/CGMY/Hyperbolic (:105-106)
+            ST = self._simulate_levy_terminal(model, S0, r, q, T)
+        else:
+            self._hint = (float(K), call)
+            try:
+                ST = self._simulate_sde_path(model, S0, r, q, T, **kwargs)
+            finally:
+                self._hint = None
+
+        if isinstance(ST, DeviceTerminal):
+            c_mean = control_mean(ST.kind, model.params, S0, r, q, T, self.n_steps)
+            stats = summarize(ST.moments, r, T, c_mean)
+            stats["seed"] = ST.seed
+            self.last_stats = stats
+            use_cv = self.control_variate and "cv_price" in stats
+            return PricingResult(price=float(stats["cv_price"] if use_cv else stats["price"]))
+
+        payoff = np.maximum(ST - K, 0) if call else np.maximum(K - ST, 0)
+        self.last_stats = {"n_samples": float(np.size(payoff))}
+        return PricingResult(price=float(np.mean(payoff) * math.exp(-r * T)))
+
+    # --------------------------------------------------------------- dispatch
+    def _get_sde_kernel_and_params(self, model, r: float, q: float, dt: float, **kwargs: Any):
+        """(kernel function, keyword arguments) exactly as monte_carlo.py:118-197 pairs them."""
+        p = model.params
+        kind = model_kind(model)
+        kp: dict[str, Any] = {"r": r, "q": q, "dt": dt}
+        if kind in ("sabr", "sabr_jump"):
+            kp.update(alpha=p["alpha"], beta=p["beta"], rho=p["rho"],
+                      v0=kwargs.get("v0", p.get("alpha")))
+        elif kind in ("heston", "bates"):
+            kp.update(kappa=p["kappa"], theta=p["theta"], rho=p["rho"],
+                      vol_of_vol=p["vol_of_vol"], v0=kwargs.get("v0", p.get("v0")))
+        elif kind == "kou":
+            kp.update(sigma=p["sigma"], lambda_=p["lambda"], p_up=p["p_up"], eta1=p["eta1"],
+                      eta2=p["eta2"])
+        elif kind == "merton":
+            kp.update(sigma=p["sigma"])
+        elif kind == "bsm":
+            kp["sigma"] = p.get("sigma")
+        if kind in ("sabr_jump", "bates", "merton"):
+            kp.update(lambda_=p["lambda"], mu_j=p["mu_j"], sigma_j=p["sigma_j"])
+        return _KERNELS[kind], kp
+
+    def _group(self):
+        """(rank, world, all_reduce or None) for the draw partition."""
+        if self.distributed is False:
+            return 0, 1, None
+        try:
+            import torch.distributed as dist
+        except ImportError:  # pragma: no cover
+            return 0, 1, None
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return 0, 1, None
+        return dist.get_rank(), dist.get_world_size(), dist.all_reduce
+
+    # ------------------------------------------------------------- simulators
+    def _simulate_sde_path(self, model, S0: float, r: float, q: float, T: float, **kwargs: Any):
+        """
+        Terminal spots of ``n_paths`` simulated paths (monte_carlo.py:199-257).
+        Called directly it returns the host array, originals then antithetic
+        partners; called from ``price`` in Philox mode it returns a
+        DeviceTerminal carrying the payoff moments, and nothing leaves the GPU.
+        """
+        if self.rng_mode == "numpy":
+            return self._simulate_sde_path_numpy(model, S0, r, q, T, **kwargs)
+        kind = model_kind(model)
+        if kind == "dupire":
+            raise NotImplementedError("Dupire local vol is outside the GPU engine (SURVEY 8 f4)")
+        eng = _engine.get_engine()
+        num_draws = self.n_paths // 2 if self.antithetic else self.n_paths
+        seed = int(self.rng.integers(0, 2**63 - 1, dtype=np.int64))
+        mdl = _engine.make_model(kind, model.params, r, q, v0=kwargs.get("v0"))
+        corr = (_engine.CORR_REFERENCE_EUROPEAN if self.correlation == "reference"
+                else _engine.CORR_INDEPENDENT_DRAWS)
+        rank, world, all_reduce = self._group()
+        off, cnt = shard_draws(num_draws, rank, world)
+        sim = eng.make_sim(float(S0), T, num_draws, self.n_steps, self.antithetic, seed, corr,
+                           off, cnt)
+        if self._hint is None:
+            term = eng.buffer("terminal", cnt * (2 if self.antithetic else 1))
+            eng.european(mdl, sim, [float(S0)], [1], terminal=term)
+            return term[: cnt * (2 if self.antithetic else 1)].cpu().numpy()
+        K, call = self._hint
+        if all_reduce is None:
+            mom = eng.european(mdl, sim, [K], [1 if call else 0])[0]
+        else:
+            dev = eng.buffer("moments", _engine.NMOM)
+            eng.european_async(mdl, sim, [K], [1 if call else 0], dev)
+            all_reduce(dev[: _engine.NMOM])
+            mom = dev[: _engine.NMOM].cpu().numpy()
+        return DeviceTerminal(mom, kind, seed)
+
+    def _simulate_sde_path_numpy(self, model, S0, r, q, T, **kwargs):
+        """The reference's host draw sequence (monte_carlo.py:209-257) on GPU fed kernels."""
+        dt = T / self.n_steps
+        num_draws = self.n_paths // 2 if self.antithetic else self.n_paths
+        kernel, kp = self._get_sde_kernel_and_params(model, r, q, dt, **kwargs)
+        sabr = getattr(model, "is_sabr", False)
+        args = {"n_paths": num_draws, "n_steps": self.n_steps, **kp}
+        args["s0" if sabr else "log_s0"] = S0 if sabr else math.log(S0)
+        shape, sd = (num_draws, self.n_steps), math.sqrt(dt)
+        if model.has_variance_process:
+            dw_v = self.rng.standard_normal(size=shape) * sd
+            dw_u = self.rng.standard_normal(size=shape) * sd
+            rho = model.params.get("rho", 0)
+            args["dw1"] = rho * dw_v + math.sqrt(1 - rho**2) * dw_u
+            args["dw2"] = dw_v
+        else:
+            args["dw"] = self.rng.standard_normal(size=shape) * sd
+        if model.has_jumps:
+            args["jump_counts"] = self.rng.poisson(lam=model.params["lambda"] * dt, size=shape)
+        ST = kernel(**args)
+        if self.antithetic:
+            for key in ("dw", "dw1", "dw2"):
+                if key in args:
+                    args[key] = -args[key]
+            ST = np.concatenate([ST, kernel(**args)])
+        return ST if sabr else np.exp(ST)
+
+    def _simulate_levy_terminal(self, model, S0: float, r: float, q: float, T: float):
+        """
+        Pure-Levy terminal sampling (monte_carlo.py:259-280).  Outside the GPU
+        hot path: as in the reference, the model's own numpy
+        sampler produces the log-returns; only the martingale correction and
+        the exponential are applied here.
+        """
+        if not hasattr(model, "sample_terminal_log_return") or not hasattr(model, "raw_cf"):
+            raise NotImplementedError(f"Levy model '{model.name}' is missing required methods.")
+        x = model.sample_terminal_log_return(T, self.n_paths, self.rng)
+        compensator = np.log(np.real(model.raw_cf(t=T)(-1j)))
+        return S0 * np.exp((r - q) * T - compensator + x)

@@ -1,0 +1,284 @@
+"""
+CPU-only checks of the host layer: the C-ABI library loads and exports every
+symbol include/optmc.h declares, and the technique classes keep the reference's
+surface (tests modelled on /root/reference/tests/techniques/test_monte_carlo.py,
+base/test_greek_mixin.py, base/test_random_utils.py, base/test_iv_mixin.py).
+No kernel is launched here.
+"""
+import math
+import os
+import re
+from unittest.mock import MagicMock, patch
+
+import numpy as np
+import pytest
+
+import optpricing_b200 as ob
+from optpricing_b200 import _engine
+from optpricing_b200.techniques import monte_carlo as mc_mod
+from optpricing_b200.techniques.kernels import mc_kernels, path_kernels
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture
+def setup():
+    return (ob.Option(strike=100, maturity=1.0, option_type=ob.OptionType.CALL),
+            ob.Stock(spot=100), ob.Rate(rate=0.05))
+
+
+def test_library_exports_every_declared_symbol():
+    from optpricing_b200.build import build
+    build()
+    header = open(os.path.join(ROOT, "include", "optmc.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(optmc_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 20
+    lib = _engine.load_library()
+    bound = {name for name, _, _ in _engine.SIGNATURES}
+    assert declared == bound, declared ^ bound
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.optmc_version() >= 100
+
+
+def test_struct_layout_matches_header():
+    assert ctypes_sizeof(_engine.OptmcModel) == 8 + 16 * 8
+    assert ctypes_sizeof(_engine.OptmcSim) == 16 + 24 + 8 + 8 + 8
+
+
+def ctypes_sizeof(t):
+    import ctypes
+    return ctypes.sizeof(t)
+
+
+def test_ctor_follows_reference():
+    t = ob.MonteCarloTechnique()
+    assert (t.n_paths, t.n_steps, t.antithetic) == (20_000, 100, True)
+    assert isinstance(t.rng, np.random.Generator)
+    assert ob.MonteCarloTechnique(n_paths=11).n_paths == 12            # monte_carlo.py:58-59
+    assert ob.MonteCarloTechnique(n_paths=11, antithetic=False).n_paths == 11
+    a = ob.AmericanMonteCarloTechnique()
+    assert (a.n_paths, a.n_steps, a.antithetic, a.lsm_degree) == (20_000, 100, True, 2)
+    assert ob.AmericanMonteCarloTechnique(n_paths=7).n_paths == 8
+    with pytest.raises(TypeError):
+        ob.MonteCarloTechnique(20_000)                                   # keyword-only
+
+
+def test_mc_model_support_check(setup):
+    option, stock, rate = setup
+    bad = MagicMock()
+    bad.supports_sde = False
+    bad.is_pure_levy = False
+    bad.name = "Unsupported"
+    with pytest.raises(TypeError, match="does not support simulation"):
+        ob.MonteCarloTechnique().price(option, stock, bad, rate)
+    with pytest.raises(TypeError, match="requires an SDE model"):
+        ob.AmericanMonteCarloTechnique().price(option, stock, bad, rate)
+
+
+@patch("optpricing_b200.techniques.monte_carlo.MonteCarloTechnique._simulate_sde_path")
+def test_sde_path_dispatcher(mock_sim, setup):
+    mock_sim.return_value = np.array([100.0, 120.0])
+    option, stock, rate = setup
+    res = ob.MonteCarloTechnique().price(option, stock, ob.BSMModel(), rate)
+    mock_sim.assert_called_once()
+    assert res.price == pytest.approx(10.0 * math.exp(-0.05))
+    assert isinstance(res, ob.PricingResult) and isinstance(res.price, float)
+
+
+@patch("optpricing_b200.techniques.monte_carlo.MonteCarloTechnique._simulate_levy_terminal")
+def test_levy_terminal_dispatcher(mock_levy, setup):
+    mock_levy.return_value = np.array([100.0])
+    option, stock, rate = setup
+    levy = MagicMock()
+    levy.supports_sde = False
+    levy.is_pure_levy = True
+    levy.has_exact_sampler = False
+    ob.MonteCarloTechnique().price(option, stock, levy, rate)
+    mock_levy.assert_called_once()
+
+
+def test_exact_sampler_dispatcher(setup):
+    option, stock, rate = setup
+    cev = MagicMock()
+    cev.supports_sde = True
+    cev.has_exact_sampler = True
+    cev.sample_terminal_spot.return_value = np.array([100.0])
+    ob.MonteCarloTechnique().price(option, stock, cev, rate)
+    cev.sample_terminal_spot.assert_called_once()
+
+
+def test_levy_terminal_formula():
+    """monte_carlo.py:259-280 with a model whose raw cf is exp(t*psi)."""
+    m = MagicMock()
+    m.name = "fake"
+    m.sample_terminal_log_return.return_value = np.array([0.0, 0.1])
+    m.raw_cf.return_value = lambda u: np.exp(0.3 + 0j)
+    got = ob.MonteCarloTechnique()._simulate_levy_terminal(m, 100.0, 0.05, 0.01, 2.0)
+    want = 100.0 * np.exp((0.05 - 0.01) * 2.0 - 0.3 + np.array([0.0, 0.1]))
+    np.testing.assert_allclose(got, want, rtol=1e-15)
+
+
+@pytest.mark.parametrize("model, expected, keys", [
+    (ob.BSMModel(), mc_kernels.bsm_kernel, {"r", "q", "dt", "sigma"}),
+    (ob.HestonModel(), mc_kernels.heston_kernel,
+     {"r", "q", "dt", "kappa", "theta", "rho", "vol_of_vol", "v0"}),
+    (ob.MertonJumpModel(), mc_kernels.merton_kernel,
+     {"r", "q", "dt", "sigma", "lambda_", "mu_j", "sigma_j"}),
+    (ob.BatesModel(), mc_kernels.bates_kernel,
+     {"r", "q", "dt", "kappa", "theta", "rho", "vol_of_vol", "v0", "lambda_", "mu_j", "sigma_j"}),
+    (ob.KouModel(), mc_kernels.kou_kernel,
+     {"r", "q", "dt", "sigma", "lambda_", "p_up", "eta1", "eta2"}),
+    (ob.SABRModel(), mc_kernels.sabr_kernel, {"r", "q", "dt", "alpha", "beta", "rho", "v0"}),
+    (ob.SABRJumpModel(), mc_kernels.sabr_jump_kernel,
+     {"r", "q", "dt", "alpha", "beta", "rho", "v0", "lambda_", "mu_j", "sigma_j"}),
+])
+def test_get_sde_kernel_selector(model, expected, keys):
+    fn, kp = ob.MonteCarloTechnique()._get_sde_kernel_and_params(model=model, r=0.05, q=0.01,
+                                                                 dt=0.01)
+    assert fn is expected
+    assert set(kp) == keys
+    assert (kp["r"], kp["q"], kp["dt"]) == (0.05, 0.01, 0.01)
+
+
+def test_v0_resolution():
+    t = ob.MonteCarloTechnique()
+    _, kp = t._get_sde_kernel_and_params(ob.HestonModel(), 0.05, 0.0, 0.01, v0=0.09)
+    assert kp["v0"] == 0.09
+    _, kp = t._get_sde_kernel_and_params(ob.HestonModel(), 0.05, 0.0, 0.01)
+    assert kp["v0"] == 0.04
+    _, kp = t._get_sde_kernel_and_params(ob.SABRModel(), 0.05, 0.0, 0.01)
+    assert kp["v0"] == 0.5                                               # alpha, monte_carlo.py:136
+    fn, kp = ob.AmericanMonteCarloTechnique()._get_path_kernel_and_params(
+        model=ob.HestonModel(), r=0.05, q=0.01, dt=0.01, v0=0.04)
+    assert fn is path_kernels.heston_path_kernel and kp["v0"] == 0.04
+
+
+def test_shard_draws_is_a_partition():
+    for n in (0, 1, 7, 8, 1 << 23, 12345677):
+        for w in (1, 2, 3, 8):
+            pieces = [mc_mod.shard_draws(n, r, w) for r in range(w)]
+            assert pieces[0][0] == 0 and sum(c for _, c in pieces) == n
+            for (o1, c1), (o2, _) in zip(pieces, pieces[1:]):
+                assert o1 + c1 == o2
+            assert max(c for _, c in pieces) - min(c for _, c in pieces) <= 1
+
+
+def test_summarize_and_control_variate():
+    rng = np.random.default_rng(3)
+    c = rng.lognormal(size=4000) * 100
+    p = np.maximum(c - 100, 0)
+    m = [p.size, p.sum(), (p * p).sum(), c.sum(), (c * c).sum(), (p * c).sum()]
+    s = mc_mod.summarize(m, 0.05, 1.0, 165.0)
+    disc = math.exp(-0.05)
+    assert s["price"] == pytest.approx(disc * p.mean(), rel=1e-13)
+    assert s["stderr"] == pytest.approx(disc * p.std(ddof=1) / math.sqrt(p.size), rel=1e-10)
+    beta = np.cov(p, c, ddof=0)[0, 1] / c.var()
+    assert s["cv_beta"] == pytest.approx(beta, rel=1e-9)
+    assert s["cv_price"] == pytest.approx(disc * (p.mean() - beta * (c.mean() - 165.0)), rel=1e-9)
+    assert s["cv_stderr"] < s["stderr"]
+
+
+def test_control_mean():
+    f = mc_mod.control_mean
+    assert f("heston", {}, 100.0, 0.05, 0.01, 2.0, 10) == pytest.approx(100 * math.exp(0.08))
+    assert f("sabr", {}, 100.0, 0.05, 0.01, 1.0, 4) == pytest.approx(100 * 1.01**4)
+    p = {"lambda": 0.4, "mu_j": -0.1, "sigma_j": 0.15}
+    k = math.exp(-0.1 + 0.5 * 0.15**2) - 1
+    want = 100 * ((1 + (0.04 - 0.4 * k) * 0.25) * math.exp(0.4 * k * 0.25)) ** 4
+    assert f("sabr_jump", p, 100.0, 0.05, 0.01, 1.0, 4) == pytest.approx(want)
+
+
+# ---- mixins, with an analytic pricer (reference: tests/techniques/base/) ------
+class LinearPricer(ob.BaseTechnique, ob.GreekMixin, ob.IVMixin):
+    """price = 2 S - 3 K + 5 sigma + 7 T + 11 r: every greek is known exactly."""
+
+    def __init__(self, with_rng):
+        if with_rng:
+            self.rng = np.random.default_rng(0)
+        self.calls = 0
+
+    def price(self, option, stock, model, rate, **kw):
+        self.calls += 1
+        noise = self.rng.standard_normal() if hasattr(self, "rng") else 0.0
+        v = (2 * stock.spot - 3 * option.strike + 5 * model.params.get("sigma", 0.0)
+             + 7 * option.maturity + 11 * rate.get_rate(option.maturity) + noise)
+        return ob.PricingResult(price=v)
+
+
+@pytest.mark.parametrize("with_rng", [True, False])
+def test_greek_mixin_central_differences(setup, with_rng):
+    option, stock, rate = setup
+    t, m = LinearPricer(with_rng), ob.BSMModel()
+    assert t.delta(option, stock, m, rate) == pytest.approx(2.0, abs=1e-6)
+    assert t.gamma(option, stock, m, rate) == pytest.approx(0.0, abs=1e-3)
+    assert t.vega(option, stock, m, rate) == pytest.approx(5.0, abs=1e-6)
+    assert t.theta(option, stock, m, rate) == pytest.approx(-7.0, abs=1e-4)
+    assert t.rho(option, stock, m, rate) == pytest.approx(11.0, abs=1e-6)
+    assert t.calls == 2 + 3 + 2 + 2 + 2
+    assert np.isnan(t.vega(option, stock, ob.HestonModel(), rate))       # greek_mixin.py:156-157
+
+
+def test_crn_restores_generator_state():
+    rng = np.random.default_rng(5)
+    with ob.crn(rng):
+        a = rng.standard_normal(4)
+    with ob.crn(rng):
+        b = rng.standard_normal(4)
+    assert np.array_equal(a, b)
+    with pytest.raises(RuntimeError):
+        with ob.crn(rng):
+            rng.standard_normal()
+            raise RuntimeError
+    assert np.array_equal(rng.standard_normal(4), a)
+
+
+class BSMAnalytic(ob.BaseTechnique, ob.IVMixin):
+    def price(self, option, stock, model, rate, **kw):
+        from scipy.stats import norm
+        S, K, T, r = stock.spot, option.strike, option.maturity, rate.get_rate()
+        s = model.params["sigma"]
+        d1 = (math.log(S / K) + (r + 0.5 * s * s) * T) / (s * math.sqrt(T))
+        return ob.PricingResult(price=S * norm.cdf(d1) - K * math.exp(-r * T) * norm.cdf(d1 - s * math.sqrt(T)))
+
+
+def test_implied_volatility_roundtrip(setup):
+    option, stock, rate = setup
+    t = BSMAnalytic()
+    target = t.price(option, stock, ob.BSMModel({"sigma": 0.27}), rate).price
+    assert t.implied_volatility(option, stock, ob.BSMModel(), rate, target) == pytest.approx(0.27, abs=1e-5)
+    assert np.isnan(t.implied_volatility(option, stock, ob.BSMModel(), rate, 1e9))
+    assert ob.IVMixin._secant_iv(lambda x: x * x - 0.04, 0.3, 1e-10, 100) == pytest.approx(0.2)
+
+
+def test_atoms_and_models_validate():
+    with pytest.raises(ValueError):
+        ob.Option(strike=-1, maturity=1.0, option_type=ob.OptionType.CALL)
+    with pytest.raises(ValueError):
+        ob.Stock(spot=0)
+    assert ob.Rate(rate=lambda t: 0.02 + 0.01 * t).get_rate(2.0) == pytest.approx(0.04)
+    with pytest.raises(ValueError):
+        ob.HestonModel({"kappa": 1.0, "theta": 0.04, "rho": 1.5, "vol_of_vol": 0.3})
+    m = ob.BSMModel().with_params(sigma=0.3)
+    assert m.params["sigma"] == 0.3 and m == ob.BSMModel({"sigma": 0.3})
+    kinds = [ob.model_kind(c()) for c in (ob.BSMModel, ob.HestonModel, ob.MertonJumpModel,
+                                          ob.BatesModel, ob.KouModel, ob.SABRModel,
+                                          ob.SABRJumpModel)]
+    assert kinds == ["bsm", "heston", "merton", "bates", "kou", "sabr", "sabr_jump"]
+
+
+def test_engine_fails_loudly_without_gpu(setup):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    option, stock, rate = setup
+    with pytest.raises(_engine.EngineError, match="no CPU fallback"):
+        ob.MonteCarloTechnique(n_paths=100, n_steps=2).price(option, stock, ob.BSMModel(), rate)
+
+
+def test_philox_reference_known_answers():
+    from philox_ref import KAT, philox4x32_10
+    for c, k, want in KAT:
+        got = philox4x32_10(*[np.array([x], dtype=np.uint32) for x in c], *k)[0]
+        assert [int(x) for x in got] == list(want)
