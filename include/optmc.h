@@ -223,7 +223,8 @@ int optmc_normals(optmc_ctx *ctx, uint64_t seed, int64_t n, int32_t step, double
 int optmc_fp64_peak(optmc_ctx *ctx, int64_t iters, double *fma_per_sec, double *elapsed_ms);
 
 /* Tunables: "normals_impl" (0 = CUDA math library Box-Muller, 1 = hand-written,
-   default 1), "euro_blocks_per_sm" (0 = occupancy API decides). */
+   default 1), "euro_blocks_per_sm" (0 = occupancy API decides), "euro_threads"
+   (threads per block of the European kernel: 64, 128 or 256). */
 int optmc_set_int(optmc_ctx *ctx, const char *key, int64_t value);
 
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */

@@ -15,7 +15,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liboptmc.so")
+LIB_PATH = os.environ.get("OPTMC_LIB") or os.path.join(_HERE, "liboptmc.so")
 
 KIND_CODES = {"bsm": 0, "heston": 1, "merton": 2, "bates": 3, "sabr": 4, "sabr_jump": 5, "kou": 6}
 TWO_FACTOR = ("heston", "bates", "sabr", "sabr_jump")

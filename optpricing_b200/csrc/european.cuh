@@ -11,11 +11,15 @@
 namespace optmc {
 
 constexpr int EURO_THREADS = 256;
+#ifndef OPTMC_EURO_MIN_BLOCKS
+#define OPTMC_EURO_MIN_BLOCKS 3   // resident 256-thread blocks per SM the register budget is
+                                  // sized for (85 regs): no constant reloads in the step loop
+#endif
 constexpr int NPART = 8;  // doubles per block partial (5 used)
 
 struct EuroArgs {
     Consts c;
-    uint64_t seed;
+    PhiloxKey key;
     int64_t draw_offset;
     int64_t n_local;
     int n_steps;
@@ -29,7 +33,7 @@ struct EuroArgs {
 };
 
 template <int KIND, int NIMPL>
-__device__ __forceinline__ double jump_size(uint4 w, const Consts &c, const LogTable *tab) {
+__device__ __forceinline__ double jump_size(uint4 w, const Consts &c, RngView tab) {
     if constexpr (KIND == OPTMC_KOU) {
         // up w.p. p_up: +Exp(eta1), else -Exp(eta2)   (mc_kernels.py:314-317)
         double e;
@@ -48,18 +52,19 @@ __device__ __forceinline__ double jump_size(uint4 w, const Consts &c, const LogT
 // Jumps of one Poisson draw (rare path; the caller has already seen w >= p0_bits).
 // Counts are shared by the antithetic partner, sizes are fresh draws for it,
 // as in the reference's second pass (monte_carlo.py:247-255).
-template <int KIND, bool ANTI, int NIMPL>
+template <int KIND, bool ANTI, int NIMPL, bool DEFER>
 __device__ __noinline__ void jumps_slow(State &sa, State &sb, uint32_t w, double mu, double p0,
-                                        uint64_t seed, uint64_t id, uint32_t step,
-                                        const Consts &c, const LogTable *tab) {
-    uint4 e = philox_draw(seed, id, step, 0xFFu);
+                                        const PhiloxKey &key, uint64_t id, uint32_t step,
+                                        const Consts &c, RngView tab) {
+    uint4 e = philox_draw(key, id, step, 0xFFu);
     int n = poisson_slow(w, e.x, mu, p0);
     for (int j = 0; j < n; ++j) {
-        apply_jump<KIND>(sa, jump_size<KIND, NIMPL>(
-                                 philox_draw(seed, id, step, 1u | ((uint32_t)j << 8)), c, tab));
+        apply_jump<KIND, DEFER>(sa, jump_size<KIND, NIMPL>(
+                                        philox_draw(key, id, step, 1u | ((uint32_t)j << 8)), c, tab));
         if constexpr (ANTI)
-            apply_jump<KIND>(sb, jump_size<KIND, NIMPL>(
-                                     philox_draw(seed, id, step, 2u | ((uint32_t)j << 8)), c, tab));
+            apply_jump<KIND, DEFER>(sb, jump_size<KIND, NIMPL>(
+                                            philox_draw(key, id, step, 2u | ((uint32_t)j << 8)), c,
+                                            tab));
     }
 }
 
@@ -67,33 +72,36 @@ __device__ __noinline__ void jumps_slow(State &sa, State &sb, uint32_t w, double
 // every completed step when PER_STEP (LSMC path store), never otherwise.
 template <int KIND, bool ANTI, int NIMPL, bool PER_STEP, class Sink>
 __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, State &sa, State &sb,
-                                              const LogTable *tab, Sink &&sink) {
+                                              RngView tab, Sink &&sink) {
     const Consts &c = A.c;
-    sa.x = sb.x = c.x0;
-    sa.v = sb.v = c.v0;
     constexpr bool TWO = kind_two_factor(KIND);
     constexpr bool JUMPS = kind_jumps(KIND);
+    // terminal-only kernels of the log models defer the deterministic drift
+    constexpr bool DEFER = !PER_STEP && !kind_sabr(KIND);
+    init_state<KIND, DEFER>(sa, c);
+    init_state<KIND, DEFER>(sb, c);
     // A Box-Muller pair feeds one step of a two-factor model, or two
     // consecutive steps of a one-factor model (terminal-only kernels).
     constexpr int SPC = (TWO || PER_STEP) ? 1 : 2;
+    const uint32_t id_lo = keep_u32((uint32_t)id), id_hi = keep_u32((uint32_t)(id >> 32));
     for (int i = 0; i < A.n_steps; i += SPC) {
-        uint4 w = philox_draw(A.seed, id, (uint32_t)i, 0u);
+        uint4 w = philox4x32_10(make_uint4(id_lo, id_hi, (uint32_t)i, 0u), A.key);
         double a, b;
         normal_pair<NIMPL>(w.x, w.y, w.z, a, b, tab);
         if constexpr (TWO) {
             double z1 = fma(c.m12, b, c.m11 * a);
             double cz = fma(c.m22, b, c.m21 * a);
-            step_diffusion<KIND>(sa, z1, cz, c);
-            if constexpr (ANTI) step_diffusion<KIND>(sb, -z1, -cz, c);
+            step_diffusion<KIND, DEFER>(sa, z1, cz, c);
+            if constexpr (ANTI) step_diffusion<KIND, DEFER>(sb, -z1, -cz, c);
         } else {
             double dw = c.sqrt_dt * a;
-            step_diffusion<KIND>(sa, dw, 0.0, c);
-            if constexpr (ANTI) step_diffusion<KIND>(sb, -dw, 0.0, c);
+            step_diffusion<KIND, DEFER>(sa, dw, 0.0, c);
+            if constexpr (ANTI) step_diffusion<KIND, DEFER>(sb, -dw, 0.0, c);
             if constexpr (SPC == 2) {
                 if (i + 1 < A.n_steps) {
                     double dw2 = c.sqrt_dt * b;
-                    step_diffusion<KIND>(sa, dw2, 0.0, c);
-                    if constexpr (ANTI) step_diffusion<KIND>(sb, -dw2, 0.0, c);
+                    step_diffusion<KIND, DEFER>(sa, dw2, 0.0, c);
+                    if constexpr (ANTI) step_diffusion<KIND, DEFER>(sb, -dw2, 0.0, c);
                 }
             }
         }
@@ -103,11 +111,13 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
             // steps does not affect S_T.
             const int two = (SPC == 2 && i + 1 < A.n_steps) ? 1 : 0;
             if (poisson_maybe(w.w, A.pois_p0_bits[two]))
-                jumps_slow<KIND, ANTI, NIMPL>(sa, sb, w.w, A.pois_mu[two], A.pois_p0[two], A.seed,
-                                              id, (uint32_t)i, c, tab);
+                jumps_slow<KIND, ANTI, NIMPL, DEFER>(sa, sb, w.w, A.pois_mu[two], A.pois_p0[two],
+                                                     A.key, id, (uint32_t)i, c, tab);
         }
         if constexpr (PER_STEP) sink(i, sa, sb);
     }
+    finish_deferred<KIND, DEFER>(sa, c);
+    if constexpr (ANTI) finish_deferred<KIND, DEFER>(sb, c);
 }
 
 struct NoSink {
@@ -115,18 +125,19 @@ struct NoSink {
 };
 
 template <int KIND, bool ANTI, int NIMPL>
-__global__ void __launch_bounds__(EURO_THREADS) k_european(const EuroArgs A) {
-    __shared__ LogTable tab;
+__global__ void __launch_bounds__(EURO_THREADS, OPTMC_EURO_MIN_BLOCKS) k_european(const EuroArgs A) {
+    __shared__ RngTables tab;
+    RngView tv{0u};
     __shared__ double scratch[5 * 32];
     if constexpr (NIMPL != 0) {
-        fill_log_table(&tab);
+        tv = load_rng_tables(&tab);
         __syncthreads();
     }
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < A.n_local; g += stride) {
         State sa, sb;
-        simulate_draw<KIND, ANTI, NIMPL, false>(A, (uint64_t)(A.draw_offset + g), sa, sb, &tab,
+        simulate_draw<KIND, ANTI, NIMPL, false>(A, (uint64_t)(A.draw_offset + g), sa, sb, tv,
                                                 NoSink{});
         double ST = terminal_spot(KIND, sa);
         double pay = A.is_call ? ST - A.strike : A.strike - ST;   // monte_carlo.py:110-114

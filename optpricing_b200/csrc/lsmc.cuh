@@ -36,16 +36,17 @@ struct StoreSink {
 template <int KIND, bool ANTI, int NIMPL>
 __global__ void __launch_bounds__(EURO_THREADS) k_lsmc_paths(const EuroArgs A, double *store,
                                                              int64_t ld) {
-    __shared__ LogTable tab;
+    __shared__ RngTables tab;
+    RngView tv{0u};
     if constexpr (NIMPL != 0) {
-        fill_log_table(&tab);
+        tv = load_rng_tables(&tab);
         __syncthreads();
     }
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < A.n_local; g += stride) {
         State sa, sb;
         StoreSink sink{store, ld, g, A.n_local, KIND, ANTI};
-        simulate_draw<KIND, ANTI, NIMPL, true>(A, (uint64_t)(A.draw_offset + g), sa, sb, &tab,
+        simulate_draw<KIND, ANTI, NIMPL, true>(A, (uint64_t)(A.draw_offset + g), sa, sb, tv,
                                                sink);
     }
 }

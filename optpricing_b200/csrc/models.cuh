@@ -30,7 +30,9 @@ struct Consts {
     double rqc_dt;            // rqc * dt
     double neg_half_dt;       // -0.5 dt
     double kappa_theta_dt;    // kappa theta dt
-    double neg_kappa_dt;      // -kappa dt
+    double one_minus_kappa_dt;
+    double n_rqc_dt;          // n_steps * rqc_dt   (deferred-drift kernels)
+    double n_drift;           // n_steps * drift
     double xi;                // vol_of_vol
     // SABR
     double alpha, beta;
@@ -57,32 +59,61 @@ __host__ __device__ constexpr bool kind_sabr(int k) {
     return k == OPTMC_SABR || k == OPTMC_SABR_JUMP;
 }
 
-// max(a, 0) on the integer pipe (keeps the fp64 pipe for arithmetic).
-// -0.0 and negatives -> +0.0.
+// max(a, 0) in ONE integer-pipe instruction: clamp the high word at 0.  A
+// negative a becomes (0, lo): a positive denormal below 2^-1042 instead of an
+// exact 0 -- a difference of < 1e-313, which no product or sum in the step can
+// turn into anything representable next to the quantities it meets.
 __device__ __forceinline__ double relu64(double a) {
-    int hi = __double2hiint(a), lo = __double2loint(a);
-    int keep = ~(hi >> 31);
-    return __hiloint2double(hi & keep, lo & keep);
+    return __hiloint2double(max(__double2hiint(a), 0), __double2loint(a));
 }
 
 struct State {
-    double x;  // log S (S for SABR kinds)
-    double v;  // variance (Heston/Bates) or vol (SABR); unused otherwise
+    double x;  // log S (S for SABR kinds); with DEFER: the stochastic part only
+    double v;  // variance (Heston/Bates, stored before the floor) or vol (SABR)
+    double w;  // DEFER only: running sum of v_pos (Heston/Bates)
 };
 
+// DEFER (terminal-value kernels of the log models): the deterministic drift is
+// added once after the last step instead of every step,
+//   one-factor:  log S_T = log S_0 + n drift + sigma sum(dw)            [+ jumps]
+//   Heston:      log S_T = log S_0 + n (r-q-c) dt - dt/2 sum(v+) + sum(sqrt(v+) z1)
+// which is the reference recurrence re-associated (agreement ~ n * 1e-16).  The
+// path kernels need log S at every step and use the literal form.
+
 // bsm_kernel mc_kernels.py:30-32; merton :105-106; kou :306-307 (diffusion part)
+template <bool DEFER>
 __device__ __forceinline__ void step_one_factor(State &s, double dw, const Consts &c) {
-    s.x += fma(c.sigma, dw, c.drift);
+    if constexpr (DEFER)
+        s.x += dw;
+    else
+        s.x += fma(c.sigma, dw, c.drift);
 }
 
 // heston_kernel mc_kernels.py:62-77, bates_kernel :151-164.
 // z1 = dw1; czx = vol_of_vol * (rho*dw1 + rho_bar*dw2).
+// s.v holds the variance BEFORE the floor of :76-77; flooring on read is the same
+// thing for every step (v0 >= 0 is enforced on the host, see make_consts).
+template <bool DEFER>
 __device__ __forceinline__ void step_heston(State &s, double z1, double czx, const Consts &c) {
     double vp = relu64(s.v);                       // v_pos = max(v, 0)
     double sq = sqrt_nonneg(vp);                   // v_sqrt
-    s.x += fma(sq, z1, fma(vp, c.neg_half_dt, c.rqc_dt));
-    double vn = fma(sq, czx, fma(vp, c.neg_kappa_dt, s.v + c.kappa_theta_dt));
-    s.v = relu64(vn);                              // v = max(v, 0)
+    if constexpr (DEFER) {
+        s.x = fma(sq, z1, s.x);
+        s.w += vp;
+    } else {
+        s.x += fma(sq, z1, fma(vp, c.neg_half_dt, c.rqc_dt));
+    }
+    s.v = fma(sq, czx, fma(vp, c.one_minus_kappa_dt, c.kappa_theta_dt));
+}
+
+template <int KIND, bool DEFER>
+__device__ __forceinline__ void finish_deferred(State &s, const Consts &c) {
+    if constexpr (DEFER) {
+        if constexpr (KIND == OPTMC_HESTON || KIND == OPTMC_BATES)
+            s.x = c.x0 + (c.n_rqc_dt + fma(s.w, c.neg_half_dt, s.x));
+        else
+            s.x = (c.x0 + fma(c.sigma, s.x, c.n_drift)) + s.w;   // s.w: sum of log-jumps
+    }
 }
 
 __device__ __forceinline__ double sabr_pow(double s_pos, const Consts &c) {
@@ -111,22 +142,33 @@ __device__ __forceinline__ void mix_fed(int kind, double dw1, double dw2, const 
     if (kind == OPTMC_HESTON || kind == OPTMC_BATES) cz *= c.xi;
 }
 
-template <int KIND>
+template <int KIND, bool DEFER = false>
 __device__ __forceinline__ void step_diffusion(State &s, double z1, double cz, const Consts &c) {
     if constexpr (KIND == OPTMC_HESTON || KIND == OPTMC_BATES)
-        step_heston(s, z1, cz, c);
+        step_heston<DEFER>(s, z1, cz, c);
     else if constexpr (kind_sabr(KIND))
         step_sabr(s, z1, cz, c);
     else
-        step_one_factor(s, z1, c);
+        step_one_factor<DEFER>(s, z1, c);
+}
+
+// Initial state.  With DEFER the log-spot accumulator starts at 0 and log S_0 is
+// added by finish_deferred; jumps (additive in log space) accumulate in x too.
+template <int KIND, bool DEFER>
+__device__ __forceinline__ void init_state(State &s, const Consts &c) {
+    s.x = (DEFER && !kind_sabr(KIND)) ? 0.0 : c.x0;
+    s.v = c.v0;
+    s.w = 0.0;
 }
 
 // Apply one jump of size J (Merton/Bates/Kou: additive in log space,
 // mc_kernels.py:115,174,323; SABR-jump: multiplicative on S, :274).
-template <int KIND>
+template <int KIND, bool DEFER = false>
 __device__ __forceinline__ void apply_jump(State &s, double J) {
     if constexpr (KIND == OPTMC_SABR_JUMP)
         s.x *= exp(J);
+    else if constexpr (DEFER && (KIND == OPTMC_MERTON || KIND == OPTMC_KOU))
+        s.w += J;      // s.x holds the unscaled Brownian sum here
     else
         s.x += J;
 }

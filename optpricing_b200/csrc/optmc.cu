@@ -22,6 +22,7 @@ struct optmc_ctx {
     int sm_count = 0;
     int normals_impl = 1;       // 0: CUDA math library, 1: hand-written (philox.cuh)
     int euro_blocks_per_sm = 0; // 0: occupancy API decides
+    int euro_threads = EURO_THREADS;
     int64_t launches = 0;
     unsigned char *scratch = nullptr;  // device
     size_t scratch_bytes = 0;
@@ -93,6 +94,21 @@ extern "C" int optmc_ctx_create(int device, optmc_ctx **out) {
     if ((e = cudaHostAlloc(&ctx->moments_host, sizeof(double) * SWEEP_MAX * OPTMC_NMOM,
                            cudaHostAllocDefault)) != cudaSuccess)
         return fail(e, "cudaHostAlloc");
+    {
+        RngTables *h = new RngTables();
+        const double pi = 3.14159265358979323846;
+        for (int i = 0; i < 128; ++i) {
+            double c = 1.0 + (i + 0.5) / 128.0;
+            h->logt[i] = make_double2(-2.0 / c, -2.0 * std::log(c) + 24.0 * std::log(2.0));
+        }
+        for (int i = 0; i < TRIG_N; ++i) {
+            double a = (i + 0.5) * (2.0 * pi / TRIG_N);
+            h->trig[i] = make_double2(std::cos(a), std::sin(a));
+        }
+        e = cudaMemcpyToSymbol(g_rng_tables, h, sizeof(RngTables));
+        delete h;
+        if (e != cudaSuccess) return fail(e, "cudaMemcpyToSymbol");
+    }
     if ((e = cudaFuncSetAttribute(k_fed<OPTMC_BSM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)fed_smem_bytes())) != cudaSuccess)
         return fail(e, "cudaFuncSetAttribute");
@@ -124,6 +140,9 @@ extern "C" int optmc_set_int(optmc_ctx *ctx, const char *key, int64_t value) {
     } else if (!strcmp(key, "euro_blocks_per_sm")) {
         if (value < 0 || value > 16) FAIL("euro_blocks_per_sm out of range");
         ctx->euro_blocks_per_sm = (int)value;
+    } else if (!strcmp(key, "euro_threads")) {
+        if (value != 64 && value != 128 && value != 256) FAIL("euro_threads must be 64, 128 or 256");
+        ctx->euro_threads = (int)value;
     } else {
         FAIL(std::string("unknown option ") + key);
     }
@@ -133,8 +152,8 @@ extern "C" int optmc_set_int(optmc_ctx *ctx, const char *key, int64_t value) {
 // ---------------------------------------------------------------------------
 // constants, in the reference's expression order
 // ---------------------------------------------------------------------------
-static int make_consts(optmc_ctx *ctx, const optmc_model *m, double x0, double dt, int correlation,
-                       Consts *out) {
+static int make_consts(optmc_ctx *ctx, const optmc_model *m, double x0, double dt, int n_steps,
+                       int correlation, Consts *out) {
     Consts c;
     memset(&c, 0, sizeof c);
     if (m->kind < OPTMC_BSM || m->kind > OPTMC_KOU) FAIL("unknown model kind");
@@ -156,9 +175,13 @@ static int make_consts(optmc_ctx *ctx, const optmc_model *m, double x0, double d
     c.drift = (m->r - m->q - 0.5 * m->sigma * m->sigma - comp) * dt;                 // :29,104,304
     c.rqc = m->r - m->q - comp;
     c.rqc_dt = c.rqc * dt;
+    c.n_rqc_dt = n_steps * c.rqc_dt;
+    c.n_drift = n_steps * c.drift;
     c.neg_half_dt = -0.5 * dt;
     c.kappa_theta_dt = m->kappa * m->theta * dt;
-    c.neg_kappa_dt = -m->kappa * dt;
+    c.one_minus_kappa_dt = 1.0 - m->kappa * dt;
+    if ((m->kind == OPTMC_HESTON || m->kind == OPTMC_BATES) && !(m->v0 >= 0.0))
+        FAIL("v0 must be non-negative for Heston/Bates");
     c.xi = m->vol_of_vol;
     c.alpha = m->alpha;
     c.beta = m->beta;
@@ -221,12 +244,13 @@ static int check_sim(optmc_ctx *ctx, const optmc_sim *s) {
 template <class K>
 static int euro_grid(optmc_ctx *ctx, K kernel, int64_t n_local) {
     int per_sm = ctx->euro_blocks_per_sm;
+    const int threads = ctx->euro_threads;
     if (per_sm <= 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, EURO_THREADS, 0) !=
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) !=
                 cudaSuccess || per_sm < 1)
             per_sm = 1;
     }
-    int64_t need = (n_local + EURO_THREADS - 1) / EURO_THREADS;
+    int64_t need = (n_local + threads - 1) / threads;
     int64_t cap = (int64_t)ctx->sm_count * per_sm;
     return (int)std::max<int64_t>(1, std::min<int64_t>(std::min(need, cap), MAX_GRID));
 }
@@ -248,7 +272,7 @@ template <int KIND, bool ANTI, int NIMPL>
 static int launch_euro_t(optmc_ctx *ctx, EuroArgs &A, cudaStream_t st, int *grid_out) {
     auto kern = k_european<KIND, ANTI, NIMPL>;
     int grid = euro_grid(ctx, kern, A.n_local);
-    kern<<<grid, EURO_THREADS, 0, st>>>(A);
+    kern<<<grid, ctx->euro_threads, 0, st>>>(A);
     ctx->launches++;
     CK(cudaGetLastError());
     *grid_out = grid;
@@ -272,10 +296,10 @@ static int fill_euro_args(optmc_ctx *ctx, const optmc_model *model, const optmc_
     double dt = sim->maturity / sim->n_steps;                                 // monte_carlo.py:209
     double x0 = kind_sabr(model->kind) ? sim->s0 : std::log(sim->s0);          // :217-220
     memset(A, 0, sizeof *A);
-    rc = make_consts(ctx, model, x0, dt, sim->correlation, &A->c);
+    rc = make_consts(ctx, model, x0, dt, sim->n_steps, sim->correlation, &A->c);
     if (rc) return rc;
     poisson_consts(*A);
-    A->seed = sim->seed;
+    philox_expand_key(sim->seed, &A->key);
     A->draw_offset = sim->draw_offset;
     A->n_local = sim->n_local;
     A->n_steps = sim->n_steps;
@@ -402,7 +426,7 @@ extern "C" int optmc_fed_async(optmc_ctx *ctx, const optmc_model *model, double 
     if (n_paths == 0) return 0;
     FedArgs A;
     memset(&A, 0, sizeof A);
-    int rc = make_consts(ctx, model, x0, dt, OPTMC_CORR_INDEPENDENT_DRAWS, &A.c);
+    int rc = make_consts(ctx, model, x0, dt, n_steps, OPTMC_CORR_INDEPENDENT_DRAWS, &A.c);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     A.n_paths = n_paths;
@@ -609,25 +633,26 @@ extern "C" int optmc_lsmc(optmc_ctx *ctx, const double *store_dev, int64_t ld, i
 // ---------------------------------------------------------------------------
 // diagnostics
 // ---------------------------------------------------------------------------
-__global__ void k_philox_raw(uint64_t seed, int64_t n, uint32_t c2, uint32_t c3, uint32_t *out) {
+__global__ void k_philox_raw(PhiloxKey key, int64_t n, uint32_t c2, uint32_t c3, uint32_t *out) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint4 w = philox_draw(seed, (uint64_t)i, c2, c3);
+    uint4 w = philox_draw(key, (uint64_t)i, c2, c3);
     reinterpret_cast<uint4 *>(out)[i] = w;
 }
 
 template <int NIMPL>
-__global__ void k_normals(uint64_t seed, int64_t n, int step, double *out) {
-    __shared__ LogTable tab;
+__global__ void k_normals(PhiloxKey key, int64_t n, int step, double *out) {
+    __shared__ RngTables tab;
+    RngView tv{0u};
     if constexpr (NIMPL != 0) {
-        fill_log_table(&tab);
+        tv = load_rng_tables(&tab);
         __syncthreads();
     }
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint4 w = philox_draw(seed, (uint64_t)i, (uint32_t)step, 0u);
+    uint4 w = philox_draw(key, (uint64_t)i, (uint32_t)step, 0u);
     double a, b;
-    normal_pair<NIMPL>(w.x, w.y, w.z, a, b, &tab);
+    normal_pair<NIMPL>(w.x, w.y, w.z, a, b, tv);
     out[2 * i] = a;
     out[2 * i + 1] = b;
 }
@@ -649,7 +674,9 @@ extern "C" int optmc_philox_raw(optmc_ctx *ctx, uint64_t seed, int64_t n, uint32
     if (!ctx) return -2;
     CK(cudaSetDevice(ctx->device));
     if (n < 1 || !out_dev) FAIL("bad arguments");
-    k_philox_raw<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(seed, n, c2, c3,
+    PhiloxKey key;
+    philox_expand_key(seed, &key);
+    k_philox_raw<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(key, n, c2, c3,
                                                                                 out_dev);
     ctx->launches++;
     CK(cudaGetLastError());
@@ -662,10 +689,12 @@ extern "C" int optmc_normals(optmc_ctx *ctx, uint64_t seed, int64_t n, int32_t s
     CK(cudaSetDevice(ctx->device));
     if (n < 1 || !out_dev) FAIL("bad arguments");
     unsigned grid = (unsigned)((n + 255) / 256);
+    PhiloxKey key;
+    philox_expand_key(seed, &key);
     if (ctx->normals_impl == 0)
-        k_normals<0><<<grid, 256, 0, (cudaStream_t)stream>>>(seed, n, step, out_dev);
+        k_normals<0><<<grid, 256, 0, (cudaStream_t)stream>>>(key, n, step, out_dev);
     else
-        k_normals<1><<<grid, 256, 0, (cudaStream_t)stream>>>(seed, n, step, out_dev);
+        k_normals<1><<<grid, 256, 0, (cudaStream_t)stream>>>(key, n, step, out_dev);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
