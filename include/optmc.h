@@ -164,21 +164,25 @@ int optmc_payoff_sweep_async(optmc_ctx *ctx, const double *terminal_dev, int64_t
  *                            _simulate_full_sde_paths (:152-207) + path_kernels.py
  *   optmc_lsmc_load_async    fill the store from a reference-layout matrix
  *                            paths_dev[n_paths][n_steps+1] (column 0 ignored)
- *   optmc_lsmc_begin_async   cashflow = payoff at T      (american_mc_kernels.py:48-51)
- *   optmc_lsmc_gram_async    date i: cashflow *= exp(-r dt); accumulate the
- *                            in-the-money power sums sum x^k (k <= 2d) and
- *                            sum y x^k (k <= d) of the shifted variable
- *                            x = S/K - 1 into gram_dev   (:54-69; the X'X and
- *                            X'y of :72 are read off these sums)
- *   optmc_lsmc_decide_async  solve the normal equations from gram_dev (after
- *                            any cross-rank all-reduce) and exercise where
- *                            intrinsic > fitted continuation (:72-80); a
- *                            rank-deficient or non-positive-definite system
- *                            skips the date like the bare `except` of :81-82
- *   optmc_lsmc_finish_async  out_dev[0..2] = n, sum cf*disc, sum (cf*disc)^2 (:84)
- *   optmc_lsmc               all of the above for one GPU, one sync, host result
+ *   optmc_lsmc_step_async    one fused sweep for exercise date `date`
+ *                            (call with date = n_steps-1, ..., 1, 0):
+ *                              date == n_steps-1: cashflow = payoff at T      (american_mc_kernels.py:48-51)
+ *                              otherwise: exercise decision of date+1 from the
+ *                                normal equations in gram_dev slot [date+1] --
+ *                                exercise where intrinsic > fitted continuation (:72-80);
+ *                                a rank-deficient or non-positive-definite system
+ *                                skips the decision like the bare `except` of :81-82
+ *                              cashflow *= discount                            (:54)
+ *                              date >= 1: in-the-money power sums sum x^k (k <= 2d)
+ *                                and sum y x^k (k <= d) of x = S/K - 1 into slot
+ *                                [date] (:57-69; X'X and X'y of :72 are read off them)
+ *                              date == 0: slot [0] = n, sum cf, sum cf^2       (:84)
+ *                            With several ranks, all-reduce slot [date] between calls.
+ *   optmc_lsmc               the whole loop for one GPU, one sync, host result
+ *                            out_host[0..2] = n, sum, sum of squares of the
+ *                            discounted cashflows
  *
- * gram_dev: OPTMC_LSMC_GRAM doubles per date:
+ * gram_dev: n_steps slots of OPTMC_LSMC_GRAM doubles:
  *   [0] n_itm, [1..2d] sum x^k, then [16 + k] sum y x^k (k = 0..d).  degree <= 7.
  */
 #define OPTMC_LSMC_GRAM 24
@@ -188,19 +192,10 @@ int optmc_lsmc_paths_async(optmc_ctx *ctx, const optmc_model *model, const optmc
                            double *store_dev, int64_t ld, void *stream);
 int optmc_lsmc_load_async(optmc_ctx *ctx, const double *paths_dev, int64_t n_paths,
                           int32_t n_steps, double *store_dev, int64_t ld, void *stream);
-int optmc_lsmc_begin_async(optmc_ctx *ctx, const double *store_dev, int64_t ld,
-                           int64_t n_paths, int32_t n_steps, double strike,
-                           int32_t is_call, double *cashflow_dev, void *stream);
-int optmc_lsmc_gram_async(optmc_ctx *ctx, const double *store_dev, int64_t ld,
-                          int64_t n_paths, int32_t date, double strike, int32_t is_call,
+int optmc_lsmc_step_async(optmc_ctx *ctx, const double *store_dev, int64_t ld, int64_t n_paths,
+                          int32_t n_steps, int32_t date, double strike, int32_t is_call,
                           double discount, int32_t degree, double *cashflow_dev,
                           double *gram_dev, void *stream);
-int optmc_lsmc_decide_async(optmc_ctx *ctx, const double *store_dev, int64_t ld,
-                            int64_t n_paths, int32_t date, double strike, int32_t is_call,
-                            int32_t degree, const double *gram_dev, double *cashflow_dev,
-                            void *stream);
-int optmc_lsmc_finish_async(optmc_ctx *ctx, int64_t n_paths, double discount,
-                            const double *cashflow_dev, double *out_dev, void *stream);
 int optmc_lsmc(optmc_ctx *ctx, const double *store_dev, int64_t ld, int64_t n_paths,
                int32_t n_steps, double strike, int32_t is_call, double r, double dt,
                int32_t degree, double *cashflow_dev, double *gram_dev, double *out_host,

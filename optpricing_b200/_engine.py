@@ -72,14 +72,8 @@ SIGNATURES = [
                                        ctypes.POINTER(OptmcSim), c_void_p, c_i64, c_void_p]),
     ("optmc_lsmc_load_async", c_int, [c_void_p, c_void_p, c_i64, c_i32, c_void_p, c_i64,
                                       c_void_p]),
-    ("optmc_lsmc_begin_async", c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i32, c_double, c_i32,
-                                       c_void_p, c_void_p]),
-    ("optmc_lsmc_gram_async", c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i32, c_double, c_i32,
-                                      c_double, c_i32, c_void_p, c_void_p, c_void_p]),
-    ("optmc_lsmc_decide_async", c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i32, c_double,
-                                        c_i32, c_i32, c_void_p, c_void_p, c_void_p]),
-    ("optmc_lsmc_finish_async", c_int, [c_void_p, c_i64, c_double, c_void_p, c_void_p,
-                                        c_void_p]),
+    ("optmc_lsmc_step_async", c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i32, c_i32, c_double,
+                                      c_i32, c_double, c_i32, c_void_p, c_void_p, c_void_p]),
     ("optmc_lsmc", c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i32, c_double, c_i32, c_double,
                            c_double, c_i32, c_void_p, c_void_p, _dp, c_void_p]),
     ("optmc_philox_raw", c_int, [c_void_p, c_u64, c_i64, c_u32, c_u32, c_void_p, c_void_p]),
@@ -294,7 +288,7 @@ class Engine:
     def lsmc(self, store, ld, n_paths, n_steps, strike, is_call, r, dt, degree):
         """Single-GPU induction: returns (n, sum, sum_sq) of discounted cashflows."""
         cash = self.buffer("lsmc_cash", n_paths)
-        gram = self.buffer("lsmc_gram", LSMC_GRAM)
+        gram = self.buffer("lsmc_gram", LSMC_GRAM * n_steps)
         out = np.empty(3)
         self._check(self.lib.optmc_lsmc(self.ctx, c_void_p(store.data_ptr()), ld, n_paths,
                                         n_steps, float(strike), 1 if is_call else 0, float(r),
@@ -306,33 +300,24 @@ class Engine:
     def lsmc_distributed(self, store, ld, n_paths, n_steps, strike, is_call, r, dt, degree,
                          all_reduce):
         """
-        The same induction with one ``all_reduce(tensor)`` of the 24-double Gram
-        vector per exercise date and one of (n, sum, sum_sq) at the end
-        (SURVEY 8 e2).  ``all_reduce`` sums a device tensor in place across ranks.
+        The same induction over this rank's shard of paths with one
+        ``all_reduce(tensor)`` of the 24-double power-sum vector per exercise
+        date.  ``all_reduce`` sums a device tensor in place
+        across ranks; every rank then solves the same normal equations.
         """
         import math
 
-        L, ctx, st = self.lib, self.ctx, self.stream()
         cash = self.buffer("lsmc_cash", n_paths)
-        gram = self.buffer("lsmc_gram", LSMC_GRAM)
-        out = self.buffer("lsmc_out", 3)
+        gram = self.buffer("lsmc_gram", LSMC_GRAM * n_steps)
         disc = math.exp(-r * dt)
         sp, cp, gp = (c_void_p(store.data_ptr()), c_void_p(cash.data_ptr()),
                       c_void_p(gram.data_ptr()))
-        ic = 1 if is_call else 0
-        self._check(L.optmc_lsmc_begin_async(ctx, sp, ld, n_paths, n_steps, float(strike), ic,
-                                             cp, st), "optmc_lsmc_begin_async")
-        for i in range(n_steps - 1, 0, -1):
-            self._check(L.optmc_lsmc_gram_async(ctx, sp, ld, n_paths, i, float(strike), ic, disc,
-                                                int(degree), cp, gp, st), "optmc_lsmc_gram_async")
-            all_reduce(gram[:LSMC_GRAM])
-            self._check(L.optmc_lsmc_decide_async(ctx, sp, ld, n_paths, i, float(strike), ic,
-                                                  int(degree), gp, cp, st),
-                        "optmc_lsmc_decide_async")
-        self._check(L.optmc_lsmc_finish_async(ctx, n_paths, disc, cp, c_void_p(out.data_ptr()),
-                                              st), "optmc_lsmc_finish_async")
-        all_reduce(out[:3])
-        return out[:3].cpu().numpy()
+        for date in range(n_steps - 1, -1, -1):
+            self._check(self.lib.optmc_lsmc_step_async(
+                self.ctx, sp, ld, n_paths, n_steps, date, float(strike), 1 if is_call else 0,
+                disc, int(degree), cp, gp, self.stream()), "optmc_lsmc_step_async")
+            all_reduce(gram[date * LSMC_GRAM:(date + 1) * LSMC_GRAM])
+        return gram[:3].cpu().numpy()
 
     # -- diagnostics ----------------------------------------------------------
     def philox_raw(self, seed, n, c2=0, c3=0):

@@ -72,72 +72,6 @@ __global__ void __launch_bounds__(256) k_lsmc_load(const double *paths, int64_t 
     }
 }
 
-// ---- cashflow = payoff at T (american_mc_kernels.py:48-51) -----------------
-__global__ void __launch_bounds__(LSMC_THREADS) k_lsmc_begin(const double *last_row, int64_t n,
-                                                             double K, int is_call,
-                                                             double *cashflow) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
-        double s = last_row[p];
-        cashflow[p] = fmax(is_call ? s - K : K - s, 0.0);
-    }
-}
-
-// ---- per-date Gram accumulation (american_mc_kernels.py:54-69) -------------
-// cashflow *= disc for every path; in-the-money paths add to the power sums.
-// Per-block partials; the last block to finish sums them in fixed order
-// (deterministic) into gram[OPTMC_LSMC_GRAM].
-template <int DEG>
-__global__ void __launch_bounds__(LSMC_THREADS)
-k_lsmc_gram(const double *row, int64_t n, double K, double inv_K, int is_call, double disc,
-            double *cashflow, double *partials, unsigned int *ticket, double *gram) {
-    constexpr int NP = 2 * DEG + 1, NQ = DEG + 1, NV = NP + NQ;
-    __shared__ double scratch[NV * 32];
-    __shared__ bool last;
-    double acc[NV];
-#pragma unroll
-    for (int k = 0; k < NV; ++k) acc[k] = 0.0;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
-        double y = cashflow[p] * disc;                          // :54
-        cashflow[p] = y;
-        double s = row[p];
-        double iv = is_call ? s - K : K - s;                    // :57-60
-        if (iv > 0.0) {                                         // :62
-            double x = fma(s, inv_K, -1.0);
-            double pw = 1.0;
-#pragma unroll
-            for (int k = 0; k < NP; ++k) {
-                acc[k] += pw;
-                if (k < NQ) acc[NP + k] = fma(y, pw, acc[NP + k]);
-                pw *= x;
-            }
-        }
-    }
-    block_sum<NV>(acc, scratch);
-    double *mine = partials + (size_t)blockIdx.x * OPTMC_LSMC_GRAM;
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) mine[k] = acc[k];
-        __threadfence();
-        unsigned int t = atomicAdd(ticket, 1u);
-        last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (last) {
-        __threadfence();
-        // fixed-order sum over blocks: thread k owns entry k
-        if (threadIdx.x < NV) {
-            double s = 0.0;
-            for (unsigned int b = 0; b < gridDim.x; ++b)
-                s += __ldcg(partials + (size_t)b * OPTMC_LSMC_GRAM + threadIdx.x);
-            int k = threadIdx.x;
-            gram[k < NP ? k : 16 + (k - NP)] = s;
-        }
-        if (threadIdx.x == 0) *ticket = 0u;
-    }
-}
-
 // Solve the (d+1)x(d+1) normal equations built from the power sums.
 // Returns false when the date must be skipped: fewer in-the-money paths than
 // basis functions, or the equilibrated Cholesky meets a non-positive pivot --
@@ -183,59 +117,147 @@ __device__ inline bool lsmc_solve(const double *gram, int deg, double *beta) {
     return true;
 }
 
-// ---- exercise decision (american_mc_kernels.py:72-80) ----------------------
-__global__ void __launch_bounds__(LSMC_THREADS)
-k_lsmc_decide(const double *row, int64_t n, double K, double inv_K, int is_call, int deg,
-              const double *gram, double *cashflow) {
-    __shared__ double beta[8];
-    __shared__ bool ok;
-    if (threadIdx.x == 0) ok = lsmc_solve(gram, deg, beta);
-    __syncthreads();
-    if (!ok) return;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
-        double s = row[p];
-        double iv = is_call ? s - K : K - s;
-        if (iv > 0.0) {
-            double x = fma(s, inv_K, -1.0);
-            double cont = beta[deg];
-            for (int k = deg - 1; k >= 0; --k) cont = fma(cont, x, beta[k]);   // X @ beta, :73
-            if (iv > cont) cashflow[p] = iv;                                   // :75-80
+// ---- one fused pass per exercise date ---------------------------------------
+// Call for date i (i = n_steps-1 ... 0) does, for every path, in one sweep:
+//   1. (i == n_steps-1)  y = payoff at T                       american_mc_kernels.py:48-51
+//      (otherwise)       y = cashflow; exercise decision of date i+1 with the
+//                        regression solved from gram_in (the all-reduced power
+//                        sums of date i+1): y = intrinsic where intrinsic > fit   :72-80
+//   2. y *= exp(-r dt)                                          :54 (and :84 for i == 0)
+//   3. (i >= 1) cashflow = y; in-the-money paths of date i add to the power
+//      sums sum x^k, sum y x^k of x = S_i/K - 1                 :57-69
+//      (i == 0) accumulate sum y, sum y^2 instead: the final mean :84
+// so the cashflow vector is read and written once per date and row i+1, read by
+// the previous call, is normally still in the 126 MB L2.  Per-block partials;
+// the last block to finish adds them in fixed order into gram_out.
+template <int DEG>
+struct LsmcAcc {
+    static constexpr int NP = 2 * DEG + 1, NQ = DEG + 1, NV = NP + NQ;
+    double a[NV];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) a[k] = 0.0;
+    }
+};
+
+// One path of the fused sweep (see k_lsmc_step).  Returns the discounted
+// cashflow to store.
+template <int DEG, bool INIT, bool FINAL>
+__device__ __forceinline__ double lsmc_path(double y_in, double s_dec, double s_acc, bool use_fit,
+                                            const double *beta, double K, double inv_K, bool call,
+                                            double disc, LsmcAcc<DEG> &acc) {
+    double y;
+    if constexpr (INIT) {
+        y = fmax(call ? s_dec - K : K - s_dec, 0.0);                 // american_mc_kernels.py:48-51
+    } else {
+        y = y_in;
+        if (use_fit) {
+            double iv = call ? s_dec - K : K - s_dec;
+            if (iv > 0.0) {                                           // :62
+                double x = fma(s_dec, inv_K, -1.0);
+                double cont = beta[DEG];
+#pragma unroll
+                for (int k = DEG - 1; k >= 0; --k) cont = fma(cont, x, beta[k]);   // X @ beta, :73
+                if (iv > cont) y = iv;                                // :75-80
+            }
         }
     }
+    y *= disc;                                                        // :54 / :84
+    if constexpr (FINAL) {
+        acc.a[0] += 1.0;
+        acc.a[1] += y;
+        acc.a[2] = fma(y, y, acc.a[2]);
+    } else {
+        double iv = call ? s_acc - K : K - s_acc;                     // :57-60
+        if (iv > 0.0) {
+            double x = fma(s_acc, inv_K, -1.0);
+            double pw = 1.0;
+#pragma unroll
+            for (int k = 0; k < LsmcAcc<DEG>::NP; ++k) {
+                acc.a[k] += pw;
+                if (k < LsmcAcc<DEG>::NQ)
+                    acc.a[LsmcAcc<DEG>::NP + k] = fma(y, pw, acc.a[LsmcAcc<DEG>::NP + k]);
+                pw *= x;
+            }
+        }
+    }
+    return y;
 }
 
-// ---- final mean (american_mc_kernels.py:84) --------------------------------
+template <int DEG, bool INIT, bool FINAL>
 __global__ void __launch_bounds__(LSMC_THREADS)
-k_lsmc_finish(const double *cashflow, int64_t n, double disc, double *partials) {
-    __shared__ double scratch[2 * 32];
-    double acc[2] = {0.0, 0.0};
+k_lsmc_step(const double *__restrict__ row_dec,   // row of date i+1
+            const double *__restrict__ row_acc,   // row of date i (unused when FINAL)
+            int64_t n, double K, double inv_K, int is_call, double disc,
+            const double *__restrict__ gram_in, double *__restrict__ cashflow,
+            double *partials, unsigned int *ticket, double *gram_out) {
+    constexpr int NV = LsmcAcc<DEG>::NV, NP = LsmcAcc<DEG>::NP;
+    __shared__ double scratch[(NV > LSMC_THREADS / 32 ? NV : LSMC_THREADS / 32) * 32];
+    __shared__ double beta[8];
+    __shared__ bool ok, last;
+    if (threadIdx.x == 0) ok = INIT ? false : lsmc_solve(gram_in, DEG, beta);
+    __syncthreads();
+    const bool use_fit = ok, call = is_call != 0;
+    LsmcAcc<DEG> acc;
+    acc.clear();
+    // two paths per thread per trip: 16-byte loads and stores (rows are 16 B aligned:
+    // ld is even and the store base comes from the allocator)
+    const int64_t n2 = n >> 1;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
-        double y = cashflow[p] * disc;
-        acc[0] += y;
-        acc[1] = fma(y, y, acc[1]);
+    const double2 *dec2 = reinterpret_cast<const double2 *>(row_dec);
+    const double2 *acc2 = reinterpret_cast<const double2 *>(row_acc);
+    double2 *cf2 = reinterpret_cast<double2 *>(cashflow);
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n2; q += stride) {
+        double2 sd = (INIT || use_fit) ? __ldcs(dec2 + q) : make_double2(0.0, 0.0);
+        double2 y = INIT ? make_double2(0.0, 0.0) : cf2[q];
+        double2 sa = FINAL ? make_double2(0.0, 0.0) : acc2[q];
+        y.x = lsmc_path<DEG, INIT, FINAL>(y.x, sd.x, sa.x, use_fit, beta, K, inv_K, call, disc, acc);
+        y.y = lsmc_path<DEG, INIT, FINAL>(y.y, sd.y, sa.y, use_fit, beta, K, inv_K, call, disc, acc);
+        if (!FINAL) cf2[q] = y;
     }
-    block_sum<2>(acc, scratch);
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {             // odd tail
+        int64_t p = n - 1;
+        double y = lsmc_path<DEG, INIT, FINAL>(INIT ? 0.0 : cashflow[p], row_dec[p],
+                                               FINAL ? 0.0 : row_acc[p], use_fit, beta, K, inv_K,
+                                               call, disc, acc);
+        if (!FINAL) cashflow[p] = y;
+    }
+    block_sum<NV>(acc.a, scratch);
+    double *mine = partials + (size_t)blockIdx.x * OPTMC_LSMC_GRAM;
     if (threadIdx.x == 0) {
-        partials[(size_t)blockIdx.x * NPART + 0] = acc[0];
-        partials[(size_t)blockIdx.x * NPART + 1] = acc[1];
+#pragma unroll
+        for (int k = 0; k < NV; ++k) mine[k] = acc.a[k];
+        __threadfence();
+        unsigned int t = atomicAdd(ticket, 1u);
+        last = (t == gridDim.x - 1);
     }
-}
-
-__global__ void __launch_bounds__(256) k_lsmc_finish2(const double *partials, int n_blocks,
-                                                      double n, double *out) {
-    __shared__ double scratch[2 * 32];
-    double acc[2] = {0.0, 0.0};
-    for (int b = threadIdx.x; b < n_blocks; b += blockDim.x) {
-        acc[0] += partials[(size_t)b * NPART + 0];
-        acc[1] += partials[(size_t)b * NPART + 1];
-    }
-    block_sum<2>(acc, scratch);
-    if (threadIdx.x == 0) {
-        out[0] = n;
-        out[1] = acc[0];
-        out[2] = acc[1];
+    __syncthreads();
+    if (last) {
+        // Fixed-order sum of the per-block partials by the last block to finish:
+        // lane = entry, warp w takes blocks w, w+8, ...; eight loads in flight.
+        __threadfence();
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        constexpr int NW = LSMC_THREADS / 32;
+        double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (lane < NV) {
+            for (unsigned int b = warp; b < gridDim.x; b += NW * 8) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    unsigned int bb = b + NW * j;
+                    if (bb < gridDim.x)
+                        s[j] += __ldcg(partials + (size_t)bb * OPTMC_LSMC_GRAM + lane);
+                }
+            }
+        }
+        scratch[warp * 32 + lane] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+        __syncthreads();
+        if (warp == 0 && lane < NV) {
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) tot += scratch[w * 32 + lane];
+            gram_out[lane < NP ? lane : 16 + (lane - NP)] = tot;
+        }
+        if (threadIdx.x == 0) *ticket = 0u;
     }
 }
 

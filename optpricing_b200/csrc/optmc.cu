@@ -523,80 +523,58 @@ extern "C" int optmc_lsmc_load_async(optmc_ctx *ctx, const double *paths_dev, in
 }
 
 static int lsmc_grid(const optmc_ctx *ctx, int64_t n) {
-    int64_t need = (n + LSMC_THREADS - 1) / LSMC_THREADS;
-    return (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)ctx->sm_count * 8));
+    int64_t need = (n / 2 + LSMC_THREADS - 1) / LSMC_THREADS;   // two paths per thread per trip
+    return (int)std::max<int64_t>(1, std::min<int64_t>(need, (int64_t)ctx->sm_count * 4));
 }
 
-extern "C" int optmc_lsmc_begin_async(optmc_ctx *ctx, const double *store_dev, int64_t ld,
-                                      int64_t n_paths, int32_t n_steps, double strike,
-                                      int32_t is_call, double *cashflow_dev, void *stream) {
-    if (!ctx) return -2;
-    CK(cudaSetDevice(ctx->device));
-    if (!store_dev || !cashflow_dev) FAIL("null pointer");
-    if (n_paths < 1 || n_steps < 1 || ld < n_paths) FAIL("bad shape");
-    k_lsmc_begin<<<lsmc_grid(ctx, n_paths), LSMC_THREADS, 0, (cudaStream_t)stream>>>(
-        store_dev + (size_t)(n_steps - 1) * ld, n_paths, strike, is_call, cashflow_dev);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    return 0;
+template <int D, bool INIT>
+static void launch_step(bool final_, int grid, cudaStream_t st, const double *row_dec,
+                        const double *row_acc, int64_t n, double K, int is_call, double disc,
+                        const double *gram_in, double *cash, double *partials,
+                        unsigned int *ticket, double *gram_out) {
+    if (final_)
+        k_lsmc_step<D, INIT, true><<<grid, LSMC_THREADS, 0, st>>>(
+            row_dec, row_acc, n, K, 1.0 / K, is_call, disc, gram_in, cash, partials, ticket, gram_out);
+    else
+        k_lsmc_step<D, INIT, false><<<grid, LSMC_THREADS, 0, st>>>(
+            row_dec, row_acc, n, K, 1.0 / K, is_call, disc, gram_in, cash, partials, ticket, gram_out);
 }
 
-extern "C" int optmc_lsmc_gram_async(optmc_ctx *ctx, const double *store_dev, int64_t ld,
-                                     int64_t n_paths, int32_t date, double strike, int32_t is_call,
-                                     double discount, int32_t degree, double *cashflow_dev,
-                                     double *gram_dev, void *stream) {
+extern "C" int optmc_lsmc_step_async(optmc_ctx *ctx, const double *store_dev, int64_t ld,
+                                     int64_t n_paths, int32_t n_steps, int32_t date,
+                                     double strike, int32_t is_call, double discount,
+                                     int32_t degree, double *cashflow_dev, double *gram_dev,
+                                     void *stream) {
     if (!ctx) return -2;
     CK(cudaSetDevice(ctx->device));
     if (!store_dev || !cashflow_dev || !gram_dev) FAIL("null pointer");
     if (degree < 1 || degree > OPTMC_LSMC_MAX_DEGREE) FAIL("degree must be in 1..7");
-    if (date < 1 || n_paths < 1 || ld < n_paths) FAIL("bad shape");
-    const double *row = store_dev + (size_t)(date - 1) * ld;
+    if (n_paths < 1 || n_steps < 1 || ld < n_paths || (ld & 1)) FAIL("bad shape (ld must be even)");
+    if (date < 0 || date > n_steps - 1) FAIL("date must be in 0..n_steps-1");
+    if (!(strike > 0.0)) FAIL("strike must be positive");
+    const bool first = date == n_steps - 1;
+    const double *row_dec = store_dev + (size_t)date * ld;                     // date + 1
+    const double *row_acc = date >= 1 ? store_dev + (size_t)(date - 1) * ld : nullptr;
+    const double *gram_in = first ? nullptr : gram_dev + (size_t)(date + 1) * OPTMC_LSMC_GRAM;
+    double *gram_out = gram_dev + (size_t)date * OPTMC_LSMC_GRAM;
     double *partials = reinterpret_cast<double *>(ctx->scratch);
     int grid = lsmc_grid(ctx, n_paths);
     cudaStream_t st = (cudaStream_t)stream;
-    CK(cudaMemsetAsync(gram_dev, 0, sizeof(double) * OPTMC_LSMC_GRAM, st));
-#define GRAM(D)                                                                               \
-    case D:                                                                                   \
-        k_lsmc_gram<D><<<grid, LSMC_THREADS, 0, st>>>(row, n_paths, strike, 1.0 / strike,     \
-                                                      is_call, discount, cashflow_dev,        \
-                                                      partials, ctx->ticket, gram_dev);       \
+    CK(cudaMemsetAsync(gram_out, 0, sizeof(double) * OPTMC_LSMC_GRAM, st));
+#define STEP(D)                                                                                  \
+    case D:                                                                                      \
+        if (first)                                                                               \
+            launch_step<D, true>(final_, grid, st, row_dec, row_acc, n_paths, strike, is_call,   \
+                                 discount, gram_in, cashflow_dev, partials, ctx->ticket,         \
+                                 gram_out);                                                      \
+        else                                                                                     \
+            launch_step<D, false>(final_, grid, st, row_dec, row_acc, n_paths, strike, is_call,  \
+                                  discount, gram_in, cashflow_dev, partials, ctx->ticket,        \
+                                  gram_out);                                                     \
         break;
-    switch (degree) { GRAM(1) GRAM(2) GRAM(3) GRAM(4) GRAM(5) GRAM(6) GRAM(7) }
-#undef GRAM
-    ctx->launches++;
-    CK(cudaGetLastError());
-    return 0;
-}
-
-extern "C" int optmc_lsmc_decide_async(optmc_ctx *ctx, const double *store_dev, int64_t ld,
-                                       int64_t n_paths, int32_t date, double strike,
-                                       int32_t is_call, int32_t degree, const double *gram_dev,
-                                       double *cashflow_dev, void *stream) {
-    if (!ctx) return -2;
-    CK(cudaSetDevice(ctx->device));
-    if (!store_dev || !cashflow_dev || !gram_dev) FAIL("null pointer");
-    if (degree < 1 || degree > OPTMC_LSMC_MAX_DEGREE) FAIL("degree must be in 1..7");
-    if (date < 1 || n_paths < 1 || ld < n_paths) FAIL("bad shape");
-    const double *row = store_dev + (size_t)(date - 1) * ld;
-    k_lsmc_decide<<<lsmc_grid(ctx, n_paths), LSMC_THREADS, 0, (cudaStream_t)stream>>>(
-        row, n_paths, strike, 1.0 / strike, is_call, degree, gram_dev, cashflow_dev);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    return 0;
-}
-
-extern "C" int optmc_lsmc_finish_async(optmc_ctx *ctx, int64_t n_paths, double discount,
-                                       const double *cashflow_dev, double *out_dev, void *stream) {
-    if (!ctx) return -2;
-    CK(cudaSetDevice(ctx->device));
-    if (!cashflow_dev || !out_dev || n_paths < 1) FAIL("bad arguments");
-    double *partials = reinterpret_cast<double *>(ctx->scratch);
-    int grid = lsmc_grid(ctx, n_paths);
-    cudaStream_t st = (cudaStream_t)stream;
-    k_lsmc_finish<<<grid, LSMC_THREADS, 0, st>>>(cashflow_dev, n_paths, discount, partials);
-    ctx->launches++;
-    CK(cudaGetLastError());
-    k_lsmc_finish2<<<1, 256, 0, st>>>(partials, grid, (double)n_paths, out_dev);
+    const bool final_ = date == 0;
+    switch (degree) { STEP(1) STEP(2) STEP(3) STEP(4) STEP(5) STEP(6) STEP(7) }
+#undef STEP
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -609,22 +587,14 @@ extern "C" int optmc_lsmc(optmc_ctx *ctx, const double *store_dev, int64_t ld, i
     if (!ctx) return -2;
     if (!out_host) FAIL("out_host is null");
     const double disc = std::exp(-r * dt);                       // american_mc_kernels.py:54
-    int rc = optmc_lsmc_begin_async(ctx, store_dev, ld, n_paths, n_steps, strike, is_call,
-                                    cashflow_dev, stream);
-    if (rc) return rc;
-    for (int i = n_steps - 1; i >= 1; --i) {                     // :53
-        rc = optmc_lsmc_gram_async(ctx, store_dev, ld, n_paths, i, strike, is_call, disc, degree,
-                                   cashflow_dev, gram_dev, stream);
-        if (rc) return rc;
-        rc = optmc_lsmc_decide_async(ctx, store_dev, ld, n_paths, i, strike, is_call, degree,
-                                     gram_dev, cashflow_dev, stream);
+    for (int i = n_steps - 1; i >= 0; --i) {                     // :53 plus the final mean :84
+        int rc = optmc_lsmc_step_async(ctx, store_dev, ld, n_paths, n_steps, i, strike, is_call,
+                                       disc, degree, cashflow_dev, gram_dev, stream);
         if (rc) return rc;
     }
-    rc = optmc_lsmc_finish_async(ctx, n_paths, disc, cashflow_dev, ctx->moments_dev, stream);
-    if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    CK(cudaMemcpyAsync(ctx->moments_host, ctx->moments_dev, 3 * sizeof(double),
-                       cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->moments_host, gram_dev, 3 * sizeof(double), cudaMemcpyDeviceToHost,
+                       st));
     CK(cudaStreamSynchronize(st));
     memcpy(out_host, ctx->moments_host, 3 * sizeof(double));
     return 0;

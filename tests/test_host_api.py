@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "optmc.h")).read()
     header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
     declared = set(re.findall(r"\b(optmc_[a-z0-9_]+)\s*\(", header))
-    assert len(declared) >= 20
+    assert len(declared) >= 18
     lib = _engine.load_library()
     bound = {name for name, _, _ in _engine.SIGNATURES}
     assert declared == bound, declared ^ bound
