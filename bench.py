@@ -65,11 +65,12 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc = [], None
+        self.all_rows, self.rows, self.proc = [], [], None
+        self.t0 = self.t1 = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "200"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -78,16 +79,24 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.all_rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def begin(self):
+        """Start of the timed region: only samples taken from here on count."""
+        self.t0 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.t1 = time.perf_counter()
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except subprocess.TimeoutExpired:
             self.proc.kill()
+        t0 = self.t0 if self.t0 is not None else 0.0
+        # a sample printed at time t describes the interval just before t
+        self.rows = [r for t, r in self.all_rows if t0 + 0.01 <= t <= self.t1 + 0.03]
         sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names)
@@ -210,6 +219,7 @@ def run_ours(args, w):
             dist.all_reduce(moments)
 
     # ---- device-timed value -------------------------------------------------
+    sampler = ClockSampler(local) if rank == 0 else None    # started early: nvidia-smi is slow to start
     for i in range(args.warmup):
         device_step(1000 + i)
     barrier()
@@ -217,9 +227,10 @@ def run_ours(args, w):
           for _ in range(args.steps)]
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
            for _ in range(args.steps)]
-    sampler = ClockSampler(local) if rank == 0 else None
     launches0 = eng.launch_count()
     barrier()
+    if sampler:
+        sampler.begin()
     t_wall0 = time.perf_counter()
     for i in range(args.steps):
         flush.zero_()                                   # L2 flush, outside the step's events
