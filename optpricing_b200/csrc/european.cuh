@@ -10,6 +10,14 @@
 
 namespace optmc {
 
+#define OPTMC_PRAGMA_(x) _Pragma(#x)
+#define OPTMC_PRAGMA(x) OPTMC_PRAGMA_(x)
+#ifdef OPTMC_UNROLL
+#define OPTMC_UNROLL_STEPS OPTMC_PRAGMA(unroll OPTMC_UNROLL)
+#else
+#define OPTMC_UNROLL_STEPS
+#endif
+
 constexpr int EURO_THREADS = 256;
 #ifndef OPTMC_EURO_MIN_BLOCKS
 #define OPTMC_EURO_MIN_BLOCKS 3   // resident 256-thread blocks per SM the register budget is
@@ -28,44 +36,47 @@ struct EuroArgs {
     // Poisson constants for a draw covering 1 step ([0]) or 2 steps ([1])
     double pois_mu[2], pois_p0[2];
     uint32_t pois_p0_bits[2];
+    double pois_mu_path, pois_p0_path;   // lambda T and exp(-lambda T): whole-path jump count
     double *partials;   // [gridDim.x][NPART]
     double *terminal;   // optional [n_local * (anti ? 2 : 1)]
 };
 
-template <int KIND, int NIMPL>
-__device__ __forceinline__ double jump_size(uint4 w, const Consts &c, RngView tab) {
+// One jump size (rare path: CUDA math library, no table needed).
+template <int KIND>
+__device__ __forceinline__ double jump_size(uint4 w, const Consts &c) {
     if constexpr (KIND == OPTMC_KOU) {
         // up w.p. p_up: +Exp(eta1), else -Exp(eta2)   (mc_kernels.py:314-317)
-        double e;
-        if constexpr (NIMPL == 0)
-            e = -log(u01_open(w.x, w.y));
-        else
-            e = 0.5 * neg2_log_u(w.x, w.y, tab);
+        double e = -log(u01_open(w.x, w.y));
         return w.w < c.p_up_bits ? e * c.inv_eta1 : -e * c.inv_eta2;
     } else {
         double z1, z2;
-        normal_pair<NIMPL>(w.x, w.y, w.z, z1, z2, tab);
+        normal_pair_lib(w.x, w.y, w.z, z1, z2);
         return fma(c.sigma_j, z1, c.mu_j);           // N(mu_j, sigma_j)  (mc_kernels.py:111)
     }
 }
 
 // Jumps of one Poisson draw (rare path; the caller has already seen w >= p0_bits).
-// Counts are shared by the antithetic partner, sizes are fresh draws for it,
-// as in the reference's second pass (monte_carlo.py:247-255).
-template <int KIND, bool ANTI, int NIMPL, bool DEFER>
-__device__ __noinline__ void jumps_slow(State &sa, State &sb, uint32_t w, double mu, double p0,
-                                        const PhiloxKey &key, uint64_t id, uint32_t step,
-                                        const Consts &c, RngView tab) {
-    uint4 e = philox_draw(key, id, step, 0xFFu);
+// Counts are shared by the antithetic partner, sizes are fresh draws for it, as in
+// the reference's second pass (monte_carlo.py:247-255).  Returns the
+// summed log-jumps (x: the draw, y: its partner) so that no path state has to be
+// passed by reference.  Inlined on purpose: an out-of-line call would force the
+// kernel parameters (constants, Philox key) to be copied to local memory so that
+// their address can be taken.
+template <int KIND, bool ANTI>
+__device__ __forceinline__ double2 jumps_slow(uint32_t w, double mu, double p0, const PhiloxKey &key,
+                                           uint32_t id_lo, uint32_t id_hi, uint32_t step,
+                                           const Consts &c) {
+    uint4 e = philox4x32_10(make_uint4(id_lo, id_hi, step, 0xFFu), key);
     int n = poisson_slow(w, e.x, mu, p0);
+    double2 acc = make_double2(0.0, 0.0);
     for (int j = 0; j < n; ++j) {
-        apply_jump<KIND, DEFER>(sa, jump_size<KIND, NIMPL>(
-                                        philox_draw(key, id, step, 1u | ((uint32_t)j << 8)), c, tab));
+        acc.x += jump_size<KIND>(
+            philox4x32_10(make_uint4(id_lo, id_hi, step, 1u | ((uint32_t)j << 8)), key), c);
         if constexpr (ANTI)
-            apply_jump<KIND, DEFER>(sb, jump_size<KIND, NIMPL>(
-                                            philox_draw(key, id, step, 2u | ((uint32_t)j << 8)), c,
-                                            tab));
+            acc.y += jump_size<KIND>(
+                philox4x32_10(make_uint4(id_lo, id_hi, step, 2u | ((uint32_t)j << 8)), key), c);
     }
+    return acc;
 }
 
 // Simulate one draw over all steps.  SINK(step_index, sa, sb) is called after
@@ -76,6 +87,14 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
     const Consts &c = A.c;
     constexpr bool TWO = kind_two_factor(KIND);
     constexpr bool JUMPS = kind_jumps(KIND);
+    // Terminal-value kernels of the models whose jumps are additive in log space
+    // and independent of the state (Merton, Bates, Kou): the sum of the per-step
+    // Poisson(lambda dt) counts is Poisson(lambda T) and the jump sizes are iid, so
+    // the whole jump contribution to log S_T is drawn once after the last step --
+    // the same law as the reference's per-step draws, without a divergent branch
+    // inside the step loop.  SABR-jump (jumps act on S between Euler steps) and the
+    // path kernels keep the per-step form.
+    constexpr bool JUMPS_AT_END = JUMPS && !PER_STEP && KIND != OPTMC_SABR_JUMP;
     // terminal-only kernels of the log models defer the deterministic drift
     constexpr bool DEFER = !PER_STEP && !kind_sabr(KIND);
     init_state<KIND, DEFER>(sa, c);
@@ -84,37 +103,63 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
     // consecutive steps of a one-factor model (terminal-only kernels).
     constexpr int SPC = (TWO || PER_STEP) ? 1 : 2;
     const uint32_t id_lo = keep_u32((uint32_t)id), id_hi = keep_u32((uint32_t)(id >> 32));
+    OPTMC_UNROLL_STEPS
     for (int i = 0; i < A.n_steps; i += SPC) {
         uint4 w = philox4x32_10(make_uint4(id_lo, id_hi, (uint32_t)i, 0u), A.key);
-        double a, b;
-        normal_pair<NIMPL>(w.x, w.y, w.z, a, b, tab);
-        if constexpr (TWO) {
-            double z1 = fma(c.m12, b, c.m11 * a);
-            double cz = fma(c.m22, b, c.m21 * a);
-            step_diffusion<KIND, DEFER>(sa, z1, cz, c);
-            if constexpr (ANTI) step_diffusion<KIND, DEFER>(sb, -z1, -cz, c);
+        // (z1, z2): two-factor models -- the mixed, scaled increments (dW_S, xi-weighted
+        // dW_v); one-factor models -- sqrt(dt) N(0,1) for this step and the next.
+        double z1, z2;
+        if constexpr (NIMPL == 0) {
+            double a, b;
+            normal_pair_lib(w.x, w.y, w.z, a, b);
+            if constexpr (TWO) {
+                z1 = fma(c.m12, b, c.m11 * a);
+                z2 = fma(c.m22, b, c.m21 * a);
+            } else {
+                z1 = c.sqrt_dt * a;
+                z2 = c.sqrt_dt * b;
+            }
         } else {
-            double dw = c.sqrt_dt * a;
-            step_diffusion<KIND, DEFER>(sa, dw, 0.0, c);
-            if constexpr (ANTI) step_diffusion<KIND, DEFER>(sb, -dw, 0.0, c);
+            normal_pair_fast<TWO>(w.x, w.y, w.z, z1, z2, tab);
+        }
+        if constexpr (TWO) {
+            step_diffusion<KIND, DEFER>(sa, z1, z2, c, tab);
+            if constexpr (ANTI) step_diffusion<KIND, DEFER>(sb, -z1, -z2, c, tab);
+        } else {
+            step_diffusion<KIND, DEFER>(sa, z1, 0.0, c, tab);
+            if constexpr (ANTI) step_diffusion<KIND, DEFER>(sb, -z1, 0.0, c, tab);
             if constexpr (SPC == 2) {
                 if (i + 1 < A.n_steps) {
-                    double dw2 = c.sqrt_dt * b;
-                    step_diffusion<KIND, DEFER>(sa, dw2, 0.0, c);
-                    if constexpr (ANTI) step_diffusion<KIND, DEFER>(sb, -dw2, 0.0, c);
+                    step_diffusion<KIND, DEFER>(sa, z2, 0.0, c, tab);
+                    if constexpr (ANTI) step_diffusion<KIND, DEFER>(sb, -z2, 0.0, c, tab);
                 }
             }
         }
-        if constexpr (JUMPS) {
+        if constexpr (JUMPS && !JUMPS_AT_END) {
             // One Poisson draw for the steps this iteration covered; for the
             // additive-in-log one-factor models the split between the two
             // steps does not affect S_T.
-            const int two = (SPC == 2 && i + 1 < A.n_steps) ? 1 : 0;
-            if (poisson_maybe(w.w, A.pois_p0_bits[two]))
-                jumps_slow<KIND, ANTI, NIMPL, DEFER>(sa, sb, w.w, A.pois_mu[two], A.pois_p0[two],
-                                                     A.key, id, (uint32_t)i, c, tab);
+            const bool two = (SPC == 2 && i + 1 < A.n_steps);
+            if (__builtin_expect(poisson_maybe(w.w, two ? A.pois_p0_bits[1] : A.pois_p0_bits[0]), 0)) {
+                double2 J = jumps_slow<KIND, ANTI>(w.w, two ? A.pois_mu[1] : A.pois_mu[0],
+                                                   two ? A.pois_p0[1] : A.pois_p0[0], A.key, id_lo,
+                                                   id_hi, (uint32_t)i, c);
+                // additive in log space (mc_kernels.py:115,174,323); multiplicative on S for
+                // SABR-jump (:274): the product of exp(J_j) is exp of the sum
+                apply_jump<KIND, DEFER>(sa, J.x);
+                if constexpr (ANTI) apply_jump<KIND, DEFER>(sb, J.y);
+            }
         }
         if constexpr (PER_STEP) sink(i, sa, sb);
+    }
+    if constexpr (JUMPS_AT_END) {
+        uint4 e = philox4x32_10(make_uint4(id_lo, id_hi, 0xFFFFFFFFu, 0xFEu), A.key);
+        if (poisson_maybe(e.x, (uint32_t)fmin(floor(A.pois_p0_path * 4294967296.0), 4294967295.0))) {
+            double2 J = jumps_slow<KIND, ANTI>(e.x, A.pois_mu_path, A.pois_p0_path, A.key, id_lo,
+                                               id_hi, 0xFFFFFFFFu, c);
+            apply_jump<KIND, DEFER>(sa, J.x);
+            if constexpr (ANTI) apply_jump<KIND, DEFER>(sb, J.y);
+        }
     }
     finish_deferred<KIND, DEFER>(sa, c);
     if constexpr (ANTI) finish_deferred<KIND, DEFER>(sb, c);
@@ -126,13 +171,12 @@ struct NoSink {
 
 template <int KIND, bool ANTI, int NIMPL>
 __global__ void __launch_bounds__(EURO_THREADS, OPTMC_EURO_MIN_BLOCKS) k_european(const EuroArgs A) {
-    __shared__ RngTables tab;
+    __shared__ RngShared<kind_two_factor(KIND)> tab;
     RngView tv{0u};
     __shared__ double scratch[5 * 32];
-    if constexpr (NIMPL != 0) {
-        tv = load_rng_tables(&tab);
-        __syncthreads();
-    }
+    tv = fill_rng_shared(&tab, kind_two_factor(KIND) ? A.c.m11 : A.c.sqrt_dt, A.c.m12, A.c.m21,
+                         A.c.m22);
+    __syncthreads();
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < A.n_local; g += stride) {

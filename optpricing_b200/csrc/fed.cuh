@@ -111,6 +111,9 @@ __global__ void __launch_bounds__(FED_P) k_fed(const FedArgs A) {
 
     constexpr bool TWO = kind_two_factor(KIND);
     constexpr bool JUMPS = kind_jumps(KIND);
+    __shared__ MathShared math;                    // fast_log / fast_exp tables
+    const RngView tv = fill_math_shared(&math);
+    __syncthreads();
     const Consts &c = A.c;
     const int tid = threadIdx.x;
     const int64_t row0 = (int64_t)blockIdx.x * FED_P;
@@ -146,7 +149,7 @@ __global__ void __launch_bounds__(FED_P) k_fed(const FedArgs A) {
                 mix_fed(KIND, A.sign * t1[tid][j], A.sign * t2[tid][j], c, z1, cz);
             else
                 z1 = A.sign * t1[tid][j];
-            step_diffusion<KIND>(s, z1, cz, c);
+            step_diffusion<KIND>(s, z1, cz, c, tv);
             if constexpr (JUMPS) {
                 int n = cnt[tid][j];
                 if (n > 0) {
@@ -161,7 +164,7 @@ __global__ void __launch_bounds__(FED_P) k_fed(const FedArgs A) {
                     }
                 }
             }
-            if (A.paths) t1[tid][j] = kind_sabr(KIND) ? s.x : exp(s.x);   // path_kernels.py:34
+            if (A.paths) t1[tid][j] = step_spot(KIND, s, tv);          // path_kernels.py:34
         }
         if (A.paths) {
             __syncthreads();

@@ -26,26 +26,26 @@ struct StoreSink {
     int64_t ld, g, n_local;
     int kind;
     bool anti;
+    RngView tab;
     __device__ __forceinline__ void operator()(int i, const State &sa, const State &sb) const {
         double *row = store + (size_t)i * ld;
-        row[g] = terminal_spot(kind, sa);                       // path_kernels.py:34
-        if (anti) row[n_local + g] = terminal_spot(kind, sb);
+        row[g] = step_spot(kind, sa, tab);                      // path_kernels.py:34
+        if (anti) row[n_local + g] = step_spot(kind, sb, tab);
     }
 };
 
 template <int KIND, bool ANTI, int NIMPL>
 __global__ void __launch_bounds__(EURO_THREADS) k_lsmc_paths(const EuroArgs A, double *store,
                                                              int64_t ld) {
-    __shared__ RngTables tab;
+    __shared__ RngShared<kind_two_factor(KIND)> tab;
     RngView tv{0u};
-    if constexpr (NIMPL != 0) {
-        tv = load_rng_tables(&tab);
-        __syncthreads();
-    }
+    tv = fill_rng_shared(&tab, kind_two_factor(KIND) ? A.c.m11 : A.c.sqrt_dt, A.c.m12, A.c.m21,
+                         A.c.m22);
+    __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < A.n_local; g += stride) {
         State sa, sb;
-        StoreSink sink{store, ld, g, A.n_local, KIND, ANTI};
+        StoreSink sink{store, ld, g, A.n_local, KIND, ANTI, tv};
         simulate_draw<KIND, ANTI, NIMPL, true>(A, (uint64_t)(A.draw_offset + g), sa, sb, tv,
                                                sink);
     }

@@ -96,7 +96,11 @@ __device__ __forceinline__ void step_one_factor(State &s, double dw, const Const
 template <bool DEFER>
 __device__ __forceinline__ void step_heston(State &s, double z1, double czx, const Consts &c) {
     double vp = relu64(s.v);                       // v_pos = max(v, 0)
+#ifdef OPTMC_FAST_VSQRT
+    double sq = sqrt_nonneg_fast(vp);
+#else
     double sq = sqrt_nonneg(vp);                   // v_sqrt
+#endif
     if constexpr (DEFER) {
         s.x = fma(sq, z1, s.x);
         s.w += vp;
@@ -116,22 +120,25 @@ __device__ __forceinline__ void finish_deferred(State &s, const Consts &c) {
     }
 }
 
-__device__ __forceinline__ double sabr_pow(double s_pos, const Consts &c) {
+// s_pos ** beta (mc_kernels.py:211): exp(beta ln s) on the table-driven helpers,
+// with the exact special cases beta in {1, 0, 1/2}.
+__device__ __forceinline__ double sabr_pow(double s_pos, const Consts &c, RngView t) {
     switch (c.beta_mode) {
         case 1: return s_pos;
         case 2: return 1.0;
         case 3: return sqrt_nonneg(s_pos);
-        default: return pow(s_pos, c.beta);
+        default: return fast_exp(c.beta * fast_log(s_pos, t), t);
     }
 }
 
 // sabr_kernel mc_kernels.py:204-216, sabr_jump_kernel :251-258.
 // z1 = dw1; cz = rho*dw1 + rho_bar*dw2.
-__device__ __forceinline__ void step_sabr(State &s, double z1, double cz, const Consts &c) {
+__device__ __forceinline__ void step_sabr(State &s, double z1, double cz, const Consts &c,
+                                          RngView t) {
     double s_pos = fmax(s.x, 1e-8);
     double v_pos = relu64(s.v);
-    s.x += fma(v_pos * sabr_pow(s_pos, c), z1, c.rqc_dt * s_pos);
-    s.v = s.v * exp(fma(c.alpha, cz, c.neg_half_alpha2_dt));
+    s.x += fma(v_pos * sabr_pow(s_pos, c, t), z1, c.rqc_dt * s_pos);
+    s.v = s.v * fast_exp(fma(c.alpha, cz, c.neg_half_alpha2_dt), t);
 }
 
 // Fed mode: the kernel's own correlation step applied to the given increments.
@@ -143,11 +150,12 @@ __device__ __forceinline__ void mix_fed(int kind, double dw1, double dw2, const 
 }
 
 template <int KIND, bool DEFER = false>
-__device__ __forceinline__ void step_diffusion(State &s, double z1, double cz, const Consts &c) {
+__device__ __forceinline__ void step_diffusion(State &s, double z1, double cz, const Consts &c,
+                                               RngView t) {
     if constexpr (KIND == OPTMC_HESTON || KIND == OPTMC_BATES)
         step_heston<DEFER>(s, z1, cz, c);
     else if constexpr (kind_sabr(KIND))
-        step_sabr(s, z1, cz, c);
+        step_sabr(s, z1, cz, c, t);
     else
         step_one_factor<DEFER>(s, z1, c);
 }
@@ -166,7 +174,7 @@ __device__ __forceinline__ void init_state(State &s, const Consts &c) {
 template <int KIND, bool DEFER = false>
 __device__ __forceinline__ void apply_jump(State &s, double J) {
     if constexpr (KIND == OPTMC_SABR_JUMP)
-        s.x *= exp(J);
+        s.x *= exp(J);     // rare path: CUDA math library
     else if constexpr (DEFER && (KIND == OPTMC_MERTON || KIND == OPTMC_KOU))
         s.w += J;      // s.x holds the unscaled Brownian sum here
     else
@@ -175,6 +183,11 @@ __device__ __forceinline__ void apply_jump(State &s, double J) {
 
 __device__ __forceinline__ double terminal_spot(int kind, const State &s) {
     return kind_sabr(kind) ? s.x : exp(s.x);        // monte_carlo.py:257
+}
+
+// Spot after a step, for the path kernels (path_kernels.py:34: paths[:, i+1] = exp(log_s))
+__device__ __forceinline__ double step_spot(int kind, const State &s, RngView t) {
+    return kind_sabr(kind) ? s.x : fast_exp(s.x, t);
 }
 
 }  // namespace optmc

@@ -95,17 +95,18 @@ extern "C" int optmc_ctx_create(int device, optmc_ctx **out) {
                            cudaHostAllocDefault)) != cudaSuccess)
         return fail(e, "cudaHostAlloc");
     {
-        RngTables *h = new RngTables();
+        RngBase *h = new RngBase();
         const double pi = 3.14159265358979323846;
-        for (int i = 0; i < 128; ++i) {
-            double c = 1.0 + (i + 0.5) / 128.0;
+        for (int i = 0; i < LOG_N; ++i) {
+            double c = 1.0 + (i + 0.5) / LOG_N;
             h->logt[i] = make_double2(-2.0 / c, -2.0 * std::log(c) + 24.0 * std::log(2.0));
         }
+        for (int j = 0; j < 32; ++j) h->exp2t[j] = std::exp2(j / 32.0);
         for (int i = 0; i < TRIG_N; ++i) {
             double a = (i + 0.5) * (2.0 * pi / TRIG_N);
             h->trig[i] = make_double2(std::cos(a), std::sin(a));
         }
-        e = cudaMemcpyToSymbol(g_rng_tables, h, sizeof(RngTables));
+        e = cudaMemcpyToSymbol(g_rng_base, h, sizeof(RngBase));
         delete h;
         if (e != cudaSuccess) return fail(e, "cudaMemcpyToSymbol");
     }
@@ -223,6 +224,8 @@ static int make_consts(optmc_ctx *ctx, const optmc_model *m, double x0, double d
 }
 
 static void poisson_consts(EuroArgs &A) {
+    A.pois_mu_path = A.c.lam_dt * A.n_steps;
+    A.pois_p0_path = std::exp(-A.pois_mu_path);
     for (int two = 0; two < 2; ++two) {
         double mu = A.c.lam_dt * (two + 1);
         double p0 = std::exp(-mu);
@@ -251,7 +254,9 @@ static int euro_grid(optmc_ctx *ctx, K kernel, int64_t n_local) {
             per_sm = 1;
     }
     int64_t need = (n_local + threads - 1) / threads;
-    int64_t cap = (int64_t)ctx->sm_count * per_sm;
+    // twice the resident blocks: the second half back-fills SMs as the first drains
+    // (measured 3.5 % faster than exactly one resident wave, profiles/r01_sweep*.log)
+    int64_t cap = (int64_t)ctx->sm_count * per_sm * (ctx->euro_blocks_per_sm > 0 ? 1 : 2);
     return (int)std::max<int64_t>(1, std::min<int64_t>(std::min(need, cap), MAX_GRID));
 }
 
@@ -298,11 +303,11 @@ static int fill_euro_args(optmc_ctx *ctx, const optmc_model *model, const optmc_
     memset(A, 0, sizeof *A);
     rc = make_consts(ctx, model, x0, dt, sim->n_steps, sim->correlation, &A->c);
     if (rc) return rc;
-    poisson_consts(*A);
     philox_expand_key(sim->seed, &A->key);
     A->draw_offset = sim->draw_offset;
     A->n_local = sim->n_local;
     A->n_steps = sim->n_steps;
+    poisson_consts(*A);
     return 0;
 }
 
@@ -612,17 +617,18 @@ __global__ void k_philox_raw(PhiloxKey key, int64_t n, uint32_t c2, uint32_t c3,
 
 template <int NIMPL>
 __global__ void k_normals(PhiloxKey key, int64_t n, int step, double *out) {
-    __shared__ RngTables tab;
+    __shared__ RngShared<false> tab;
     RngView tv{0u};
-    if constexpr (NIMPL != 0) {
-        tv = load_rng_tables(&tab);
-        __syncthreads();
-    }
+    tv = fill_rng_shared(&tab, 1.0, 0.0, 0.0, 0.0);
+    __syncthreads();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint4 w = philox_draw(key, (uint64_t)i, (uint32_t)step, 0u);
     double a, b;
-    normal_pair<NIMPL>(w.x, w.y, w.z, a, b, tv);
+    if constexpr (NIMPL == 0)
+        normal_pair_lib(w.x, w.y, w.z, a, b);
+    else
+        normal_pair_fast<false>(w.x, w.y, w.z, a, b, tv);
     out[2 * i] = a;
     out[2 * i + 1] = b;
 }

@@ -113,34 +113,80 @@ __device__ __forceinline__ uint32_t keep_u32(uint32_t x) {
 
 // ---------------------------------------------------------------------------
 // Two N(0,1) from three Philox words (Box-Muller): radius from 64 bits, angle
-// from 32.  IMPL 0 = CUDA math library calls (baseline, kept for A/B checks);
-// IMPL 1 = hand-written for the fp64 pipe.
+// from 32.  IMPL 0 = CUDA math library calls (baseline, kept for A/B checks and
+// used on the rare jump-size path); IMPL 1 = hand-written for the fp64 pipe.
 // ---------------------------------------------------------------------------
+constexpr int LOG_N = 512;     // buckets of [1,2) for ln
 constexpr int TRIG_N = 1024;   // angle buckets over the full circle
-struct RngTables {
-    // ln on [1,2): bucket i has midpoint c_i = 1 + (i + .5)/128;
+
+// Host-filled base tables (one copy per context, in global memory).
+struct RngBase {
+    // bucket i has midpoint c_i = 1 + (i + .5)/512;
     //   x = -2 / c_i,  y = -2 ln c_i + 24 ln 2   (the 24 ln 2 pre-pays the exponent offset)
-    double2 logt[128];
+    double2 logt[LOG_N];
+    // 2^(j/32), j = 0..31
+    double exp2t[32];
     // angle bucket i of [0, 2 pi): a_i = (i + .5) 2 pi / 1024;  x = cos a_i, y = sin a_i
     double2 trig[TRIG_N];
 };
-constexpr int RNG_TABLE_VEC = (int)(sizeof(RngTables) / sizeof(double2));
+__device__ RngBase g_rng_base;
 
-__device__ RngTables g_rng_tables;   // filled once per context from the host (optmc.cu)
+// Shared-memory layout common to every kernel that uses the math helpers
+// (fast_log / fast_exp) -- the RNG tables extend it.
+struct MathShared {
+    double2 logt[LOG_N];
+    double exp2t[32];
+};
+constexpr uint32_t EXP_OFF = (uint32_t)sizeof(double2) * LOG_N;
+constexpr uint32_t TRIG_OFF = EXP_OFF + 32u * (uint32_t)sizeof(double);
 
-// Shared-memory copy of the tables, addressed by a 32-bit shared-window offset so
-// that lookups are a single LDS.128 with no generic-address arithmetic.
-struct RngView {
-    uint32_t base;   // shared address of RngTables
+// Per-block shared-memory tables.  The trig rows are specialised per launch:
+//   MIXED = false: (s cos a_i, s sin a_i) with a scale s (sqrt(dt) for the
+//                  one-factor models, 1 for plain normals);
+//   MIXED = true : the 2x2 mixing matrix M of the two-factor models applied to
+//                  the rotation basis, (A1, B1, A2, B2) with
+//                  A_r = M_r1 cos a_i + M_r2 sin a_i,  B_r = M_r2 cos a_i - M_r1 sin a_i,
+//                  so that  M (cos(a_i + d), sin(a_i + d))^T = (A_r cos d + B_r sin d)_r
+//                  and the correlated, scaled increments need no further arithmetic.
+template <bool MIXED>
+struct RngShared {
+    MathShared math;
+    double2 trig[TRIG_N * (MIXED ? 2 : 1)];
 };
 
-__device__ __forceinline__ RngView load_rng_tables(RngTables *t) {
-    const double2 *src = reinterpret_cast<const double2 *>(&g_rng_tables);
-    double2 *dst = reinterpret_cast<double2 *>(t);
-    for (int i = threadIdx.x; i < RNG_TABLE_VEC; i += blockDim.x) dst[i] = src[i];
+// 32-bit shared-window address of the tables: lookups are one LDS.128 each.
+struct RngView {
+    uint32_t base;
+};
+
+__device__ __forceinline__ RngView fill_math_shared(MathShared *t) {
+    for (int i = threadIdx.x; i < LOG_N; i += blockDim.x) t->logt[i] = g_rng_base.logt[i];
+    for (int i = threadIdx.x; i < 32; i += blockDim.x) t->exp2t[i] = g_rng_base.exp2t[i];
     RngView v;
     v.base = keep_u32((uint32_t)__cvta_generic_to_shared(t));
     return v;
+}
+
+template <bool MIXED>
+__device__ __forceinline__ RngView fill_rng_shared(RngShared<MIXED> *t, double m11, double m12,
+                                                   double m21, double m22) {
+    RngView v = fill_math_shared(&t->math);
+    for (int i = threadIdx.x; i < TRIG_N; i += blockDim.x) {
+        double2 cs = g_rng_base.trig[i];
+        if constexpr (MIXED) {
+            t->trig[2 * i] = make_double2(fma(m12, cs.y, m11 * cs.x), fma(m12, cs.x, -(m11 * cs.y)));
+            t->trig[2 * i + 1] = make_double2(fma(m22, cs.y, m21 * cs.x), fma(m22, cs.x, -(m21 * cs.y)));
+        } else {
+            t->trig[i] = make_double2(m11 * cs.x, m11 * cs.y);
+        }
+    }
+    return v;
+}
+
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double r;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r) : "r"(addr));
+    return r;
 }
 
 __device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
@@ -150,13 +196,19 @@ __device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
 }
 
 // Polynomial coefficients, read straight from the constant bank.
-//   -2 ln(1 + r) with r = -r'/2:  r' + r'^2/4 + r'^3/12 + r'^4/32 + r'^5/80 + r'^6/192
-__constant__ double C_LOG[5] = {1.0 / 192.0, 1.0 / 80.0, 1.0 / 32.0, 1.0 / 12.0, 0.25};
+//   -2 ln(1 + r) with r = -r'/2, |r'| <= 2^-9:  r' + r'^2/4 + r'^3/12 + r'^4/32  (+ 3.6e-16)
+// A DFMA can take one operand from the constant bank / an immediate; an immediate
+// must have its low 32 bits zero.  Each two-constant FMA below therefore pairs one
+// exactly-representable "short" literal with one constant-bank value, so that no
+// coefficient has to live in (and be read from) a vector register.
+__constant__ double C_1_12 = 1.0 / 12.0;
 __constant__ double C_N2LN2 = -1.3862943611198906188;        // -2 ln 2
-__constant__ double C_TRIG[4] = {1.0 / 24.0, -0.5, 1.0 / 120.0, -1.0 / 6.0};
-// offset inside an angle bucket: d = (j + .5) h / 2^22 - h/2, j = 22 random bits, h = 2 pi / 1024
-__constant__ double C_FINE[2] = {6.283185307179586477 / 1024.0 / 4194304.0,
-                                 (0.5 / 4194304.0 - 0.5) * (6.283185307179586477 / 1024.0)};
+__constant__ double C_1_24 = 1.0 / 24.0;
+__constant__ double C_N1_6 = -1.0 / 6.0;
+// 1/120 rounded to 20 mantissa bits (rel. 6e-8): it multiplies d^5 <= 3e-13
+#define OPTMC_SHORT_1_120 0x1.11111p-7
+// offset inside an angle bucket: d = j' h / 2^23 with j' odd in (-2^22, 2^22), h = 2 pi / 1024
+__constant__ double C_FINE = 6.283185307179586477 / 1024.0 / 8388608.0;
 
 // -2 ln u for a uniform u in (0,1) built from the words (lo, hi):
 //   hi[31:20] exponent bits: k = their leading zeros, u in [2^-(k+1), 2^-k)
@@ -164,11 +216,9 @@ __constant__ double C_FINE[2] = {6.283185307179586477 / 1024.0 / 4194304.0,
 // If all 12 exponent bits are zero (p = 2^-12) the exponent continues into the
 // mantissa bits (slow path), so u stays exactly uniform on its 2^-64 grid.
 __device__ __forceinline__ double neg2_log_poly(double m, double2 tb, double kfac) {
-    double r = fma(m, tb.x, 2.0);                  // r' = -2 (m / c - 1), |r'| <= 2^-7
-    double p = fma(r, C_LOG[0], C_LOG[1]);
-    p = fma(p, r, C_LOG[2]);
-    p = fma(p, r, C_LOG[3]);
-    p = fma(p, r, C_LOG[4]);
+    double r = fma(m, tb.x, 2.0);                  // r' = -2 (m / c - 1)
+    double p = fma(r, 0.03125, C_1_12);
+    p = fma(p, r, 0.25);
     p = fma(p, r, 1.0);
     // -2 ln u = 2 (k+1) ln2 - 2 ln m;  tb.y carries 24 ln2, kfac = 11 - k (top set bit index)
     return fma(p, r, fma(kfac, C_N2LN2, tb.y));
@@ -182,7 +232,7 @@ __device__ __noinline__ double neg2_log_u_tail(uint32_t lo, uint32_t hi, RngView
     uint64_t frac = ((x << k) << 1) & 0xFFFFFFFFFFFFFull;
     uint64_t mbits = 0x3FF0000000000000ull | frac;
     double m = __longlong_as_double((long long)mbits);
-    double2 tb = lds_f64x2(t.base + (uint32_t)((mbits >> 45) & 127) * 16u);
+    double2 tb = lds_f64x2(t.base + (uint32_t)((mbits >> 43) & (LOG_N - 1)) * 16u);
     return neg2_log_poly(m, tb, (double)(11 - (12 + k)));
 }
 
@@ -190,33 +240,84 @@ __device__ __forceinline__ double neg2_log_u(uint32_t lo, uint32_t hi, RngView t
     uint32_t e = hi >> 20;
     if (__builtin_expect(e == 0u, 0)) return neg2_log_u_tail(lo, hi, t);
     double m = __hiloint2double(0x3FF00000 | (hi & 0xFFFFF), lo);
-    double2 tb = lds_f64x2(t.base + ((hi >> 9) & 0x7F0u));
+    double2 tb = lds_f64x2(t.base + ((hi >> 7) & ((LOG_N - 1) * 16u)));
     return neg2_log_poly(m, tb, (double)top_bit(e));
 }
 
-template <int IMPL>
-__device__ __forceinline__ void normal_pair(uint32_t w0, uint32_t w1, uint32_t w2, double &z1,
-                                            double &z2, RngView t) {
-    if constexpr (IMPL == 0) {
-        double rad = sqrt(-2.0 * log(u01_open(w0, w1)));
-        double s, c;
-        sincospi(((double)w2 + 0.5) * 0x1.0p-31, &s, &c);  // angle = 2 pi (w2 + .5) / 2^32
-        z1 = rad * c;
-        z2 = rad * s;
+// ln s for a positive normal double s: exponent from the bit pattern, ln of the
+// mantissa from the same table/polynomial as above.  7 fp64-pipe instructions
+// (CUDA's log: ~30 plus special-case branches); abs. error <= 4e-15.
+__constant__ double C_LN2 = 0.69314718055994530942;
+__device__ __forceinline__ double fast_log(double s, RngView t) {
+    int hi = __double2hiint(s);
+    double m = __hiloint2double((hi & 0xFFFFF) | 0x3FF00000, __double2loint(s));
+    double2 tb = lds_f64x2(t.base + (((uint32_t)hi >> 7) & ((LOG_N - 1) * 16u)));
+    double r = fma(m, tb.x, 2.0);
+    double p = fma(r, 0.03125, C_1_12);
+    p = fma(p, r, 0.25);
+    p = fma(p, r, 1.0);
+    double q = fma(p, r, tb.y);                       // -2 ln m + 24 ln 2
+    return fma((double)((hi >> 20) - 1023 + 12), C_LN2, -0.5 * q);
+}
+
+// e^x for |x| < 700: x = (32 k + j) ln2/32 + r, |r| <= ln2/64;
+// e^x = 2^k * 2^(j/32) * e^r with a degree-6 polynomial.  11 fp64-pipe
+// instructions (CUDA's exp: ~18 plus range branches); rel. error <= 5e-16 for |x| <= 10.
+__constant__ double C_EXP[6] = {46.166241308446828384,          // 32 / ln 2
+                                -0.021660849392498290395,        // -(ln2/32) high part (27 bits)
+                                0.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0};
+#define OPTMC_LN2_32_HI 0x1.62e42fcp-6     /* ln2/32 with the low 26 mantissa bits cleared */
+#define OPTMC_LN2_32_LO (0.021660849392498290395 - OPTMC_LN2_32_HI)
+#define OPTMC_SHORT_1_720 0x1.6c16cp-10    /* 1/720 to 20 bits: multiplies r^6 <= 1.6e-12 */
+__device__ __forceinline__ double fast_exp(double x, RngView t) {
+    const double MAGIC = 6755399441055744.0;          // 1.5 * 2^52: low word = rint(value)
+    double tt = fma(x, C_EXP[0], MAGIC);
+    int n = __double2loint(tt);
+    double nd = tt - MAGIC;
+    double r = fma(nd, -OPTMC_LN2_32_HI, x);
+    r = fma(nd, -OPTMC_LN2_32_LO, r);
+    double p = fma(r, OPTMC_SHORT_1_720, C_EXP[3]);
+    p = fma(p, r, C_EXP[4]);
+    p = fma(p, r, C_EXP[5]);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    double y = p * lds_f64(t.base + EXP_OFF + ((uint32_t)(n & 31) << 3));
+    return __hiloint2double(__double2hiint(y) + ((n >> 5) << 20), __double2loint(y));
+}
+
+// Baseline pair by the CUDA math library (also the jump-size path).
+__device__ __forceinline__ void normal_pair_lib(uint32_t w0, uint32_t w1, uint32_t w2, double &z1,
+                                                double &z2) {
+    double rad = sqrt(-2.0 * log(u01_open(w0, w1)));
+    double s, c;
+    sincospi(((double)w2 + 0.5) * 0x1.0p-31, &s, &c);  // angle = 2 pi (w2 + .5) / 2^32
+    z1 = rad * c;
+    z2 = rad * s;
+}
+
+// Hand-written pair.  angle = a_i + d: the top 10 bits of w2 pick the bucket, the
+// low 22 bits the offset d in (-h/2, h/2).
+//   MIXED = false: (z1, z2) = s R (cos, sin)(angle)
+//   MIXED = true : (z1, z2) = M R (cos, sin)(angle)^T
+template <bool MIXED>
+__device__ __forceinline__ void normal_pair_fast(uint32_t w0, uint32_t w1, uint32_t w2, double &z1,
+                                                 double &z2, RngView t) {
+    double rad = sqrt_nonneg_fast(neg2_log_u(w0, w1, t));
+    int fine = (int)((w2 & 0x3FFFFFu) * 2u) - 0x3FFFFF;            // odd, in (-2^22, 2^22)
+    double d = (double)fine * C_FINE;
+    double d2 = d * d;
+    double cd = fma(fma(d2, C_1_24, -0.5), d2, 1.0);                         // cos d
+    double sd = fma(fma(d2, OPTMC_SHORT_1_120, C_N1_6), d2, 1.0) * d;        // sin d
+    if constexpr (MIXED) {
+        uint32_t row = t.base + TRIG_OFF + ((w2 >> 17) & ((TRIG_N - 1) * 32u));
+        double2 r1 = lds_f64x2(row), r2 = lds_f64x2(row + 16u);
+        z1 = rad * fma(r1.x, cd, r1.y * sd);
+        z2 = rad * fma(r2.x, cd, r2.y * sd);
     } else {
-        double rad = sqrt_nonneg_fast(neg2_log_u(w0, w1, t));
-        // angle = a_i + d: the top 10 bits pick one of 1024 buckets of the circle
-        // (cos, sin of its midpoint from the table), the low 22 bits the offset d
-        // in (-h/2, h/2); rotate the table entry by d.
-        double2 cs = lds_f64x2(t.base + (uint32_t)sizeof(double2) * 128u + ((w2 >> 18) & 0x3FF0u));
-        double d = fma((double)(w2 & 0x3FFFFFu), C_FINE[0], C_FINE[1]);
-        double d2 = d * d;
-        double cd = fma(fma(d2, C_TRIG[0], C_TRIG[1]), d2, 1.0);       // cos d
-        double sd = fma(fma(d2, C_TRIG[2], C_TRIG[3]), d2, 1.0) * d;   // sin d
-        double cx = fma(cs.x, cd, -(cs.y * sd));
-        double sx = fma(cs.y, cd, cs.x * sd);
-        z1 = rad * cx;
-        z2 = rad * sx;
+        double2 cs = lds_f64x2(t.base + TRIG_OFF + ((w2 >> 18) & ((TRIG_N - 1) * 16u)));
+        z1 = rad * fma(cs.x, cd, -(cs.y * sd));
+        z2 = rad * fma(cs.y, cd, cs.x * sd);
     }
 }
 
@@ -230,7 +331,7 @@ __device__ __forceinline__ int poisson_slow(uint32_t w, uint32_t extra, double m
     double u = ((double)(((uint64_t)w << 32 | extra) >> 11) + 0.5) * 0x1.0p-53;
     double p = p0, cdf = p0;
     int n = 0;
-    while (u > cdf && n < 64) {
+    while (u > cdf && n < 1024) {
         ++n;
         p *= mu / (double)n;
         cdf += p;
