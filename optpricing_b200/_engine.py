@@ -226,13 +226,15 @@ class Engine:
                                                   c_void_p(moments.data_ptr()), tptr,
                                                   self.stream()), "optmc_european_async")
 
-    def payoff_sweep(self, terminal, n_local, antithetic, strikes, is_call):
+    def payoff_sweep(self, terminal, n_local, antithetic, strikes, is_call, to_host=True):
         k, c, kp, cp = self._contracts(strikes, is_call)
         mom = self.buffer("sweep_moments", k.size * NMOM)
         self._check(self.lib.optmc_payoff_sweep_async(self.ctx, c_void_p(terminal.data_ptr()),
                                                       int(n_local), 1 if antithetic else 0,
                                                       k.size, kp, cp, c_void_p(mom.data_ptr()),
                                                       self.stream()), "optmc_payoff_sweep_async")
+        if not to_host:
+            return mom
         return mom[: k.size * NMOM].cpu().numpy().reshape(k.size, NMOM)
 
     # -- fed-draw kernels ---------------------------------------------------

@@ -35,7 +35,7 @@ from optpricing_b200 import _engine
 from optpricing_b200.atoms import is_call as _is_call
 from optpricing_b200.models import model_kind
 
-from .base import BaseTechnique, GreekMixin, IVMixin, PricingResult
+from .base import BaseTechnique, GreekMixin, IVMixin, PricingResult, crn
 from .kernels import mc_kernels
 
 _KERNELS = {
@@ -120,7 +120,14 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
         self._hint = None
 
     # ------------------------------------------------------------------ price
-    def price(self, option, stock, model, rate, **kwargs: Any) -> PricingResult:
+    def price(self, option, stock, model, rate, **kwargs: Any):
+        """
+        Price one option -> PricingResult (monte_carlo.py:65-116).  A list / tuple /
+        array of options (the ``Option | np.ndarray`` the reference's ABC hints at,
+        base_technique.py:25-32) is priced by ``price_many`` -> np.ndarray.
+        """
+        if isinstance(option, (list, tuple, np.ndarray)):
+            return self.price_many(option, stock, model, rate, **kwargs)
         if not (model.supports_sde or getattr(model, "is_pure_levy", False)):
             raise TypeError(f"Model '{model.name}' does not support simulation.")
         S0, K, T = stock.spot, option.strike, option.maturity
@@ -248,6 +255,130 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
                     args[key] = -args[key]
             ST = np.concatenate([ST, kernel(**args)])
         return ST if sabr else np.exp(ST)
+
+    # ------------------------------------------------- batched contracts
+    def _philox_sde(self, model) -> bool:
+        return (self.rng_mode == "philox" and model.supports_sde
+                and not getattr(model, "has_exact_sampler", False)
+                and not getattr(model, "is_pure_levy", False)
+                and model_kind(model) != "dupire")
+
+    def _sweep(self, model, S0, r, q, T, strikes, calls, seed=None, **kwargs):
+        """
+        ONE simulation to maturity T, payoff moments for every (strike, type):
+        the terminal spots stay in HBM (8 B per path) and a sweep kernel reduces
+        them per contract.  Returns (moments[n, 6], kind, seed).
+        """
+        eng = _engine.get_engine()
+        kind = model_kind(model)
+        num_draws = self.n_paths // 2 if self.antithetic else self.n_paths
+        if seed is None:
+            seed = int(self.rng.integers(0, 2**63 - 1, dtype=np.int64))
+        mdl = _engine.make_model(kind, model.params, r, q, v0=kwargs.get("v0"))
+        corr = (_engine.CORR_REFERENCE_EUROPEAN if self.correlation == "reference"
+                else _engine.CORR_INDEPENDENT_DRAWS)
+        rank, world, all_reduce = self._group()
+        off, cnt = shard_draws(num_draws, rank, world)
+        sim = eng.make_sim(float(S0), T, num_draws, self.n_steps, self.antithetic, seed, corr,
+                           off, cnt)
+        strikes = np.ascontiguousarray(strikes, dtype=np.float64)
+        calls = np.ascontiguousarray(calls, dtype=np.int32)
+        term = eng.buffer("terminal", cnt * (2 if self.antithetic else 1))
+        out = np.empty((strikes.size, _engine.NMOM))
+        for lo in range(0, strikes.size, 64):
+            ks, cs = strikes[lo:lo + 64], calls[lo:lo + 64]
+            if lo == 0:
+                if all_reduce is None:
+                    out[lo:lo + ks.size] = eng.european(mdl, sim, ks, cs, terminal=term)
+                    continue
+                dev = eng.buffer("moments_many", 64 * _engine.NMOM)
+                eng.european_async(mdl, sim, ks, cs, dev, terminal=term)
+            else:                                   # further chunks reuse the stored terminals
+                if all_reduce is None:
+                    out[lo:lo + ks.size] = eng.payoff_sweep(term, cnt, self.antithetic, ks, cs)
+                    continue
+                dev = eng.payoff_sweep(term, cnt, self.antithetic, ks, cs, to_host=False)
+            all_reduce(dev[: ks.size * _engine.NMOM])
+            out[lo:lo + ks.size] = dev[: ks.size * _engine.NMOM].cpu().numpy().reshape(-1, 6)
+        return out, kind, seed
+
+    def price_many(self, options, stock, model, rate, **kwargs: Any) -> np.ndarray:
+        """
+        Prices of many European contracts on one underlying.  Contracts sharing a
+        maturity share one simulation (BASELINE config 3: 64 strikes x 4
+        maturities = 4 simulations instead of 256).  Equivalent to calling
+        ``price`` per contract with common random numbers within a maturity.
+        """
+        options = list(options)
+        if not self._philox_sde(model):
+            return np.array([self.price(o, stock, model, rate, **kwargs).price for o in options])
+        prices = np.empty(len(options))
+        self.last_stats_many = [None] * len(options)
+        by_T: dict[float, list[int]] = {}
+        for i, o in enumerate(options):
+            by_T.setdefault(float(o.maturity), []).append(i)
+        S0, q = stock.spot, stock.dividend
+        for T, idx in by_T.items():
+            r = rate.get_rate(T)
+            mom, kind, seed = self._sweep(model, S0, r, q, T, [options[i].strike for i in idx],
+                                          [1 if _is_call(options[i]) else 0 for i in idx],
+                                          **kwargs)
+            c_mean = control_mean(kind, model.params, S0, r, q, T, self.n_steps)
+            for row, i in zip(mom, idx):
+                st = summarize(row, r, T, c_mean)
+                st["seed"] = seed
+                self.last_stats_many[i] = st
+                use_cv = self.control_variate and "cv_price" in st
+                prices[i] = st["cv_price"] if use_cv else st["price"]
+        return prices
+
+    # ------------------------------------------------------ fused greeks (SURVEY 8 f1)
+    _LOG_KINDS = ("bsm", "heston", "merton", "bates", "kou")
+
+    def _scaling_greeks_ok(self, model) -> bool:
+        """Spot / rate bumps can be read off ONE simulation: the log-Euler models'
+        log S_T is (log S_0 + r T) plus a term that depends on neither."""
+        return (self._philox_sde(model) and model_kind(model) in self._LOG_KINDS
+                and not self.control_variate)
+
+    def _bumped_prices(self, option, stock, model, rate, spot_factors=(), rate_shifts=(), **kw):
+        """
+        Prices under S0 -> f S0 and r -> r + h on common random numbers, from one
+        simulation: S_T(f S0, r + h) = f e^{hT} S_T(S0, r) path by path, so
+          P(f, h) = f e^{-rT} E[(S_T - K')^+]  with  K' = K / (f e^{hT})
+        (puts alike).  This is what GreekMixin's re-pricings compute
+        (greek_mixin.py:59-73,105-122,249-265), without re-simulating.
+        """
+        S0, K, T = stock.spot, option.strike, option.maturity
+        r, q = rate.get_rate(T), stock.dividend
+        call = _is_call(option)
+        scen = [(f, 0.0) for f in spot_factors] + [(1.0, h) for h in rate_shifts]
+        strikes = [K / (f * math.exp(h * T)) for f, h in scen]
+        with crn(self.rng):                       # greeks do not advance the stream
+            mom, _, _ = self._sweep(model, S0, r, q, T, strikes, [1 if call else 0] * len(scen),
+                                    **kw)
+        disc = math.exp(-r * T)
+        return [f * disc * m[1] / m[0] for (f, h), m in zip(scen, mom)]
+
+    def delta(self, option, stock, model, rate, h_frac: float = 1e-3, **kwargs: Any) -> float:
+        if not self._scaling_greeks_ok(model):
+            return super().delta(option, stock, model, rate, h_frac, **kwargs)
+        up, dn = self._bumped_prices(option, stock, model, rate, (1 + h_frac, 1 - h_frac), **kwargs)
+        return (up - dn) / (2 * stock.spot * h_frac)
+
+    def gamma(self, option, stock, model, rate, h_frac: float = 1e-3, **kw: Any) -> float:
+        if not self._scaling_greeks_ok(model):
+            return super().gamma(option, stock, model, rate, h_frac, **kw)
+        up, mid, dn = self._bumped_prices(option, stock, model, rate,
+                                          (1 + h_frac, 1.0, 1 - h_frac), **kw)
+        h = stock.spot * h_frac
+        return (up - 2 * mid + dn) / (h * h)
+
+    def rho(self, option, stock, model, rate, h: float = 1e-4, **kw: Any) -> float:
+        if not self._scaling_greeks_ok(model):
+            return super().rho(option, stock, model, rate, h, **kw)
+        up, dn = self._bumped_prices(option, stock, model, rate, (), (h, -h), **kw)
+        return (up - dn) / (2 * h)
 
     def _simulate_levy_terminal(self, model, S0: float, r: float, q: float, T: float):
         """
