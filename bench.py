@@ -43,7 +43,7 @@ sys.path.insert(0, ROOT)
 # fp64-pipe thread-instructions per path-step of the dominant kernel, counted
 # from the SASS of its step loop (tools/sass_stats.py; see profiles/ and
 # DESIGN.md "Roofline").  Pair-step count / 2 for the antithetic kernels.
-I64_PER_PATH_STEP = {"heston": 23.0, "bsm": 8.0}
+I64_PER_PATH_STEP = {"heston": 20.0, "bsm": 6.0}
 # Algorithmic flops per path-step (antithetic pairs share the draws)
 FLOPS_PER_PATH_STEP = {"heston": 28.0, "bsm": 6.0}
 
@@ -342,16 +342,117 @@ def run_ours(args, w):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------
+# secondary workloads (BASELINE configs 3-5): through the public API only
+# ---------------------------------------------------------------------------
+def run_secondary(args, name):
+    import numpy as np
+    import torch
+
+    import optpricing_b200 as ob
+    from optpricing_b200 import _engine
+
+    torch.cuda.set_device(0)
+    eng = _engine.get_engine(0)
+    stock, rate = ob.Stock(spot=100.0, dividend=0.01), ob.Rate(rate=0.05)
+    extra = {}
+    if name == "c3":
+        model = ob.BatesModel()
+        strikes = np.linspace(70, 130, 64)
+        mats = (0.25, 0.5, 1.0, 2.0)
+        techs = {T: ob.MonteCarloTechnique(n_paths=1 << 22, n_steps=int(252 * T), seed=7) for T in mats}
+        opts = {T: [ob.Option(float(k), T, ob.OptionType.CALL) for k in strikes] for T in mats}
+        units = sum((1 << 22) * int(252 * T) for T in mats)
+        label = ("C3 Bates European strike sweep, 64 strikes x 4 maturities, 2^22 paths per maturity, "
+                 "n_steps = 252 T, one simulation per maturity (price_many)")
+
+        def step():
+            return [techs[T].price_many(opts[T], stock, model, rate) for T in mats]
+        extra["contracts_per_step"] = 256
+    elif name == "c4":
+        model = ob.BSMModel({"sigma": 0.2})
+        aput = ob.Option(strike=110.0, maturity=1.0, option_type=ob.OptionType.PUT)
+        tech = ob.AmericanMonteCarloTechnique(n_paths=1 << 22, n_steps=50, seed=42, lsm_degree=3)
+        units = (1 << 22) * 50
+        label = "C4 American put Longstaff-Schwartz (GBM), 2^22 paths x 50 exercise dates, cubic basis"
+
+        def step():
+            return tech.price(aput, stock, model, rate).price
+    elif name == "c5":
+        call = ob.Option(strike=100.0, maturity=1.0, option_type=ob.OptionType.CALL)
+        models = (ob.SABRJumpModel(), ob.KouModel())
+        techs = [ob.MonteCarloTechnique(n_paths=1 << 24, n_steps=365, seed=11, control_variate=True)
+                 for _ in models]
+        units = 2 * (1 << 24) * 365
+        label = ("C5 SABR-with-jumps and Kou European call, 2^24 paths x 365 steps each, control "
+                 "variate (price only; the bump greeks re-price 2x each)")
+
+        def step():
+            return [t.price(call, stock, m, rate).price for t, m in zip(techs, models)]
+    else:
+        raise SystemExit(name)
+    for _ in range(max(args.warmup, 3)):
+        out = step()
+    torch.cuda.synchronize()
+    launches0 = eng.launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    a.record()
+    for _ in range(args.steps):
+        out = step()
+    b.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    dev_ms = a.elapsed_time(b)
+    line = {"metric": "path-steps/sec (fp64)", "value": args.steps * units / (dev_ms * 1e-3),
+            "unit": "path-steps/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": label, "l2": "path store / terminal buffers exceed L2 or no HBM "
+                                                "input; no flush between steps", **extra},
+            "e2e": {"value": args.steps * units / wall, "unit": "path-steps/s",
+                    "h2d_bytes_per_step": 212, "d2h_bytes_per_step": 48, "api": "technique.price"},
+            "gpu_launches": eng.launch_count() - launches0,
+            "result_sample": (float(np.ravel(out)[0]) if not isinstance(out, float) else out)}
+    if name == "c4":
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak = peaks.get("hbm_gbs", 6650.0)
+        store, ld = eng.lsmc_store(1 << 22, 50)
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            eng.lsmc(store, ld, 1 << 22, 50, 110.0, False, 0.05, 1.0 / 50, 3)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        ach = (1 << 22) * 50 * 32 / (best * 1e-3) / 1e9
+        line["roofline"] = {"bound": "hbm", "kernel": "k_lsmc_step<3> x 50 dates (induction only)",
+                            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                            "traffic": None, "per_unit": "32 B per path-date (SURVEY 8 d4)",
+                            "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
+                            "kernel_ms": best}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=("ours", "reference"))
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c3", "c4", "c5"])
     ap.add_argument("--scaling", default="weak", choices=("weak", "strong"))
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.workload in ("c3", "c4", "c5"):
+        if args.impl == "reference":
+            raise SystemExit("--impl reference is defined for the c1/c2 workloads")
+        return run_secondary(args, args.workload)
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, w)
