@@ -178,7 +178,10 @@ int optmc_payoff_sweep_async(optmc_ctx *ctx, const double *terminal_dev, int64_t
  *                                [date] (:57-69; X'X and X'y of :72 are read off them)
  *                              date == 0: slot [0] = n, sum cf, sum cf^2       (:84)
  *                            With several ranks, all-reduce slot [date] between calls.
- *   optmc_lsmc               the whole loop for one GPU, one sync, host result
+ *   optmc_lsmc               the whole loop for one GPU, one sync, host result;
+ *                            by default a single persistent launch (one block
+ *                            per SM, a grid barrier per date) running the same
+ *                            per-path arithmetic as optmc_lsmc_step_async
  *                            out_host[0..2] = n, sum, sum of squares of the
  *                            discounted cashflows
  *
@@ -219,7 +222,9 @@ int optmc_fp64_peak(optmc_ctx *ctx, int64_t iters, double *fma_per_sec, double *
 
 /* Tunables: "normals_impl" (0 = CUDA math library Box-Muller, 1 = hand-written,
    default 1), "euro_blocks_per_sm" (0 = occupancy API decides), "euro_threads"
-   (threads per block of the European kernel: 64, 128 or 256). */
+   (threads per block of the European kernel: 64, 128 or 256), "lsmc_mode"
+   (optmc_lsmc: 1 = every exercise date in one persistent cooperative launch,
+   default; 0 = one optmc_lsmc_step_async launch per date). */
 int optmc_set_int(optmc_ctx *ctx, const char *key, int64_t value);
 
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */

@@ -76,43 +76,58 @@ __global__ void __launch_bounds__(256) k_lsmc_load(const double *paths, int64_t 
 // Returns false when the date must be skipped: fewer in-the-money paths than
 // basis functions, or the equilibrated Cholesky meets a non-positive pivot --
 // the counterpart of the LinAlgError the reference swallows (:71-82).
-__device__ inline bool lsmc_solve(const double *gram, int deg, double *beta) {
-    const int m = deg + 1;
+// Fully unrolled for the degree, so the factor lives in registers, and every
+// division by a pivot is a multiplication by its reciprocal square root: one
+// thread solves the system on the critical path between two exercise dates.
+template <int DEG>
+__device__ __forceinline__ bool lsmc_solve(const double *gram, double *beta) {
+    constexpr int m = DEG + 1;
     const double *P = gram;        // P[k] = sum x^k (P[0] = n_itm)
     const double *Q = gram + 16;   // Q[k] = sum y x^k
     if (!(P[0] >= (double)m)) return false;
-    double L[8][8], d[8], rhs[8];
+    double L[m][m], d[m], rhs[m], inv[m];
+#pragma unroll
     for (int a = 0; a < m; ++a) {
         double diag = P[2 * a];
         if (!(diag > 0.0)) return false;
-        d[a] = 1.0 / sqrt(diag);
+        d[a] = rsqrt(diag);
     }
+#pragma unroll
     for (int a = 0; a < m; ++a) {
         rhs[a] = Q[a] * d[a];
+#pragma unroll
         for (int b = 0; b <= a; ++b) L[a][b] = P[a + b] * d[a] * d[b];
     }
+#pragma unroll
     for (int j = 0; j < m; ++j) {
         double s = L[j][j];
-        for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
+#pragma unroll
+        for (int k = 0; k < j; ++k) s = fma(-L[j][k], L[j][k], s);
         if (!(s > 1e-13)) return false;
-        double lj = sqrt(s);
-        L[j][j] = lj;
+        inv[j] = rsqrt(s);
+#pragma unroll
         for (int i = j + 1; i < m; ++i) {
             double t = L[i][j];
-            for (int k = 0; k < j; ++k) t -= L[i][k] * L[j][k];
-            L[i][j] = t / lj;
+#pragma unroll
+            for (int k = 0; k < j; ++k) t = fma(-L[i][k], L[j][k], t);
+            L[i][j] = t * inv[j];
         }
     }
+#pragma unroll
     for (int i = 0; i < m; ++i) {
         double t = rhs[i];
-        for (int k = 0; k < i; ++k) t -= L[i][k] * rhs[k];
-        rhs[i] = t / L[i][i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) t = fma(-L[i][k], rhs[k], t);
+        rhs[i] = t * inv[i];
     }
+#pragma unroll
     for (int i = m - 1; i >= 0; --i) {
         double t = rhs[i];
-        for (int k = i + 1; k < m; ++k) t -= L[k][i] * rhs[k];
-        rhs[i] = t / L[i][i];
+#pragma unroll
+        for (int k = i + 1; k < m; ++k) t = fma(-L[k][i], rhs[k], t);
+        rhs[i] = t * inv[i];
     }
+#pragma unroll
     for (int a = 0; a < m; ++a) beta[a] = rhs[a] * d[a];
     return true;
 }
@@ -142,25 +157,26 @@ struct LsmcAcc {
 
 // One path of the fused sweep (see k_lsmc_step).  Returns the discounted
 // cashflow to store.
+// Branch-free on purpose: within a warp some lanes are almost always in the
+// money, so a branch saves nothing, while straight-line code lets the compiler
+// interleave the independent paths a thread handles per trip.  Out-of-the-money
+// paths enter the power sums with weight 0.
 template <int DEG, bool INIT, bool FINAL>
 __device__ __forceinline__ double lsmc_path(double y_in, double s_dec, double s_acc, bool use_fit,
                                             const double *beta, double K, double inv_K, bool call,
                                             double disc, LsmcAcc<DEG> &acc) {
     double y;
+    const double iv_dec = call ? s_dec - K : K - s_dec;
     if constexpr (INIT) {
-        y = fmax(call ? s_dec - K : K - s_dec, 0.0);                 // american_mc_kernels.py:48-51
+        y = fmax(iv_dec, 0.0);                                        // american_mc_kernels.py:48-51
     } else {
-        y = y_in;
-        if (use_fit) {
-            double iv = call ? s_dec - K : K - s_dec;
-            if (iv > 0.0) {                                           // :62
-                double x = fma(s_dec, inv_K, -1.0);
-                double cont = beta[DEG];
+        const double x = fma(s_dec, inv_K, -1.0);
+        double cont = beta[DEG];
 #pragma unroll
-                for (int k = DEG - 1; k >= 0; --k) cont = fma(cont, x, beta[k]);   // X @ beta, :73
-                if (iv > cont) y = iv;                                // :75-80
-            }
-        }
+        for (int k = DEG - 1; k >= 0; --k) cont = fma(cont, x, beta[k]);   // X @ beta, :73
+        // in the money (:62) and intrinsic above the fitted continuation (:75-80)
+        const bool ex = use_fit && iv_dec > 0.0 && iv_dec > cont;
+        y = ex ? iv_dec : y_in;
     }
     y *= disc;                                                        // :54 / :84
     if constexpr (FINAL) {
@@ -168,18 +184,19 @@ __device__ __forceinline__ double lsmc_path(double y_in, double s_dec, double s_
         acc.a[1] += y;
         acc.a[2] = fma(y, y, acc.a[2]);
     } else {
-        double iv = call ? s_acc - K : K - s_acc;                     // :57-60
-        if (iv > 0.0) {
-            double x = fma(s_acc, inv_K, -1.0);
-            double pw = 1.0;
+        constexpr int NP = LsmcAcc<DEG>::NP, NQ = LsmcAcc<DEG>::NQ;
+        const double iv = call ? s_acc - K : K - s_acc;               // :57-60
+        const double w = iv > 0.0 ? 1.0 : 0.0;
+        const double x = fma(s_acc, inv_K, -1.0);
+        double pw[NP];
+        pw[0] = w;
+        pw[1] = w * x;
 #pragma unroll
-            for (int k = 0; k < LsmcAcc<DEG>::NP; ++k) {
-                acc.a[k] += pw;
-                if (k < LsmcAcc<DEG>::NQ)
-                    acc.a[LsmcAcc<DEG>::NP + k] = fma(y, pw, acc.a[LsmcAcc<DEG>::NP + k]);
-                pw *= x;
-            }
-        }
+        for (int k = 2; k < NP; ++k) pw[k] = pw[k / 2] * pw[k - k / 2];   // w^2 = w: still w x^k
+#pragma unroll
+        for (int k = 0; k < NP; ++k) acc.a[k] += pw[k];
+#pragma unroll
+        for (int k = 0; k < NQ; ++k) acc.a[NP + k] = fma(y, pw[k], acc.a[NP + k]);
     }
     return y;
 }
@@ -195,7 +212,7 @@ k_lsmc_step(const double *__restrict__ row_dec,   // row of date i+1
     __shared__ double scratch[(NV > LSMC_THREADS / 32 ? NV : LSMC_THREADS / 32) * 32];
     __shared__ double beta[8];
     __shared__ bool ok, last;
-    if (threadIdx.x == 0) ok = INIT ? false : lsmc_solve(gram_in, DEG, beta);
+    if (threadIdx.x == 0) ok = INIT ? false : lsmc_solve<DEG>(gram_in, beta);
     __syncthreads();
     const bool use_fit = ok, call = is_call != 0;
     LsmcAcc<DEG> acc;
@@ -259,6 +276,262 @@ k_lsmc_step(const double *__restrict__ row_dec,   // row of date i+1
         }
         if (threadIdx.x == 0) *ticket = 0u;
     }
+}
+
+
+// ---- the whole induction in ONE launch (single GPU) --------------------------
+// k_lsmc_step costs one launch, one memset and one serial "last block adds the
+// partials" tail per exercise date; at 2^22 paths that overhead is as large as
+// the sweep itself.  k_lsmc_persistent keeps one block resident on every SM for
+// all dates (cooperative launch):
+//   * each block owns a fixed slice of paths: its cashflows are touched by no
+//     other SM and stay in L2, its rows stream from HBM once per date;
+//   * the per-date exchange needs no separate barrier: every block publishes its
+//     NV partial sums as self-validating 16-byte slots (lo, tag, hi, tag) -- the
+//     flag-in-data scheme of NCCL's LL protocol -- and every block polls all G
+//     rows and adds them in the same fixed order, so all blocks solve identical
+//     normal equations one memory round trip after the last block has published.
+// Per-path arithmetic is lsmc_path, the same code k_lsmc_step runs.
+constexpr int LSMC_P_STRIDE = 24;           // slots per block row (NV <= 23)
+// One 512-thread block per SM: 128 registers per thread hold the 3d+2 running sums
+// next to the loads in flight without spilling (1024 threads x 64 registers
+// spilled in the sweep and measured 7 % slower at degree 3).
+__host__ __device__ constexpr int lsmc_p_threads(int) { return 512; }
+#ifndef OPTMC_LSMC_UNROLL
+#define OPTMC_LSMC_UNROLL 4
+#endif
+// trips in flight per thread
+__host__ __device__ constexpr int lsmc_p_unroll(int deg) { return deg <= 3 ? OPTMC_LSMC_UNROLL : 2; }
+
+struct LsmcPersistArgs {
+    const double *store;
+    int64_t ld, n;
+    int n_steps;
+    double K, inv_K, disc;
+    int is_call;
+    double *cashflow;
+    uint4 *slots;              // [2][gridDim.x][LSMC_P_STRIDE], flag-carrying partials
+    uint32_t nonce;            // per-launch tag prefix
+    unsigned int *error;       // set to 1 if an exchange times out
+    double *gram;              // [n_steps][OPTMC_LSMC_GRAM], written by block 0
+    unsigned long long *timing;   // optional [n_steps + 1][4] globaltimer stamps of block 0 (ns)
+};
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ void ll_store(uint4 *slot, double v, uint32_t tag) {
+    uint32_t lo = (uint32_t)__double2loint(v), hi = (uint32_t)__double2hiint(v);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(slot), "r"(lo), "r"(tag),
+                 "r"(hi), "r"(tag)
+                 : "memory");
+}
+
+__device__ __forceinline__ uint4 ll_peek(const uint4 *slot) {
+    uint4 w;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
+                 : "l"(slot)
+                 : "memory");
+    return w;
+}
+
+// `w` is a first look at the slot; spin until both halves carry `tag`.  False on timeout.
+__device__ __forceinline__ bool ll_wait(const uint4 *slot, uint32_t tag, uint4 w, double &v) {
+    unsigned int spins = 0;
+    while (w.y != tag || w.w != tag) {
+        if (++spins > (1u << 24)) return false;     // ~ seconds: a lost block, never the normal path
+        w = ll_peek(slot);
+    }
+    v = __hiloint2double((int)w.z, (int)w.x);
+    return true;
+}
+
+// One date's sweep over this block's slice of path pairs [q0, q1): U trips in
+// flight per thread, i.e. up to 3 U 16-byte loads before the first use.
+// Measured alternatives that were slower at 2^22 x 50 (profiles/r01_lsmc_persistent.md):
+// shared-memory-resident cashflows (+3 %), and a TMA (cp.async.bulk + mbarrier)
+// ring for the two store rows (2.07 ms vs 1.06 ms: without per-load eviction
+// hints the rows and the cashflows no longer stay in L2).
+template <int DEG, bool INIT, bool FINAL>
+__device__ __forceinline__ void lsmc_sweep(const double *__restrict__ row_dec,
+                                           const double *__restrict__ row_acc,
+                                           double *__restrict__ cashflow, int64_t q0, int64_t q1,
+                                           bool use_fit, const double *beta, double K, double inv_K,
+                                           bool call, double disc, LsmcAcc<DEG> &acc) {
+    constexpr int T = lsmc_p_threads(DEG), U = lsmc_p_unroll(DEG);
+    const double2 *dec2 = reinterpret_cast<const double2 *>(row_dec);
+    const double2 *acc2 = reinterpret_cast<const double2 *>(row_acc);
+    double2 *cf2 = reinterpret_cast<double2 *>(cashflow);
+    const double2 zero = make_double2(0.0, 0.0);
+    const bool need_dec = INIT || use_fit;
+    for (int64_t qa = q0 + threadIdx.x; qa < q1; qa += (int64_t)U * T) {
+        double2 sd[U], sa[U], y[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t q = qa + (int64_t)u * T;
+            const bool in = u == 0 || q < q1;
+            sd[u] = (in && need_dec) ? __ldcs(dec2 + q) : zero;
+            y[u] = (in && !INIT) ? cf2[q] : zero;
+            sa[u] = (in && !FINAL) ? acc2[q] : zero;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t q = qa + (int64_t)u * T;
+            if (u == 0 || q < q1) {
+                y[u].x = lsmc_path<DEG, INIT, FINAL>(y[u].x, sd[u].x, sa[u].x, use_fit, beta, K,
+                                                     inv_K, call, disc, acc);
+                y[u].y = lsmc_path<DEG, INIT, FINAL>(y[u].y, sd[u].y, sa[u].y, use_fit, beta, K,
+                                                     inv_K, call, disc, acc);
+                if (!FINAL) cf2[q] = y[u];
+            }
+        }
+    }
+}
+
+// Sum P (16 or 32) values per lane over the warp with P - 1 (+1) shuffles instead
+// of 5 P: at every halving step a lane keeps one half of its values and trades
+// the other half with its partner.  Afterwards v[0] of lane l is the warp total of
+// entry l (P = 32) or l / 2 (P = 16).  Fixed order, hence reproducible.
+template <int P>
+__device__ __forceinline__ void warp_transpose_sum(double (&v)[P], int lane) {
+    static_assert(P == 16 || P == 32, "P must be 16 or 32");
+    int m = 16;
+#pragma unroll
+    for (int c = P / 2; c >= 1; c >>= 1, m >>= 1) {
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int i = 0; i < c; ++i) {
+            const double send = up ? v[i] : v[i + c];
+            const double keep = up ? v[i + c] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+        }
+    }
+    if constexpr (P == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+template <int DEG>
+__global__ void __launch_bounds__(lsmc_p_threads(DEG), 1)
+k_lsmc_persistent(const LsmcPersistArgs A) {
+    constexpr int NV = LsmcAcc<DEG>::NV, NP = LsmcAcc<DEG>::NP;
+    constexpr int T = lsmc_p_threads(DEG), NW = T / 32;
+    constexpr int GPAD = 161;      // >= gridDim.x (checked on the host), odd: no bank conflicts
+    constexpr int SLOTS = 4;       // polls in flight per thread
+    constexpr int P = NV <= 16 ? 16 : 32;
+    __shared__ double scratch[NV * 32];
+    __shared__ double vals[NV * GPAD];
+    __shared__ double tot[OPTMC_LSMC_GRAM];
+    __shared__ double beta[8];
+    __shared__ bool ok;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned int G = gridDim.x;
+    const bool call = A.is_call != 0;
+    // this block's slice of path pairs
+    const int64_t n2 = A.n >> 1;
+    const int64_t chunk = (n2 + G - 1) / G;
+    const int64_t q0 = min((int64_t)blockIdx.x * chunk, n2);
+    const int64_t q1 = min(q0 + chunk, n2);
+    const bool odd_owner = (A.n & 1) && blockIdx.x == 0 && threadIdx.x == 0;
+    unsigned int epoch = 0;
+    bool timed_out = false;
+    const bool stamp = A.timing && blockIdx.x == 0 && threadIdx.x == 0;
+    for (int date = A.n_steps - 1; date >= -1; --date) {
+        const bool first = date == A.n_steps - 1;
+        if (stamp) A.timing[(size_t)(date + 1) * 4 + 0] = globaltimer_ns();
+        if (!first) {
+            // totals of the previous sweep.  All threads poll: slot i = b * NV + e goes to
+            // thread i mod T, every thread has its (<= SLOTS) loads in flight at once, and
+            // the values land in shared memory as vals[e][b]; then warp e adds entry e
+            // over the blocks in a fixed order (lane-strided partial sums, shuffle tree).
+            const uint32_t tag = (A.nonce << 12) | ((epoch - 1) & 0xFFFu);
+            const uint4 *src = A.slots + (size_t)((epoch - 1) & 1u) * G * LSMC_P_STRIDE;
+            const unsigned int n_slots = G * NV;
+            if (threadIdx.x < OPTMC_LSMC_GRAM) tot[threadIdx.x] = 0.0;   // unused slots read as zero
+            for (unsigned int i0 = 0; i0 < n_slots; i0 += T * SLOTS) {
+                uint4 w[SLOTS];
+#pragma unroll
+                for (int j = 0; j < SLOTS; ++j) {
+                    const unsigned int i = i0 + j * T + threadIdx.x;
+                    if (i < n_slots) w[j] = ll_peek(src + (size_t)(i / NV) * LSMC_P_STRIDE + i % NV);
+                }
+#pragma unroll
+                for (int j = 0; j < SLOTS; ++j) {
+                    const unsigned int i = i0 + j * T + threadIdx.x;
+                    if (i < n_slots) {
+                        const unsigned int b = i / NV, e = i % NV;
+                        double v = 0.0;
+                        if (!ll_wait(src + (size_t)b * LSMC_P_STRIDE + e, tag, w[j], v))
+                            timed_out = true;
+                        vals[e * GPAD + b] = v;
+                    }
+                }
+            }
+            __syncthreads();
+            if (stamp) A.timing[(size_t)(date + 1) * 4 + 1] = globaltimer_ns();
+            for (int e = warp; e < NV; e += NW) {
+                double t = 0.0;
+                for (unsigned int b = lane; b < G; b += 32) t += vals[e * GPAD + b];
+                t = warp_sum(t);
+                if (lane == 0) tot[e < NP ? e : 16 + (e - NP)] = t;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                if (blockIdx.x == 0 && lane < OPTMC_LSMC_GRAM)
+                    A.gram[(size_t)(date + 1) * OPTMC_LSMC_GRAM + lane] = tot[lane];
+                if (lane == 0) ok = date >= 0 ? lsmc_solve<DEG>(tot, beta) : false;
+            }
+            __syncthreads();
+            if (date < 0) break;
+        }
+        if (stamp) A.timing[(size_t)(date + 1) * 4 + 2] = globaltimer_ns();
+        const bool use_fit = first ? false : ok;
+        const bool final_ = date == 0;
+        const double *row_dec = A.store + (size_t)date * A.ld;
+        const double *row_acc = final_ ? nullptr : A.store + (size_t)(date - 1) * A.ld;
+        LsmcAcc<DEG> acc;
+        acc.clear();
+#define OPTMC_SWEEP(I, F)                                                                       \
+    do {                                                                                        \
+        lsmc_sweep<DEG, I, F>(row_dec, row_acc, A.cashflow, q0, q1, use_fit, beta, A.K,         \
+                              A.inv_K, call, A.disc, acc);                                      \
+        if (odd_owner) {                                                                        \
+            const int64_t p = A.n - 1;                                                          \
+            double y = lsmc_path<DEG, I, F>(I ? 0.0 : A.cashflow[p], row_dec[p],                \
+                                            F ? 0.0 : row_acc[p], use_fit, beta, A.K, A.inv_K,  \
+                                            call, A.disc, acc);                                 \
+            if (!F) A.cashflow[p] = y;                                                          \
+        }                                                                                       \
+    } while (0)
+        if (first && final_) OPTMC_SWEEP(true, true);
+        else if (first) OPTMC_SWEEP(true, false);
+        else if (final_) OPTMC_SWEEP(false, true);
+        else OPTMC_SWEEP(false, false);
+#undef OPTMC_SWEEP
+        if (stamp) A.timing[(size_t)(date + 1) * 4 + 3] = globaltimer_ns();
+        // block totals: transposed warp reduction, then warp e adds entry e over the warps
+        // and its lane 0 publishes it
+        {
+            double v[P];
+#pragma unroll
+            for (int k = 0; k < P; ++k) v[k] = k < NV ? acc.a[k] : 0.0;
+            warp_transpose_sum<P>(v, lane);
+            const int e = P == 32 ? lane : lane >> 1;
+            if (e < NV && (P == 32 || (lane & 1) == 0)) scratch[e * 32 + warp] = v[0];
+        }
+        __syncthreads();
+        for (int e = warp; e < NV; e += NW) {
+            double t = lane < NW ? scratch[e * 32 + lane] : 0.0;
+            t = warp_sum(t);
+            if (lane == 0)
+                ll_store(A.slots + ((size_t)(epoch & 1u) * G + blockIdx.x) * LSMC_P_STRIDE + e, t,
+                         (A.nonce << 12) | (epoch & 0xFFFu));
+        }
+        ++epoch;
+    }
+    if (timed_out) atomicExch(A.error, 1u);
 }
 
 }  // namespace optmc

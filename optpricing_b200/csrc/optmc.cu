@@ -23,12 +23,16 @@ struct optmc_ctx {
     int normals_impl = 1;       // 0: CUDA math library, 1: hand-written (philox.cuh)
     int euro_blocks_per_sm = 0; // 0: occupancy API decides
     int euro_threads = EURO_THREADS;
+    int lsmc_mode = 1;          // 1: one persistent launch for all dates, 0: one launch per date
     int64_t launches = 0;
     unsigned char *scratch = nullptr;  // device
     size_t scratch_bytes = 0;
     double *moments_dev = nullptr;     // SWEEP_MAX * OPTMC_NMOM
     double *moments_host = nullptr;    // pinned
     unsigned int *ticket = nullptr;    // device, zero between launches
+    uint4 *lsmc_slots = nullptr;       // device: flag-carrying partial sums of k_lsmc_persistent
+    uint32_t lsmc_nonce = 0;
+    unsigned long long *lsmc_timing = nullptr;   // diagnostics: see optmc_set_ptr("lsmc_timing")
     std::string err;
 };
 
@@ -91,6 +95,11 @@ extern "C" int optmc_ctx_create(int device, optmc_ctx **out) {
         return fail(e, "cudaMalloc");
     if ((e = cudaMalloc(&ctx->ticket, 64)) != cudaSuccess) return fail(e, "cudaMalloc");
     if ((e = cudaMemset(ctx->ticket, 0, 64)) != cudaSuccess) return fail(e, "cudaMemset");
+    {
+        const size_t bytes = sizeof(uint4) * 2 * (size_t)ctx->sm_count * LSMC_P_STRIDE;
+        if ((e = cudaMalloc(&ctx->lsmc_slots, bytes)) != cudaSuccess) return fail(e, "cudaMalloc");
+        if ((e = cudaMemset(ctx->lsmc_slots, 0, bytes)) != cudaSuccess) return fail(e, "cudaMemset");
+    }
     if ((e = cudaHostAlloc(&ctx->moments_host, sizeof(double) * SWEEP_MAX * OPTMC_NMOM,
                            cudaHostAllocDefault)) != cudaSuccess)
         return fail(e, "cudaHostAlloc");
@@ -129,12 +138,17 @@ extern "C" void optmc_ctx_destroy(optmc_ctx *ctx) {
     cudaFree(ctx->scratch);
     cudaFree(ctx->moments_dev);
     cudaFree(ctx->ticket);
+    cudaFree(ctx->lsmc_slots);
     cudaFreeHost(ctx->moments_host);
     delete ctx;
 }
 
 extern "C" int optmc_set_int(optmc_ctx *ctx, const char *key, int64_t value) {
     if (!ctx || !key) return -2;
+    if (!strcmp(key, "lsmc_timing_ptr")) {     // device buffer of (n_steps + 1) * 4 uint64, or 0
+        ctx->lsmc_timing = reinterpret_cast<unsigned long long *>((uintptr_t)value);
+        return 0;
+    }
     if (!strcmp(key, "normals_impl")) {
         if (value != 0 && value != 1) FAIL("normals_impl must be 0 or 1");
         ctx->normals_impl = (int)value;
@@ -144,6 +158,9 @@ extern "C" int optmc_set_int(optmc_ctx *ctx, const char *key, int64_t value) {
     } else if (!strcmp(key, "euro_threads")) {
         if (value != 64 && value != 128 && value != 256) FAIL("euro_threads must be 64, 128 or 256");
         ctx->euro_threads = (int)value;
+    } else if (!strcmp(key, "lsmc_mode")) {
+        if (value != 0 && value != 1) FAIL("lsmc_mode must be 0 (launch per date) or 1 (persistent)");
+        ctx->lsmc_mode = (int)value;
     } else {
         FAIL(std::string("unknown option ") + key);
     }
@@ -585,6 +602,56 @@ extern "C" int optmc_lsmc_step_async(optmc_ctx *ctx, const double *store_dev, in
     return 0;
 }
 
+template <int D>
+static int launch_persistent(optmc_ctx *ctx, LsmcPersistArgs &A, cudaStream_t st) {
+    if (ctx->sm_count > 160) FAIL("k_lsmc_persistent is sized for at most 160 SMs");
+    void *args[] = {&A};
+    CK(cudaLaunchCooperativeKernel((const void *)k_lsmc_persistent<D>, dim3(ctx->sm_count),
+                                   dim3(lsmc_p_threads(D)), args, 0, st));
+    ctx->launches++;
+    return 0;
+}
+
+// All exercise dates in one cooperative launch (one block per SM, grid barrier per date).
+static int lsmc_persistent(optmc_ctx *ctx, const double *store_dev, int64_t ld, int64_t n_paths,
+                           int32_t n_steps, double strike, int32_t is_call, double disc,
+                           int32_t degree, double *cashflow_dev, double *gram_dev,
+                           cudaStream_t st) {
+    CK(cudaSetDevice(ctx->device));
+    if (!store_dev || !cashflow_dev || !gram_dev) FAIL("null pointer");
+    if (degree < 1 || degree > OPTMC_LSMC_MAX_DEGREE) FAIL("degree must be in 1..7");
+    if (n_paths < 1 || n_steps < 1 || ld < n_paths || (ld & 1)) FAIL("bad shape (ld must be even)");
+    if (!(strike > 0.0)) FAIL("strike must be positive");
+    LsmcPersistArgs A;
+    A.store = store_dev;
+    A.ld = ld;
+    A.n = n_paths;
+    A.n_steps = n_steps;
+    A.K = strike;
+    A.inv_K = 1.0 / strike;
+    A.disc = disc;
+    A.is_call = is_call;
+    A.cashflow = cashflow_dev;
+    A.slots = ctx->lsmc_slots;
+    A.nonce = (++ctx->lsmc_nonce) & 0xFFFFFu;      // tag 0 is never used: nonce >= 1
+    if (A.nonce == 0) A.nonce = ctx->lsmc_nonce = 1;
+    A.error = ctx->ticket + 8;
+    A.gram = gram_dev;
+    A.timing = ctx->lsmc_timing;
+    CK(cudaMemsetAsync(ctx->ticket + 8, 0, 4, st));
+    int rc = 0;
+    switch (degree) {
+        case 1: rc = launch_persistent<1>(ctx, A, st); break;
+        case 2: rc = launch_persistent<2>(ctx, A, st); break;
+        case 3: rc = launch_persistent<3>(ctx, A, st); break;
+        case 4: rc = launch_persistent<4>(ctx, A, st); break;
+        case 5: rc = launch_persistent<5>(ctx, A, st); break;
+        case 6: rc = launch_persistent<6>(ctx, A, st); break;
+        case 7: rc = launch_persistent<7>(ctx, A, st); break;
+    }
+    return rc;
+}
+
 extern "C" int optmc_lsmc(optmc_ctx *ctx, const double *store_dev, int64_t ld, int64_t n_paths,
                           int32_t n_steps, double strike, int32_t is_call, double r, double dt,
                           int32_t degree, double *cashflow_dev, double *gram_dev, double *out_host,
@@ -592,12 +659,25 @@ extern "C" int optmc_lsmc(optmc_ctx *ctx, const double *store_dev, int64_t ld, i
     if (!ctx) return -2;
     if (!out_host) FAIL("out_host is null");
     const double disc = std::exp(-r * dt);                       // american_mc_kernels.py:54
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ctx->lsmc_mode == 1) {
+        int rc = lsmc_persistent(ctx, store_dev, ld, n_paths, n_steps, strike, is_call, disc, degree,
+                                 cashflow_dev, gram_dev, st);
+        if (rc) return rc;
+        unsigned int *flag = reinterpret_cast<unsigned int *>(ctx->moments_host + 8);
+        CK(cudaMemcpyAsync(ctx->moments_host, gram_dev, 3 * sizeof(double), cudaMemcpyDeviceToHost,
+                           st));
+        CK(cudaMemcpyAsync(flag, ctx->ticket + 8, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (*flag) FAIL("k_lsmc_persistent: grid barrier timed out");
+        memcpy(out_host, ctx->moments_host, 3 * sizeof(double));
+        return 0;
+    }
     for (int i = n_steps - 1; i >= 0; --i) {                     // :53 plus the final mean :84
         int rc = optmc_lsmc_step_async(ctx, store_dev, ld, n_paths, n_steps, i, strike, is_call,
                                        disc, degree, cashflow_dev, gram_dev, stream);
         if (rc) return rc;
     }
-    cudaStream_t st = (cudaStream_t)stream;
     CK(cudaMemcpyAsync(ctx->moments_host, gram_dev, 3 * sizeof(double), cudaMemcpyDeviceToHost,
                        st));
     CK(cudaStreamSynchronize(st));

@@ -175,7 +175,16 @@ def test_numpy_mode_reproduces_reference_greeks(price_goldens):
 
 
 # ------------------------------------------------------------------ LSMC
-def test_ls_pricer_matches_reference_vectors(ls_vectors):
+@pytest.fixture
+def lsmc_mode(request, eng):
+    """1 = all dates in one persistent launch (default), 0 = one launch per date."""
+    eng.set_int("lsmc_mode", request.param)
+    yield request.param
+    eng.set_int("lsmc_mode", 1)
+
+
+@pytest.mark.parametrize("lsmc_mode", [1, 0], indirect=True)
+def test_ls_pricer_matches_reference_vectors(ls_vectors, lsmc_mode):
     z, cases = ls_vectors
     paths, dt, r = z["paths"], float(z["dt"]), float(z["r"])
     for c in cases:
@@ -208,6 +217,28 @@ def test_american_numpy_mode_reproduces_reference_prices(price_goldens):
     got = A(n_paths=8000, n_steps=25, seed=9, rng_mode="numpy").price(
         aput, STQ, ob.MertonJumpModel(), RT).price
     assert got == pytest.approx(g["lsmc_merton_8000x25_seed9_deg2_numba99"], rel=1e-10)
+
+
+@pytest.mark.parametrize("n_paths,n_steps,degree", [(1, 3, 2), (7, 1, 1), (1001, 5, 3), (40000, 12, 3),
+                                                    (300001, 7, 4), (20000, 6, 7)])
+def test_lsmc_persistent_launch_equals_per_date_launches(eng, n_paths, n_steps, degree):
+    """Same arithmetic per path, different summation order of the power sums:
+    the two drivers agree to rounding, and both with the oracle on the same paths."""
+    rng = np.random.default_rng(n_paths + degree)
+    z = rng.standard_normal((n_paths, n_steps)) * 0.2 * math.sqrt(1.0 / n_steps)
+    paths = 100.0 * np.exp(np.concatenate([np.zeros((n_paths, 1)), np.cumsum(z, axis=1)], axis=1))
+    got = {}
+    for mode in (1, 0):
+        eng.set_int("lsmc_mode", mode)
+        try:
+            got[mode] = american_mc_kernels.longstaff_schwartz_pricer(paths, 105.0, 1.0 / n_steps,
+                                                                      0.05, False, degree)
+        finally:
+            eng.set_int("lsmc_mode", 1)
+    assert got[1] == pytest.approx(got[0], rel=1e-9 if degree >= 4 else 1e-11, abs=1e-13)
+    if degree <= 3 and n_paths > 100:
+        want = orc.longstaff_schwartz(paths, 105.0, 1.0 / n_steps, 0.05, False, degree)
+        assert got[1] == pytest.approx(want, rel=1e-9)
 
 
 def test_lsmc_high_degree_is_statistically_consistent():

@@ -10,6 +10,7 @@ import optpricing_b200 as ob
 from optpricing_b200 import _engine
 
 eng = _engine.get_engine()
+eng.set_int("lsmc_mode", int(os.environ.get("LSMC_MODE", "1")))
 n_paths = int(os.environ.get("N_PATHS", 1 << 22)); n_steps = int(os.environ.get("N_STEPS", 50))
 degree = int(os.environ.get("DEGREE", 3))
 mdl = _engine.make_model("bsm", {"sigma": 0.2}, 0.05, 0.01)
@@ -30,7 +31,7 @@ for rep in range(4):
 price = out[1] / out[0]
 se = ((out[2] / out[0] - price ** 2) / out[0]) ** 0.5
 pd = n_paths * n_steps
-print(f"LSMC {n_paths} x {n_steps} deg {degree}: fill {best_fill:.3f} ms ({pd * 8 / best_fill / 1e6:.0f} GB/s store, "
+print(f"[mode {os.environ.get('LSMC_MODE', '1')}] LSMC {n_paths} x {n_steps} deg {degree}: fill {best_fill:.3f} ms ({pd * 8 / best_fill / 1e6:.0f} GB/s store, "
       f"{pd / best_fill / 1e6:.1f} G path-steps/s), induction {best_ind:.3f} ms "
       f"({pd * 32 / best_ind / 1e6:.0f} GB/s at 32 B/path-date), total {best_fill + best_ind:.3f} ms = "
       f"{pd / (best_fill + best_ind) / 1e6:.2f} G path-steps/s; price {price:.4f} +- {se:.4f} (CRR 12.2777)")
