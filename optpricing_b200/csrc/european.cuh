@@ -99,9 +99,10 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
     constexpr bool DEFER = !PER_STEP && !kind_sabr(KIND);
     init_state<KIND, DEFER>(sa, c);
     init_state<KIND, DEFER>(sb, c);
-    // A Box-Muller pair feeds one step of a two-factor model, or two
-    // consecutive steps of a one-factor model (terminal-only kernels).
-    constexpr int SPC = (TWO || PER_STEP) ? 1 : 2;
+    // A Box-Muller pair feeds one step of a two-factor model, or two consecutive
+    // steps of a one-factor model.  The path kernels of the jump models keep one
+    // step per Philox call: every step needs its own Poisson word.
+    constexpr int SPC = (TWO || (PER_STEP && JUMPS)) ? 1 : 2;
     const uint32_t id_lo = keep_u32((uint32_t)id), id_hi = keep_u32((uint32_t)(id >> 32));
     OPTMC_UNROLL_STEPS
     for (int i = 0; i < A.n_steps; i += SPC) {
@@ -129,9 +130,11 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
             step_diffusion<KIND, DEFER>(sa, z1, 0.0, c, tab);
             if constexpr (ANTI) step_diffusion<KIND, DEFER>(sb, -z1, 0.0, c, tab);
             if constexpr (SPC == 2) {
+                if constexpr (PER_STEP) sink(i, sa, sb);
                 if (i + 1 < A.n_steps) {
                     step_diffusion<KIND, DEFER>(sa, z2, 0.0, c, tab);
                     if constexpr (ANTI) step_diffusion<KIND, DEFER>(sb, -z2, 0.0, c, tab);
+                    if constexpr (PER_STEP) sink(i + 1, sa, sb);
                 }
             }
         }
@@ -150,7 +153,7 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
                 if constexpr (ANTI) apply_jump<KIND, DEFER>(sb, J.y);
             }
         }
-        if constexpr (PER_STEP) sink(i, sa, sb);
+        if constexpr (PER_STEP && SPC == 1) sink(i, sa, sb);
     }
     if constexpr (JUMPS_AT_END) {
         uint4 e = philox4x32_10(make_uint4(id_lo, id_hi, 0xFFFFFFFFu, 0xFEu), A.key);
