@@ -153,6 +153,53 @@ int optmc_payoff_sweep_async(optmc_ctx *ctx, const double *terminal_dev, int64_t
                              double *moments_dev, void *stream);
 
 /*
+ * Single-step terminal samplers: the pure-Levy and exact-sampler branches of
+ * MonteCarloTechnique.price (monte_carlo.py:103-106) and _simulate_levy_terminal
+ * (:259-280), which in the reference call each model's numpy/scipy sampler on
+ * the host.  The host layer folds the model parameters into p[] (the laws, in
+ * the reference's own parameterisation):
+ *   OPTMC_LEVY_VG          models/vg.py:136-168          p = {T/nu, nu, theta, sigma}
+ *                          x = theta g + sigma sqrt(g) z,  g = p[1] Gamma(p[0])
+ *   OPTMC_LEVY_NIG         models/nig.py:136-169         p = {mu_ig, beta}
+ *                          x = beta w + sqrt(w) z,  w ~ inverse Gaussian(mean mu_ig, shape 1)
+ *   OPTMC_LEVY_CGMY1       models/cgmy.py:134-178 (Y=1)  p = {C T, 1/M, 1/G}
+ *                          x = p[1] Gamma(p[0]) - p[2] Gamma'(p[0])
+ *   OPTMC_LEVY_HYPERBOLIC  models/hyperbolic.py:123-152  p = {b_gig, s_gig, beta, loc, scale,
+ *                          p_gig - 1, mode m, u-, u+, log g(m)} (optmc_levy_gig_setup fills 5..9)
+ *                          x = loc + scale (beta v + sqrt(v) z),  v = s_gig GIG(p_gig, b_gig)
+ *   OPTMC_LEVY_CEV         models/cev.py:49-96           p = {df, nc, k, 1/(2(1-gamma))}, df > 1
+ *                          S_T = (ncx2(df, nc) / k)^p[3]            (no drift, no exp)
+ *   OPTMC_LEVY_LOGNORMAL   models/cev.py:81-85 (gamma -> 1)  p = {drift, sigma sqrt(T)}
+ *                          S_T = s0 exp(p[0] + p[1] z)
+ * Levy kinds: S_T = s0 exp(drift + x), drift = (r - q) T - log Re phi_raw(-i)  (:276-280).
+ * Samples [offset, offset + n_local) of one seed are drawn (disjoint Philox
+ * counters per sample: any partition over ranks gives the same samples).
+ * Moments as optmc_european_async (control = S_T); terminal_dev (optional,
+ * required for n_contracts > 1) receives the n_local terminal spots.
+ */
+enum optmc_levy_kind {
+    OPTMC_LEVY_VG = 0, OPTMC_LEVY_NIG = 1, OPTMC_LEVY_CGMY1 = 2, OPTMC_LEVY_HYPERBOLIC = 3,
+    OPTMC_LEVY_CEV = 4, OPTMC_LEVY_LOGNORMAL = 5
+};
+#define OPTMC_LEVY_NPARAM 12
+
+typedef struct optmc_levy {
+    int32_t kind;       /* enum optmc_levy_kind */
+    int32_t reserved;
+    double p[OPTMC_LEVY_NPARAM];
+} optmc_levy;
+
+/* Bounding rectangle of the ratio-of-uniforms GIG sampler (Hoermann & Leydold 2014,
+   mode-shift branch; needs p_gig >= 1 or b_gig > 1): reads p[0] (b_gig) and p[5]
+   (p_gig - 1), writes p[6..9]. */
+int optmc_levy_gig_setup(optmc_levy *levy);
+
+int optmc_levy_terminal_async(optmc_ctx *ctx, const optmc_levy *levy, double s0, double drift,
+                              uint64_t seed, int64_t offset, int64_t n_local,
+                              int32_t n_contracts, const double *strikes, const int32_t *is_call,
+                              double *moments_dev, double *terminal_dev, void *stream);
+
+/*
  * Longstaff-Schwartz, replacing AmericanMonteCarloTechnique.price
  * (american_monte_carlo.py:52-73).
  *

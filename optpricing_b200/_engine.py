@@ -25,6 +25,8 @@ CORR_REFERENCE_EUROPEAN = 0
 CORR_INDEPENDENT_DRAWS = 1
 NMOM = 6
 LSMC_GRAM = 24
+LEVY_CODES = {"vg": 0, "nig": 1, "cgmy": 2, "hyperbolic": 3, "cev": 4, "lognormal": 5}
+LEVY_NPARAM = 12
 
 c_void_p, c_int, c_i32, c_i64, c_u32, c_u64, c_double = (
     ctypes.c_void_p, ctypes.c_int, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32,
@@ -51,6 +53,11 @@ class OptmcSim(ctypes.Structure):
                 ("reserved", c_i32)]
 
 
+class OptmcLevy(ctypes.Structure):
+    """struct optmc_levy (include/optmc.h)."""
+    _fields_ = [("kind", c_i32), ("reserved", c_i32), ("p", c_double * LEVY_NPARAM)]
+
+
 # every symbol include/optmc.h declares: (name, restype, argtypes)
 SIGNATURES = [
     ("optmc_version", c_int, []),
@@ -68,6 +75,10 @@ SIGNATURES = [
                                 c_i32, c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
     ("optmc_payoff_sweep_async", c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i32, _dp, _ip,
                                          c_void_p, c_void_p]),
+    ("optmc_levy_gig_setup", c_int, [ctypes.POINTER(OptmcLevy)]),
+    ("optmc_levy_terminal_async", c_int, [c_void_p, ctypes.POINTER(OptmcLevy), c_double, c_double,
+                                          c_u64, c_i64, c_i64, c_i32, _dp, _ip, c_void_p,
+                                          c_void_p, c_void_p]),
     ("optmc_lsmc_paths_async", c_int, [c_void_p, ctypes.POINTER(OptmcModel),
                                        ctypes.POINTER(OptmcSim), c_void_p, c_i64, c_void_p]),
     ("optmc_lsmc_load_async", c_int, [c_void_p, c_void_p, c_i64, c_i32, c_void_p, c_i64,
@@ -133,6 +144,50 @@ def make_model(kind: str, params: dict, r: float, q: float, v0=None) -> OptmcMod
         m.lambda_, m.p_up, m.eta1, m.eta2 = (float(p["lambda"]), float(p["p_up"]),
                                              float(p["eta1"]), float(p["eta2"]))
     return m
+
+
+def make_levy(kind: str, params: dict, r: float, T: float, S0: float) -> OptmcLevy:
+    """
+    Fold a single-step model's parameters into struct optmc_levy, in the
+    reference's own parameterisation of each sampler:
+    vg.py:164-168, nig.py:163-169, cgmy.py:174-178, hyperbolic.py:143-152
+    (scipy genhyperbolic._rvs: GIG(p, sqrt(a^2-b^2)) scaled by 1/sqrt(a^2-b^2)),
+    cev.py:80-94.
+    """
+    import math
+
+    L = OptmcLevy()
+    p = params
+    vals: list[float]
+    if kind == "vg":
+        vals = [T / p["nu"], p["nu"], p["theta"], p["sigma"]]
+    elif kind == "nig":
+        vals = [p["delta"] * T / math.sqrt(p["alpha"] ** 2 - p["beta"] ** 2), p["beta"]]
+    elif kind == "cgmy":
+        if not math.isclose(p["Y"], 1.0, rel_tol=1e-5, abs_tol=1e-8):        # cgmy.py:168-171
+            raise NotImplementedError("Monte Carlo sampling for CGMY is only implemented for Y=1.")
+        vals = [p["C"] * T, 1.0 / p["M"], 1.0 / p["G"]]
+    elif kind == "hyperbolic":
+        t1 = p["alpha"] ** 2 - p["beta"] ** 2
+        vals = [math.sqrt(t1), 1.0 / math.sqrt(t1), p["beta"], p["mu"] * T, p["delta"] * T, 0.0]
+    elif kind == "cev":
+        sigma, gamma = p["sigma"], p["gamma"]
+        if abs(1.0 - gamma) < 1e-6:                                           # cev.py:81-85
+            kind = "lognormal"
+            vals = [(r - 0.5 * sigma ** 2) * T, sigma * math.sqrt(T)]
+        else:
+            df = 2 + 2 / (1 - gamma)
+            k = 2 * r / (sigma ** 2 * (1 - gamma) * (math.exp(r * (1 - gamma) * T) - 1))
+            nc = k * S0 ** (2 * (1 - gamma)) * math.exp(-r * (1 - gamma) * T)
+            vals = [df, nc, k, 1 / (2 * (1 - gamma))]
+    else:
+        raise KeyError(kind)
+    L.kind = LEVY_CODES[kind]
+    for i, v in enumerate(vals):
+        L.p[i] = float(v)
+    if kind == "hyperbolic" and load_library().optmc_levy_gig_setup(ctypes.byref(L)) != 0:
+        raise EngineError("optmc_levy_gig_setup: parameters outside the sampler's range")
+    return L
 
 
 class Engine:
@@ -236,6 +291,17 @@ class Engine:
         if not to_host:
             return mom
         return mom[: k.size * NMOM].cpu().numpy().reshape(k.size, NMOM)
+
+    # -- single-step terminal samplers --------------------------------------
+    def levy_terminal_async(self, levy: OptmcLevy, s0, drift, seed, offset, n_local, strikes,
+                            is_call, moments, terminal=None):
+        """optmc_levy_terminal_async into the torch tensor ``moments`` (n_contracts*6 f64)."""
+        k, c, kp, cp = self._contracts(strikes, is_call)
+        tptr = c_void_p(terminal.data_ptr()) if terminal is not None else None
+        self._check(self.lib.optmc_levy_terminal_async(
+            self.ctx, ctypes.byref(levy), float(s0), float(drift),
+            int(seed) & 0xFFFFFFFFFFFFFFFF, int(offset), int(n_local), k.size, kp, cp,
+            c_void_p(moments.data_ptr()), tptr, self.stream()), "optmc_levy_terminal_async")
 
     # -- fed-draw kernels ---------------------------------------------------
     def fed(self, kind, model: OptmcModel, x0, dt, dw1, dw2=None, counts=None, jumps=None,

@@ -13,6 +13,7 @@
 #include "../../include/optmc.h"
 #include "european.cuh"
 #include "fed.cuh"
+#include "levy.cuh"
 #include "lsmc.cuh"
 
 using namespace optmc;
@@ -419,6 +420,100 @@ extern "C" int optmc_payoff_sweep_async(optmc_ctx *ctx, const double *terminal_d
     CK(cudaSetDevice(ctx->device));
     return sweep_launch(ctx, terminal_dev, n_local, antithetic, n_contracts, strikes, is_call,
                         moments_dev, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------
+// single-step terminal samplers (Levy / exact-sampler branches)
+// ---------------------------------------------------------------------------
+extern "C" int optmc_levy_gig_setup(optmc_levy *L) {
+    if (!L) return -2;
+    const double b = L->p[0], lm1 = L->p[5], lam = lm1 + 1.0;
+    if (!(b > 0.0) || !(lam >= 1.0 || b > 1.0)) return -2;
+    // Hoermann & Leydold (2014), Algorithm "ratio-of-uniforms with mode shift"
+    const double m = (std::sqrt(lm1 * lm1 + b * b) + lm1) / b;
+    auto logg = [&](double x) { return lm1 * std::log(x) - 0.5 * b * (x + 1.0 / x); };
+    const double a2 = -(2.0 * (lam + 1.0) / b + m);
+    const double a1 = 2.0 * lm1 * m / b - 1.0;
+    const double a0 = m;
+    const double pp = a1 - a2 * a2 / 3.0;
+    const double qq = 2.0 * a2 * a2 * a2 / 27.0 - a2 * a1 / 3.0 + a0;
+    double arg = -0.5 * qq * std::sqrt(-27.0 / (pp * pp * pp));
+    arg = std::min(1.0, std::max(-1.0, arg));
+    const double phi = std::acos(arg);
+    const double pi = 3.14159265358979323846;
+    const double amp = std::sqrt(-4.0 * pp / 3.0);
+    const double xm = amp * std::cos(phi / 3.0 + 4.0 * pi / 3.0) - a2 / 3.0;
+    const double xp = amp * std::cos(phi / 3.0) - a2 / 3.0;
+    const double lgm = logg(m);
+    L->p[6] = m;
+    L->p[7] = (xm - m) * std::exp(0.5 * (logg(xm) - lgm));
+    L->p[8] = (xp - m) * std::exp(0.5 * (logg(xp) - lgm));
+    L->p[9] = lgm;
+    return (std::isfinite(L->p[7]) && std::isfinite(L->p[8]) && L->p[7] < 0.0 && L->p[8] > 0.0) ? 0 : -2;
+}
+
+extern "C" int optmc_levy_terminal_async(optmc_ctx *ctx, const optmc_levy *levy, double s0,
+                                         double drift, uint64_t seed, int64_t offset,
+                                         int64_t n_local, int32_t n_contracts,
+                                         const double *strikes, const int32_t *is_call,
+                                         double *moments_dev, double *terminal_dev, void *stream) {
+    if (!ctx) return -2;
+    CK(cudaSetDevice(ctx->device));
+    if (!levy) FAIL("null levy");
+    if (levy->kind < OPTMC_LEVY_VG || levy->kind > OPTMC_LEVY_LOGNORMAL) FAIL("unknown levy kind");
+    if (n_contracts < 1 || !strikes || !is_call || !moments_dev) FAIL("bad contract arguments");
+    if (n_contracts > 1 && !terminal_dev)
+        FAIL("terminal_dev is required when n_contracts > 1 (strike sweep)");
+    if (!(s0 > 0.0)) FAIL("s0 must be positive");
+    if (offset < 0 || n_local < 0) FAIL("negative sample range");
+    const double *p = levy->p;
+    switch (levy->kind) {
+        case OPTMC_LEVY_VG:
+            if (!(p[0] > 0.0 && p[1] > 0.0 && p[3] > 0.0)) FAIL("VG needs T/nu, nu, sigma > 0");
+            break;
+        case OPTMC_LEVY_NIG:
+            if (!(p[0] > 0.0)) FAIL("NIG needs mu_ig > 0");
+            break;
+        case OPTMC_LEVY_CGMY1:
+            if (!(p[0] > 0.0 && p[1] > 0.0 && p[2] > 0.0)) FAIL("CGMY needs C T, M, G > 0");
+            break;
+        case OPTMC_LEVY_HYPERBOLIC:
+            if (!(p[0] > 0.0 && p[1] > 0.0 && p[4] > 0.0 && p[7] < 0.0 && p[8] > 0.0))
+                FAIL("hyperbolic: bad GIG constants (call optmc_levy_gig_setup)");
+            break;
+        case OPTMC_LEVY_CEV:
+            if (!(p[0] > 1.0 && p[1] >= 0.0 && p[2] > 0.0))
+                FAIL("CEV needs df > 1, nc >= 0, k > 0 (gamma < 1 and r != 0)");
+            break;
+        default:
+            if (!(p[1] > 0.0)) FAIL("lognormal needs sigma sqrt(T) > 0");
+    }
+    LevyArgs A;
+    memset(&A, 0, sizeof A);
+    A.kind = levy->kind;
+    memcpy(A.p, levy->p, sizeof A.p);
+    philox_expand_key(seed, &A.key);
+    A.offset = offset;
+    A.n_local = n_local;
+    A.s0 = s0;
+    A.drift = drift;
+    A.is_call = is_call[0] ? 1 : 0;
+    A.strike = strikes[0];
+    A.partials = reinterpret_cast<double *>(ctx->scratch);
+    A.terminal = terminal_dev;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = (int)std::max<int64_t>(
+        1, std::min<int64_t>((n_local + 255) / 256, (int64_t)ctx->sm_count * 8));
+    k_levy_terminal<<<grid, 256, 0, st>>>(A);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    if (n_contracts == 1) {
+        k_finish_moments<<<1, 256, 0, st>>>(A.partials, grid, (double)n_local, moments_dev);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        return 0;
+    }
+    return sweep_launch(ctx, terminal_dev, n_local, 0, n_contracts, strikes, is_call, moments_dev, st);
 }
 
 // ---------------------------------------------------------------------------

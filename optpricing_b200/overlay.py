@@ -13,6 +13,7 @@ What is replaced:
     optpricing.techniques.kernels.mc_kernels          -> ....kernels.mc_kernels
     optpricing.techniques.kernels.path_kernels        -> ....kernels.path_kernels
     optpricing.techniques.kernels.american_mc_kernels -> ....kernels.american_mc_kernels
+    optpricing.models.cev.CEVModel.sample_terminal_spot -> device sampler (csrc/levy.cuh)
 The aliases are entries in ``sys.modules``, so ``from .monte_carlo import
 MonteCarloTechnique`` inside the reference's own ``techniques/__init__.py`` (:15),
 ``unittest.mock.patch("optpricing.techniques.monte_carlo....")`` and the
@@ -76,6 +77,17 @@ def install(reference_src: str | None = None) -> None:
         for name in _CLASSES:
             if hasattr(top, name):
                 setattr(top, name, getattr(ours, name))
+    # The one sampler the technique reaches through the model object
+    # (monte_carlo.py:103-104): CEVModel.sample_terminal_spot -> device sampler.
+    # The pure-Levy laws need no rebinding: _simulate_levy_terminal picks the
+    # device sampler by model name and never calls sample_terminal_log_return.
+    try:
+        cev = importlib.import_module("optpricing.models.cev")
+    except Exception:  # noqa: BLE001 - models not importable in this environment: nothing to rebind
+        cev = None
+    if cev is not None and hasattr(cev, "CEVModel"):
+        from optpricing_b200.models import device_sample_terminal_spot
+        cev.CEVModel.sample_terminal_spot = device_sample_terminal_spot
 
 
 def installed() -> bool:

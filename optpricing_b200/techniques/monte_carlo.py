@@ -33,7 +33,7 @@ import numpy as np
 
 from optpricing_b200 import _engine
 from optpricing_b200.atoms import is_call as _is_call
-from optpricing_b200.models import model_kind
+from optpricing_b200.models import levy_kind, model_kind
 
 from .base import BaseTechnique, GreekMixin, IVMixin, PricingResult, crn
 from .kernels import mc_kernels
@@ -60,6 +60,13 @@ def control_mean(kind: str, params: dict, S0: float, r: float, q: float, T: floa
     models are exact one-step martingales (jump compensators match E[e^J]), so
     E[S_T] = S0 e^{(r-q)T}; SABR is Euler on S itself (mc_kernels.py:211,257).
     """
+    if kind in ("cev", "lognormal"):
+        return S0 * math.exp(r * T)               # cev.py:49-96 takes no dividend yield
+    if kind in ("nig", "hyperbolic", "cgmy"):
+        # the reference's samplers of these laws are not the time-T marginals of the
+        # process raw_cf describes (nig.py:163-166 draws IG with shape 1), so the
+        # martingale-corrected mean is not S0 e^{(r-q)T}: no control variate
+        return float("nan")
     dt = T / n_steps
     if kind == "sabr":
         return S0 * (1.0 + (r - q) * dt) ** n_steps
@@ -134,10 +141,20 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
         r, q = rate.get_rate(T), stock.dividend
         call = _is_call(option)
 
-        if getattr(model, "has_exact_sampler", False):      # CEV: model's own sampler (:103-104)
-            ST = model.sample_terminal_spot(S0, r, T, self.n_paths)
+        if getattr(model, "has_exact_sampler", False):      # CEV (:103-104)
+            sampler = model.sample_terminal_spot
+            if (self._device_single_step(model)
+                    and getattr(sampler, "__optmc_device__", False) is True):
+                # the engine's own sampler: same draws, but only the moments leave the GPU
+                ST = self._device_terminal(model, S0, r, q, T, hint=(float(K), call))
+            else:                                           # a model bringing its own sampler
+                ST = sampler(S0, r, T, self.n_paths)
         elif getattr(model, "is_pure_levy", False):         # VG/NIG/CGMY/Hyperbolic (:105-106)
-            ST = self._simulate_levy_terminal(model, S0, r, q, T)
+            self._hint = (float(K), call)
+            try:
+                ST = self._simulate_levy_terminal(model, S0, r, q, T)
+            finally:
+                self._hint = None
         else:
             self._hint = (float(K), call)
             try:
@@ -150,7 +167,7 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
             stats = summarize(ST.moments, r, T, c_mean)
             stats["seed"] = ST.seed
             self.last_stats = stats
-            use_cv = self.control_variate and "cv_price" in stats
+            use_cv = self.control_variate and "cv_price" in stats and math.isfinite(c_mean)
             return PricingResult(price=float(stats["cv_price"] if use_cv else stats["price"]))
 
         payoff = np.maximum(ST - K, 0) if call else np.maximum(K - ST, 0)
@@ -380,13 +397,52 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
         up, dn = self._bumped_prices(option, stock, model, rate, (), (h, -h), **kw)
         return (up - dn) / (2 * h)
 
+    # ------------------------------------------- single-step models
+    def _device_single_step(self, model) -> bool:
+        """VG / NIG / CGMY / Hyperbolic / CEV on the device samplers (csrc/levy.cuh)."""
+        return self.rng_mode == "philox" and levy_kind(model) is not None
+
+    def _device_terminal(self, model, S0, r, q, T, hint=None):
+        """
+        Terminal spots of ``n_paths`` samples of a single-step model drawn on the
+        GPU (one thread per sample; samples sharded by rank like the SDE draws).
+        With ``hint`` = (strike, is_call) only the payoff moments come back
+        (DeviceTerminal); without it the host array of terminal spots.
+        """
+        kind = levy_kind(model)
+        eng = _engine.get_engine()
+        levy = _engine.make_levy(kind, model.params, r, T, S0)
+        if kind == "cev":
+            drift = 0.0                                   # cev.py:49-96 samples S_T directly (q unused)
+        else:
+            compensator = float(np.log(np.real(model.raw_cf(t=T)(-1j))))     # monte_carlo.py:276-278
+            drift = (r - q) * T - compensator
+        seed = int(self.rng.integers(0, 2**63 - 1, dtype=np.int64))
+        rank, world, all_reduce = self._group()
+        off, cnt = shard_draws(self.n_paths, rank, world)
+        dev = eng.buffer("moments", _engine.NMOM)
+        if hint is None:
+            term = eng.buffer("terminal", cnt)
+            eng.levy_terminal_async(levy, S0, drift, seed, off, cnt, [float(S0)], [1], dev, term)
+            return term[:cnt].cpu().numpy()
+        K, call = hint
+        eng.levy_terminal_async(levy, S0, drift, seed, off, cnt, [K], [1 if call else 0], dev)
+        if all_reduce is not None:
+            all_reduce(dev[: _engine.NMOM])
+        return DeviceTerminal(dev[: _engine.NMOM].cpu().numpy(), kind, seed)
+
     def _simulate_levy_terminal(self, model, S0: float, r: float, q: float, T: float):
         """
-        Pure-Levy terminal sampling (monte_carlo.py:259-280).  Outside the GPU
-        hot path: as in the reference, the model's own numpy
-        sampler produces the log-returns; only the martingale correction and
-        the exponential are applied here.
+        Pure-Levy terminal sampling (monte_carlo.py:259-280).  The four laws the
+        reference ships (VG, NIG, CGMY with Y=1, Hyperbolic) are drawn on the GPU;
+        a model that brings its own ``sample_terminal_log_return`` (the reference's
+        plug-in contract, and ``rng_mode="numpy"``) has that sampler called exactly
+        as the reference does, with the martingale correction applied here.
         """
+        if self._device_single_step(model):
+            if not hasattr(model, "raw_cf"):
+                raise NotImplementedError(f"Levy model '{model.name}' is missing required methods.")
+            return self._device_terminal(model, S0, r, q, T, hint=self._hint)
         if not hasattr(model, "sample_terminal_log_return") or not hasattr(model, "raw_cf"):
             raise NotImplementedError(f"Levy model '{model.name}' is missing required methods.")
         x = model.sample_terminal_log_return(T, self.n_paths, self.rng)

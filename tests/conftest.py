@@ -32,3 +32,9 @@ def ls_vectors():
 def price_goldens():
     with open(os.path.join(GOLDEN, "price_goldens.json")) as f:
         return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def levy_goldens():
+    with open(os.path.join(GOLDEN, "levy_goldens.json")) as f:
+        return json.load(f)

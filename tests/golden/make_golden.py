@@ -14,6 +14,8 @@ import untouched.  Nothing here is read at test time except the files written:
     kernel_vectors.npz   inputs + outputs of the 7 terminal and 7 path kernels
     ls_vectors.npz       a path matrix + longstaff_schwartz_pricer outputs
     price_goldens.json   technique.price()/delta/gamma/vega values
+    levy_goldens.json    single-step models (VG, NIG, CGMY, Hyperbolic, CEV): seeded prices,
+                         large-sample prices / quantiles, FFT prices
 
 The GPU box has no /root/reference; tests compare the oracle and the CUDA path
 against these files.
@@ -234,9 +236,68 @@ def price_goldens():
     return g
 
 
+# ---------------------------------------------------------------- single-step models
+def levy_goldens():
+    """Pure-Levy / exact-sampler branches of MonteCarloTechnique.price (monte_carlo.py:103-106):
+    the reference's seeded prices (pin the oracle restatement bit for bit), large-sample
+    prices with standard errors and sample quantiles of the terminal spot (pin the device
+    samplers statistically), and the reference's FFT prices where a cf exists."""
+    from optpricing.models import CEVModel, CGMYModel, HyperbolicModel, NIGModel, VarianceGammaModel
+
+    call = Option(strike=100, maturity=1.0, option_type=OptionType.CALL)
+    put = Option(strike=95, maturity=0.5, option_type=OptionType.PUT)
+    stq = Stock(spot=100.0, dividend=0.01)
+    rt = Rate(rate=0.05)
+    models = {
+        "vg": VarianceGammaModel(params=VarianceGammaModel.default_params),
+        "vg_small_shape": VarianceGammaModel(params={"sigma": 0.25, "nu": 1.5, "theta": -0.1}),
+        "nig": NIGModel(params=NIGModel.default_params),
+        "cgmy": CGMYModel(params={"C": 0.5, "G": 6.0, "M": 9.0, "Y": 1.000001}),
+        "hyperbolic": HyperbolicModel(params=HyperbolicModel.default_params),
+        "cev": CEVModel(params=CEVModel.default_params),
+        "cev_gamma1": CEVModel(params={"sigma": 0.2, "gamma": 1.0}),
+    }
+    qs = [0.001, 0.01, 0.1, 0.25, 0.5, 0.75, 0.9, 0.99, 0.999]
+    g = {"_quantile_levels": qs, "_toolchain": dict(numpy=np.__version__)}
+    import scipy
+    g["_toolchain"]["scipy"] = scipy.__version__
+    for name, mdl in models.items():
+        e = {"params": dict(mdl.params)}
+        for tag, opt in (("call", call), ("put", put)):
+            np.random.seed(4321)                       # CEV draws from numpy's global state
+            e[f"{tag}_20000_seed42"] = MonteCarloTechnique(n_paths=20000, seed=42).price(opt, stq, mdl, rt).price
+        # large sample: price, standard error, quantiles of S_T (call maturity)
+        np.random.seed(99)
+        t = MonteCarloTechnique(n_paths=2_000_000, seed=7)
+        if name.startswith("cev"):
+            ST = mdl.sample_terminal_spot(100.0, 0.05, 1.0, t.n_paths)
+        else:
+            ST = t._simulate_levy_terminal(mdl, 100.0, 0.05, 0.01, 1.0)
+        pay = np.maximum(ST - 100.0, 0) * math.exp(-0.05)
+        e["call_2m_price"] = float(pay.mean())
+        e["call_2m_stderr"] = float(pay.std(ddof=1) / math.sqrt(pay.size))
+        e["ST_2m_mean"] = float(ST.mean())
+        e["ST_2m_quantiles"] = [float(x) for x in np.quantile(ST, qs)]
+        if not name.startswith("cev"):
+            try:
+                e["call_fft"] = float(FFTTechnique().price(call, stq, mdl, rt).price)
+            except Exception as exc:                  # noqa: BLE001
+                e["call_fft_error"] = repr(exc)
+        g[name] = e
+    with open(os.path.join(HERE, "levy_goldens.json"), "w") as f:
+        json.dump(g, f, indent=1, sort_keys=True)
+    return g
+
+
 if __name__ == "__main__":
+    if "--levy-only" in sys.argv:
+        for k, v in levy_goldens().items():
+            print(k, v)
+        raise SystemExit(0)
     kv = kernel_vectors()
     print("kernel_vectors.npz:", len(kv), "arrays")
     print("ls_vectors.npz:", len(ls_vectors()), "cases")
     for k, v in price_goldens().items():
+        print(k, v)
+    for k, v in levy_goldens().items():
         print(k, v)

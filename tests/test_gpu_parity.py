@@ -543,3 +543,79 @@ def test_config5_control_variates_and_bumps_2p24_x_365(kind):
         assert 20 < v < 45                                   # has 'sigma'
     else:
         assert np.isnan(v)                                   # greek_mixin.py:156-157
+
+
+# ------------------------------------------------------------------ single-step models
+LEVY_CASES = ("vg", "vg_small_shape", "nig", "cgmy", "hyperbolic", "cev", "cev_gamma1")
+LEVY_MODELS = {"vg": ob.VarianceGammaModel, "nig": ob.NIGModel, "cgmy": ob.CGMYModel,
+               "hyperbolic": ob.HyperbolicModel, "cev": ob.CEVModel}
+
+
+@pytest.mark.parametrize("case", LEVY_CASES)
+def test_single_step_device_samplers_follow_the_reference_law(levy_goldens, case):
+    """Device gamma / inverse-Gaussian / GIG / non-central chi-square samplers against
+    2M draws of the reference's numpy/scipy samplers: price within 4 combined standard
+    errors, empirical CDF at the reference's quantiles within 5 sigma."""
+    e = levy_goldens[case]
+    model = LEVY_MODELS[case.split("_")[0]](e["params"])
+    call = ob.Option(strike=100.0, maturity=1.0, option_type=ob.OptionType.CALL)
+    t = ob.MonteCarloTechnique(n_paths=1 << 22, seed=5)
+    price = t.price(call, STQ, model, RT).price
+    se = math.hypot(t.last_stats["stderr"], e["call_2m_stderr"])
+    assert abs(price - e["call_2m_price"]) < 4 * se, (price, e["call_2m_price"], se)
+    spots = t._device_terminal(model, 100.0, 0.05, 0.01, 1.0)
+    assert spots.shape == (1 << 22,) and np.all(np.isfinite(spots)) and np.all(spots > 0)
+    assert spots.mean() == pytest.approx(e["ST_2m_mean"], abs=5 * spots.std() * math.sqrt(1 / spots.size + 1 / 2e6))
+    for q, x in zip(levy_goldens["_quantile_levels"], e["ST_2m_quantiles"]):
+        sd = math.sqrt(q * (1 - q) * (1 / spots.size + 1 / 2e6))
+        assert abs(float((spots <= x).mean()) - q) < 5 * sd, (case, q)
+
+
+@pytest.mark.parametrize("kind", ("vg", "hyperbolic", "cev"))
+def test_single_step_price_within_3_sigma_of_oracle(kind):
+    model = LEVY_MODELS[kind]()
+    put = ob.Option(strike=95.0, maturity=0.5, option_type=ob.OptionType.PUT)
+    t = ob.MonteCarloTechnique(n_paths=1 << 21, seed=3)
+    got = t.price(put, STQ, model, RT).price
+    np.random.seed(17)
+    want, STv = orc.price_single_step(kind, model.params, 100.0, 95.0, 0.5, 0.05, 0.01, False,
+                                      400_000, np.random.default_rng(8), return_terminal=True)
+    se_o = math.exp(-0.025) * np.maximum(95.0 - STv, 0).std(ddof=1) / math.sqrt(STv.size)
+    assert abs(got - want) < 3 * math.hypot(t.last_stats["stderr"], se_o)
+
+
+def test_single_step_samples_do_not_depend_on_the_partition(eng):
+    levy = _engine.make_levy("vg", ob.VarianceGammaModel().params, 0.05, 1.0, 100.0)
+    torch = eng.torch
+    mom = torch.zeros(6, dtype=torch.float64, device=eng.device)
+    whole = torch.empty(5000, dtype=torch.float64, device=eng.device)
+    eng.levy_terminal_async(levy, 100.0, 0.01, 77, 0, 5000, [100.0], [1], mom, whole)
+    parts = []
+    for off, cnt in ((0, 1234), (1234, 3766)):
+        part = torch.empty(cnt, dtype=torch.float64, device=eng.device)
+        eng.levy_terminal_async(levy, 100.0, 0.01, 77, off, cnt, [100.0], [1], mom, part)
+        parts.append(part)
+    assert torch.equal(whole, torch.cat(parts))
+
+
+def test_single_step_errors_are_the_references():
+    call = ob.Option(strike=100.0, maturity=1.0, option_type=ob.OptionType.CALL)
+    with pytest.raises(NotImplementedError, match="only implemented for Y=1"):
+        ob.MonteCarloTechnique(n_paths=100).price(call, STQ, ob.CGMYModel(), RT)    # default Y = 1.2
+
+
+def test_cev_sample_terminal_spot_is_the_device_sampler(levy_goldens):
+    """models/cev.py:49-96 signature; reproducible through numpy's global seed as in the reference."""
+    m = ob.CEVModel()
+    np.random.seed(5)
+    a = m.sample_terminal_spot(100.0, 0.05, 1.0, 100_000)
+    np.random.seed(5)
+    b = m.sample_terminal_spot(100.0, 0.05, 1.0, 100_000)
+    assert a.shape == (100_000,) and np.array_equal(a, b)
+    e = levy_goldens["cev"]
+    assert a.mean() == pytest.approx(e["ST_2m_mean"], abs=5 * a.std() * math.sqrt(1 / a.size + 1 / 2e6))
+    # a user-supplied sampler is called as is (monte_carlo.py:103-104)
+    m.sample_terminal_spot = lambda S0, r, T, size: np.full(size, 120.0)
+    call = ob.Option(strike=100.0, maturity=1.0, option_type=ob.OptionType.CALL)
+    assert ob.MonteCarloTechnique(n_paths=10).price(call, STQ, m, RT).price == pytest.approx(
+        20.0 * math.exp(-0.05))
