@@ -97,8 +97,10 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
     constexpr bool JUMPS_AT_END = JUMPS && !PER_STEP && KIND != OPTMC_SABR_JUMP;
     // terminal-only kernels of the log models defer the deterministic drift
     constexpr bool DEFER = !PER_STEP && !kind_sabr(KIND);
-    init_state<KIND, DEFER>(sa, c);
-    init_state<KIND, DEFER>(sb, c);
+    // SABR kinds with the hand-written maths: log-vol form, one exponential per step
+    constexpr bool LOGV = kind_sabr(KIND) && NIMPL == 1;
+    init_state<KIND, DEFER, LOGV>(sa, c);
+    init_state<KIND, DEFER, LOGV>(sb, c);
     // A Box-Muller pair feeds one step of a two-factor model, or two consecutive
     // steps of a one-factor model.  The path kernels of the jump models keep one
     // step per Philox call: every step needs its own Poisson word.
@@ -124,8 +126,8 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
             normal_pair_fast<TWO>(w.x, w.y, w.z, z1, z2, tab);
         }
         if constexpr (TWO) {
-            step_diffusion<KIND, DEFER>(sa, z1, z2, c, tab);
-            if constexpr (ANTI) step_diffusion<KIND, DEFER>(sb, -z1, -z2, c, tab);
+            step_diffusion<KIND, DEFER, LOGV>(sa, z1, z2, c, tab);
+            if constexpr (ANTI) step_diffusion<KIND, DEFER, LOGV>(sb, -z1, -z2, c, tab);
         } else {
             step_diffusion<KIND, DEFER>(sa, z1, 0.0, c, tab);
             if constexpr (ANTI) step_diffusion<KIND, DEFER>(sb, -z1, 0.0, c, tab);

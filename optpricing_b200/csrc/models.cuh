@@ -37,6 +37,7 @@ struct Consts {
     // SABR
     double alpha, beta;
     double neg_half_alpha2_dt;
+    double log_v0;            // ln v0 (SABR kinds, log-vol form; -600 stands for v0 <= 0)
     // correlation of the kernel itself (mc_kernels.py:59,67)
     double rho, rho_bar;
     // Philox mode: (z1, cz) = M (a, b) for iid N(0,1) a, b; sqrt(dt) and, for
@@ -133,12 +134,28 @@ __device__ __forceinline__ double sabr_pow(double s_pos, const Consts &c, RngVie
 
 // sabr_kernel mc_kernels.py:204-216, sabr_jump_kernel :251-258.
 // z1 = dw1; cz = rho*dw1 + rho_bar*dw2.
+// LOGV (device-RNG kernels): the vol recurrence v *= exp(a + alpha cz) is carried as
+// ln v += a + alpha cz, and the diffusion coefficient v s^beta = exp(ln v + beta ln s)
+// costs ONE exponential per step instead of two (the same reals; rounding differs by
+// ~1e-16 per step, so the fed-draw parity kernels keep the literal form).
+template <bool LOGV>
 __device__ __forceinline__ void step_sabr(State &s, double z1, double cz, const Consts &c,
                                           RngView t) {
     double s_pos = fmax(s.x, 1e-8);
-    double v_pos = relu64(s.v);
-    s.x += fma(v_pos * sabr_pow(s_pos, c, t), z1, c.rqc_dt * s_pos);
-    s.v = s.v * fast_exp(fma(c.alpha, cz, c.neg_half_alpha2_dt), t);
+    if constexpr (LOGV) {
+        double coef;
+        switch (c.beta_mode) {
+            case 1: coef = fast_exp(fmax(s.v, -650.0), t) * s_pos; break;
+            case 2: coef = fast_exp(fmax(s.v, -650.0), t); break;
+            default: coef = fast_exp(fmax(fma(c.beta, fast_log(s_pos, t), s.v), -650.0), t);
+        }
+        s.x += fma(coef, z1, c.rqc_dt * s_pos);
+        s.v += fma(c.alpha, cz, c.neg_half_alpha2_dt);
+    } else {
+        double v_pos = relu64(s.v);
+        s.x += fma(v_pos * sabr_pow(s_pos, c, t), z1, c.rqc_dt * s_pos);
+        s.v = s.v * fast_exp(fma(c.alpha, cz, c.neg_half_alpha2_dt), t);
+    }
 }
 
 // Fed mode: the kernel's own correlation step applied to the given increments.
@@ -149,23 +166,23 @@ __device__ __forceinline__ void mix_fed(int kind, double dw1, double dw2, const 
     if (kind == OPTMC_HESTON || kind == OPTMC_BATES) cz *= c.xi;
 }
 
-template <int KIND, bool DEFER = false>
+template <int KIND, bool DEFER = false, bool LOGV = false>
 __device__ __forceinline__ void step_diffusion(State &s, double z1, double cz, const Consts &c,
                                                RngView t) {
     if constexpr (KIND == OPTMC_HESTON || KIND == OPTMC_BATES)
         step_heston<DEFER>(s, z1, cz, c);
     else if constexpr (kind_sabr(KIND))
-        step_sabr(s, z1, cz, c, t);
+        step_sabr<LOGV>(s, z1, cz, c, t);
     else
         step_one_factor<DEFER>(s, z1, c);
 }
 
 // Initial state.  With DEFER the log-spot accumulator starts at 0 and log S_0 is
 // added by finish_deferred; jumps (additive in log space) accumulate in x too.
-template <int KIND, bool DEFER>
+template <int KIND, bool DEFER, bool LOGV = false>
 __device__ __forceinline__ void init_state(State &s, const Consts &c) {
     s.x = (DEFER && !kind_sabr(KIND)) ? 0.0 : c.x0;
-    s.v = c.v0;
+    s.v = (LOGV && kind_sabr(KIND)) ? c.log_v0 : c.v0;
     s.w = 0.0;
 }
 

@@ -205,6 +205,7 @@ static int make_consts(optmc_ctx *ctx, const optmc_model *m, double x0, double d
     c.alpha = m->alpha;
     c.beta = m->beta;
     c.neg_half_alpha2_dt = -0.5 * m->alpha * m->alpha * dt;
+    c.log_v0 = m->v0 > 0.0 ? std::max(std::log(m->v0), -600.0) : -600.0;
     c.beta_mode = m->beta == 1.0 ? 1 : m->beta == 0.0 ? 2 : m->beta == 0.5 ? 3 : 0;
     c.rho = m->rho;
     c.rho_bar = std::sqrt(1 - m->rho * m->rho);                                      // :59
