@@ -237,6 +237,8 @@ int optmc_levy_terminal_async(optmc_ctx *ctx, const optmc_levy *levy, double s0,
  */
 #define OPTMC_LSMC_GRAM 24
 #define OPTMC_LSMC_MAX_DEGREE 7
+#define OPTMC_MAX_PEERS 8
+#define OPTMC_IPC_HANDLE_BYTES 64
 
 int optmc_lsmc_paths_async(optmc_ctx *ctx, const optmc_model *model, const optmc_sim *sim,
                            double *store_dev, int64_t ld, void *stream);
@@ -250,6 +252,26 @@ int optmc_lsmc(optmc_ctx *ctx, const double *store_dev, int64_t ld, int64_t n_pa
                int32_t n_steps, double strike, int32_t is_call, double r, double dt,
                int32_t degree, double *cashflow_dev, double *gram_dev, double *out_host,
                void *stream);
+
+/*
+ * Multi-GPU Longstaff-Schwartz without a collective library on the data path
+ * (SURVEY 8 e2): one process per GPU, each owning its shard of the path store.
+ *   optmc_lsmc_peer_export   writes the CUDA IPC handle (OPTMC_IPC_HANDLE_BYTES) of
+ *                            this ctx's exchange buffer
+ *   optmc_lsmc_peer_attach   handles = world * OPTMC_IPC_HANDLE_BYTES bytes, rank order
+ *                            (all-gathered by the host layer); maps every peer's buffer
+ *                            (NVLink peer access).  world <= OPTMC_MAX_PEERS.
+ *                            Call with world = 1 to detach.
+ * After attach and optmc_set_int(ctx, "lsmc_use_peers", 1), optmc_lsmc runs the
+ * persistent kernel on every rank at once (set it back to 0 for a local call): per
+ * exercise date each rank's power sums cross NVLink as 24 flag-carrying 16-byte
+ * stores into every peer's buffer and every rank adds the rows in rank order, so
+ * all ranks solve bit-identical normal equations; out_host holds the GLOBAL
+ * (n, sum, sum of squares).  Ranks must make the same sequence of attached
+ * optmc_lsmc calls (SPMD); a missing rank ends in a bounded time-out error, not a hang.
+ */
+int optmc_lsmc_peer_export(optmc_ctx *ctx, void *handle_out);
+int optmc_lsmc_peer_attach(optmc_ctx *ctx, int32_t rank, int32_t world, const void *handles);
 
 /*
  * Diagnostics used by the tests and by bench.py's roofline.

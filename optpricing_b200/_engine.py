@@ -25,6 +25,8 @@ CORR_REFERENCE_EUROPEAN = 0
 CORR_INDEPENDENT_DRAWS = 1
 NMOM = 6
 LSMC_GRAM = 24
+MAX_PEERS = 8
+IPC_HANDLE_BYTES = 64
 LEVY_CODES = {"vg": 0, "nig": 1, "cgmy": 2, "hyperbolic": 3, "cev": 4, "lognormal": 5}
 LEVY_NPARAM = 12
 
@@ -87,6 +89,8 @@ SIGNATURES = [
                                       c_i32, c_double, c_i32, c_void_p, c_void_p, c_void_p]),
     ("optmc_lsmc", c_int, [c_void_p, c_void_p, c_i64, c_i64, c_i32, c_double, c_i32, c_double,
                            c_double, c_i32, c_void_p, c_void_p, _dp, c_void_p]),
+    ("optmc_lsmc_peer_export", c_int, [c_void_p, c_void_p]),
+    ("optmc_lsmc_peer_attach", c_int, [c_void_p, c_i32, c_i32, c_void_p]),
     ("optmc_philox_raw", c_int, [c_void_p, c_u64, c_i64, c_u32, c_u32, c_void_p, c_void_p]),
     ("optmc_normals", c_int, [c_void_p, c_u64, c_i64, c_i32, c_void_p, c_void_p]),
     ("optmc_fp64_peak", c_int, [c_void_p, c_i64, _dp, _dp]),
@@ -353,8 +357,14 @@ class Engine:
                                                    n_paths, n_steps, c_void_p(store.data_ptr()),
                                                    ld, self.stream()), "optmc_lsmc_load_async")
 
-    def lsmc(self, store, ld, n_paths, n_steps, strike, is_call, r, dt, degree):
-        """Single-GPU induction: returns (n, sum, sum_sq) of discounted cashflows."""
+    def lsmc(self, store, ld, n_paths, n_steps, strike, is_call, r, dt, degree, peers=False):
+        """
+        The whole induction in one call: returns (n, sum, sum_sq) of the discounted
+        cashflows.  ``peers=True`` (after ``lsmc_peer_attach``): a joint call of all
+        attached ranks over their shards; the sums are global.
+        """
+        if peers or getattr(self, "_peer_key", None) is not None:
+            self.set_int("lsmc_use_peers", 1 if peers else 0)
         cash = self.buffer("lsmc_cash", n_paths)
         gram = self.buffer("lsmc_gram", LSMC_GRAM * n_steps)
         out = np.empty(3)
@@ -364,6 +374,39 @@ class Engine:
                                         c_void_p(gram.data_ptr()), out.ctypes.data_as(_dp),
                                         self.stream()), "optmc_lsmc")
         return out
+
+    def lsmc_peer_attach(self, group=None):
+        """
+        Map every rank's exchange buffer into this process (CUDA IPC over NVLink) so
+        that ``lsmc`` runs the persistent kernel on all ranks at once, the per-date
+        Gram all-reduce fused into it.  Collective over ``group`` (default: world);
+        idempotent per group.  Returns (rank, world).
+        """
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        key = (id(group), rank, world)
+        if getattr(self, "_peer_key", None) == key:
+            return rank, world
+        if world > MAX_PEERS:
+            raise EngineError(f"NVLink exchange supports at most {MAX_PEERS} ranks (one node)")
+        mine = (ctypes.c_ubyte * IPC_HANDLE_BYTES)()
+        self._check(self.lib.optmc_lsmc_peer_export(self.ctx, mine), "optmc_lsmc_peer_export")
+        t = self.torch.tensor(list(mine), dtype=self.torch.uint8, device=self.device)
+        gathered = [self.torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t, group=group)
+        blob = bytes(self.torch.cat(gathered).cpu().numpy().tobytes())
+        self._check(self.lib.optmc_lsmc_peer_attach(self.ctx, rank, world, blob),
+                    "optmc_lsmc_peer_attach")
+        dist.barrier(group=group)          # every rank has mapped every buffer before first use
+        self._peer_key = key
+        return rank, world
+
+    def lsmc_peer_detach(self):
+        if getattr(self, "_peer_key", None) is not None:
+            self._check(self.lib.optmc_lsmc_peer_attach(self.ctx, 0, 1, None),
+                        "optmc_lsmc_peer_attach")
+            self._peer_key = None
 
     def lsmc_distributed(self, store, ld, n_paths, n_steps, strike, is_call, r, dt, degree,
                          all_reduce):

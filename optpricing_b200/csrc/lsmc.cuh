@@ -312,6 +312,12 @@ struct LsmcPersistArgs {
     double *cashflow;
     uint4 *slots;              // [2][gridDim.x][LSMC_P_STRIDE], flag-carrying partials
     uint32_t nonce;            // per-launch tag prefix
+    // multi-GPU (world > 1): rank totals travel over NVLink as the same kind of slots.
+    // peer_rank_slots[r] is rank r's buffer [2 call parity][2 epoch parity][world][LSMC_P_STRIDE]
+    // mapped into this process (CUDA IPC); [rank] is the local one.
+    int rank, world;
+    uint32_t peer_nonce;       // per distributed call, identical on every rank
+    uint4 *peer_rank_slots[OPTMC_MAX_PEERS];
     unsigned int *error;       // set to 1 if an exchange times out
     double *gram;              // [n_steps][OPTMC_LSMC_GRAM], written by block 0
     unsigned long long *timing;   // optional [n_steps + 1][4] globaltimer stamps of block 0 (ns)
@@ -330,6 +336,14 @@ __device__ __forceinline__ void ll_store(uint4 *slot, double v, uint32_t tag) {
                  : "memory");
 }
 
+// the same store towards a peer GPU's memory (system scope: it crosses NVLink)
+__device__ __forceinline__ void ll_store_sys(uint4 *slot, double v, uint32_t tag) {
+    uint32_t lo = (uint32_t)__double2loint(v), hi = (uint32_t)__double2hiint(v);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(slot), "r"(lo), "r"(tag),
+                 "r"(hi), "r"(tag)
+                 : "memory");
+}
+
 __device__ __forceinline__ uint4 ll_peek(const uint4 *slot) {
     uint4 w;
     asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
@@ -339,11 +353,14 @@ __device__ __forceinline__ uint4 ll_peek(const uint4 *slot) {
     return w;
 }
 
-// `w` is a first look at the slot; spin until both halves carry `tag`.  False on timeout.
-__device__ __forceinline__ bool ll_wait(const uint4 *slot, uint32_t tag, uint4 w, double &v) {
+// `w` is a first look at the slot; spin until both halves carry `tag`.  False on timeout
+// (a lost block or rank, never the normal path: ~ seconds, and only the first wait of a
+// thread pays it -- callers stop waiting once they have seen one).
+__device__ __forceinline__ bool ll_wait(const uint4 *slot, uint32_t tag, uint4 w, double &v,
+                                        bool dead = false) {
     unsigned int spins = 0;
     while (w.y != tag || w.w != tag) {
-        if (++spins > (1u << 24)) return false;     // ~ seconds: a lost block, never the normal path
+        if (dead || ++spins > (1u << 22)) return false;
         w = ll_peek(slot);
     }
     v = __hiloint2double((int)w.z, (int)w.x);
@@ -463,7 +480,7 @@ k_lsmc_persistent(const LsmcPersistArgs A) {
                     if (i < n_slots) {
                         const unsigned int b = i / NV, e = i % NV;
                         double v = 0.0;
-                        if (!ll_wait(src + (size_t)b * LSMC_P_STRIDE + e, tag, w[j], v))
+                        if (!ll_wait(src + (size_t)b * LSMC_P_STRIDE + e, tag, w[j], v, timed_out))
                             timed_out = true;
                         vals[e * GPAD + b] = v;
                     }
@@ -478,6 +495,33 @@ k_lsmc_persistent(const LsmcPersistArgs A) {
                 if (lane == 0) tot[e < NP ? e : 16 + (e - NP)] = t;
             }
             __syncthreads();
+            if (A.world > 1) {
+                // Second level, across GPUs: block 0 stores this rank's totals into every
+                // rank's buffer (peer stores over NVLink), every block of every rank polls
+                // its LOCAL copy and adds the W rows in rank order -- the all-reduce of the
+                // Gram matrix fused into the induction kernel, one NVLink hop per date.
+                const uint32_t ptag = (A.peer_nonce << 12) | ((epoch - 1) & 0xFFFu);
+                const size_t base = (((size_t)(A.peer_nonce & 1u) * 2 + ((epoch - 1) & 1u)) * A.world) *
+                                    LSMC_P_STRIDE;
+                if (blockIdx.x == 0 && threadIdx.x < OPTMC_LSMC_GRAM * A.world) {
+                    const int r = threadIdx.x / OPTMC_LSMC_GRAM, e = threadIdx.x % OPTMC_LSMC_GRAM;
+                    ll_store_sys(A.peer_rank_slots[r] + base + (size_t)A.rank * LSMC_P_STRIDE + e,
+                                 tot[e], ptag);
+                }
+                __syncthreads();         // everyone has read its own tot[] before it is overwritten
+                double v = 0.0;
+                if (threadIdx.x < OPTMC_LSMC_GRAM) {
+                    const uint4 *mine = A.peer_rank_slots[A.rank] + base + threadIdx.x;
+                    for (int r = 0; r < A.world; ++r) {
+                        double x = 0.0;
+                        const uint4 *slot = mine + (size_t)r * LSMC_P_STRIDE;
+                        if (!ll_wait(slot, ptag, ll_peek(slot), x, timed_out)) timed_out = true;
+                        v += x;
+                    }
+                    tot[threadIdx.x] = v;
+                }
+                __syncthreads();
+            }
             if (warp == 0) {
                 if (blockIdx.x == 0 && lane < OPTMC_LSMC_GRAM)
                     A.gram[(size_t)(date + 1) * OPTMC_LSMC_GRAM + lane] = tot[lane];

@@ -34,6 +34,12 @@ struct optmc_ctx {
     uint4 *lsmc_slots = nullptr;       // device: flag-carrying partial sums of k_lsmc_persistent
     uint32_t lsmc_nonce = 0;
     unsigned long long *lsmc_timing = nullptr;   // diagnostics: see optmc_set_ptr("lsmc_timing")
+    // multi-GPU exchange of k_lsmc_persistent (optmc_lsmc_peer_*)
+    uint4 *rank_slots = nullptr;                 // local buffer, exported over CUDA IPC
+    uint4 *peer_rank_slots[OPTMC_MAX_PEERS] = {};
+    int peer_rank = 0, peer_world = 1;
+    int use_peers = 0;                           // "lsmc_use_peers": next optmc_lsmc is a joint call
+    uint32_t peer_nonce = 0;
     std::string err;
 };
 
@@ -105,6 +111,11 @@ extern "C" int optmc_ctx_create(int device, optmc_ctx **out) {
                            cudaHostAllocDefault)) != cudaSuccess)
         return fail(e, "cudaHostAlloc");
     {
+        const size_t bytes = sizeof(uint4) * 4 * OPTMC_MAX_PEERS * LSMC_P_STRIDE;
+        if ((e = cudaMalloc(&ctx->rank_slots, bytes)) != cudaSuccess) return fail(e, "cudaMalloc");
+        if ((e = cudaMemset(ctx->rank_slots, 0, bytes)) != cudaSuccess) return fail(e, "cudaMemset");
+    }
+    {
         RngBase *h = new RngBase();
         const double pi = 3.14159265358979323846;
         for (int i = 0; i < LOG_N; ++i) {
@@ -140,6 +151,10 @@ extern "C" void optmc_ctx_destroy(optmc_ctx *ctx) {
     cudaFree(ctx->moments_dev);
     cudaFree(ctx->ticket);
     cudaFree(ctx->lsmc_slots);
+    for (int r = 0; r < ctx->peer_world; ++r)
+        if (ctx->peer_world > 1 && r != ctx->peer_rank && ctx->peer_rank_slots[r])
+            cudaIpcCloseMemHandle(ctx->peer_rank_slots[r]);
+    cudaFree(ctx->rank_slots);
     cudaFreeHost(ctx->moments_host);
     delete ctx;
 }
@@ -159,6 +174,10 @@ extern "C" int optmc_set_int(optmc_ctx *ctx, const char *key, int64_t value) {
     } else if (!strcmp(key, "euro_threads")) {
         if (value != 64 && value != 128 && value != 256) FAIL("euro_threads must be 64, 128 or 256");
         ctx->euro_threads = (int)value;
+    } else if (!strcmp(key, "lsmc_use_peers")) {
+        if (value != 0 && value != 1) FAIL("lsmc_use_peers must be 0 or 1");
+        if (value == 1 && ctx->peer_world < 2) FAIL("no peers attached (optmc_lsmc_peer_attach)");
+        ctx->use_peers = (int)value;
     } else if (!strcmp(key, "lsmc_mode")) {
         if (value != 0 && value != 1) FAIL("lsmc_mode must be 0 (launch per date) or 1 (persistent)");
         ctx->lsmc_mode = (int)value;
@@ -734,6 +753,15 @@ static int lsmc_persistent(optmc_ctx *ctx, const double *store_dev, int64_t ld, 
     A.error = ctx->ticket + 8;
     A.gram = gram_dev;
     A.timing = ctx->lsmc_timing;
+    const bool joint = ctx->use_peers && ctx->peer_world > 1;
+    A.rank = joint ? ctx->peer_rank : 0;
+    A.world = joint ? ctx->peer_world : 1;
+    for (int r = 0; r < OPTMC_MAX_PEERS; ++r) A.peer_rank_slots[r] = ctx->peer_rank_slots[r];
+    if (joint) {
+        ctx->peer_nonce = (ctx->peer_nonce + 1) & 0xFFFFFu;
+        if (ctx->peer_nonce == 0) ctx->peer_nonce = 2;       // keeps the call parity alternating
+    }
+    A.peer_nonce = ctx->peer_nonce;
     CK(cudaMemsetAsync(ctx->ticket + 8, 0, 4, st));
     int rc = 0;
     switch (degree) {
@@ -748,6 +776,49 @@ static int lsmc_persistent(optmc_ctx *ctx, const double *store_dev, int64_t ld, 
     return rc;
 }
 
+extern "C" int optmc_lsmc_peer_export(optmc_ctx *ctx, void *handle_out) {
+    if (!ctx) return -2;
+    CK(cudaSetDevice(ctx->device));
+    if (!handle_out) FAIL("handle_out is null");
+    static_assert(sizeof(cudaIpcMemHandle_t) == OPTMC_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ctx->rank_slots));
+    memcpy(handle_out, &h, sizeof h);
+    return 0;
+}
+
+extern "C" int optmc_lsmc_peer_attach(optmc_ctx *ctx, int32_t rank, int32_t world,
+                                      const void *handles) {
+    if (!ctx) return -2;
+    CK(cudaSetDevice(ctx->device));
+    if (world < 1 || world > OPTMC_MAX_PEERS || rank < 0 || rank >= world) FAIL("bad rank / world");
+    for (int r = 0; r < ctx->peer_world; ++r)          // drop an earlier attachment
+        if (ctx->peer_world > 1 && r != ctx->peer_rank && ctx->peer_rank_slots[r])
+            cudaIpcCloseMemHandle(ctx->peer_rank_slots[r]);
+    for (int r = 0; r < OPTMC_MAX_PEERS; ++r) ctx->peer_rank_slots[r] = nullptr;
+    ctx->peer_rank = 0;
+    ctx->peer_world = 1;
+    ctx->peer_nonce = 0;
+    ctx->use_peers = 0;
+    CK(cudaMemset(ctx->rank_slots, 0, sizeof(uint4) * 4 * OPTMC_MAX_PEERS * LSMC_P_STRIDE));
+    if (world == 1) return 0;
+    if (!handles) FAIL("handles is null");
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            ctx->peer_rank_slots[r] = ctx->rank_slots;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char *>(handles) + (size_t)r * OPTMC_IPC_HANDLE_BYTES, sizeof h);
+        void *p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_rank_slots[r] = static_cast<uint4 *>(p);
+    }
+    ctx->peer_rank = rank;
+    ctx->peer_world = world;
+    return 0;
+}
+
 extern "C" int optmc_lsmc(optmc_ctx *ctx, const double *store_dev, int64_t ld, int64_t n_paths,
                           int32_t n_steps, double strike, int32_t is_call, double r, double dt,
                           int32_t degree, double *cashflow_dev, double *gram_dev, double *out_host,
@@ -756,7 +827,7 @@ extern "C" int optmc_lsmc(optmc_ctx *ctx, const double *store_dev, int64_t ld, i
     if (!out_host) FAIL("out_host is null");
     const double disc = std::exp(-r * dt);                       // american_mc_kernels.py:54
     cudaStream_t st = (cudaStream_t)stream;
-    if (ctx->lsmc_mode == 1) {
+    if (ctx->lsmc_mode == 1 || (ctx->use_peers && ctx->peer_world > 1)) {
         int rc = lsmc_persistent(ctx, store_dev, ld, n_paths, n_steps, strike, is_call, disc, degree,
                                  cashflow_dev, gram_dev, st);
         if (rc) return rc;

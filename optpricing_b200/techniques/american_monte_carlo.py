@@ -41,16 +41,19 @@ _PATH_KERNELS = {
 class AmericanMonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
     def __init__(self, *, n_paths: int = 20_000, n_steps: int = 100, antithetic: bool = True,
                  seed: int | None = None, lsm_degree: int = 2, rng_mode: str = "philox",
-                 distributed: bool | None = None):
+                 distributed: bool | None = None, exchange: str = "nvlink"):
         if antithetic and n_paths % 2 != 0:
             n_paths += 1                       # american_monte_carlo.py:44-45
         if rng_mode not in ("philox", "numpy"):
             raise ValueError("rng_mode must be 'philox' or 'numpy'")
+        if exchange not in ("nvlink", "nccl"):
+            raise ValueError("exchange must be 'nvlink' or 'nccl'")
         self.n_paths = n_paths
         self.n_steps = n_steps
         self.antithetic = antithetic
         self.rng = np.random.default_rng(seed)
         self.lsm_degree = lsm_degree
+        self.exchange = exchange
         self.rng_mode = rng_mode
         self.distributed = distributed
 
@@ -59,12 +62,26 @@ class AmericanMonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
             raise TypeError("American MC pricing requires an SDE model.")
         spot_paths = self._simulate_full_sde_paths(option, stock, model, rate, _handle=True,
                                                    **kwargs)
-        _, _, all_reduce = self._group()
+        _, world, all_reduce = self._group()
+        sharded = world > 1 and isinstance(spot_paths, DevicePathStore)
+        # Several ranks: the per-date Gram exchange runs inside the persistent kernel
+        # over NVLink peer memory (default), or as one NCCL all-reduce per date.
+        peers = sharded and self.exchange == "nvlink" and self._nvlink_ready(spot_paths.engine)
         value = longstaff_schwartz_pricer(
             stock_paths=spot_paths, K=option.strike, dt=option.maturity / self.n_steps,
             r=rate.get_rate(option.maturity), is_call=_is_call(option), degree=self.lsm_degree,
-            all_reduce=all_reduce if isinstance(spot_paths, DevicePathStore) else None)
+            all_reduce=all_reduce if sharded and not peers else None, peers=peers)
         return PricingResult(price=value)
+
+    @staticmethod
+    def _nvlink_ready(eng) -> bool:
+        """Attach the ranks' exchange buffers (once per group); NCCL groups only."""
+        import torch.distributed as dist
+
+        if dist.get_backend() != "nccl":
+            return False
+        eng.lsmc_peer_attach()
+        return True
 
     def _group(self):
         if self.distributed is False:

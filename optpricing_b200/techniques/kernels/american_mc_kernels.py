@@ -31,10 +31,14 @@ class DevicePathStore:
         return out if dtype is None else out.astype(dtype)
 
 
-def longstaff_schwartz_pricer(stock_paths, K, dt, r, is_call, degree, all_reduce=None):
+def longstaff_schwartz_pricer(stock_paths, K, dt, r, is_call, degree, all_reduce=None,
+                              peers=False):
     """
-    Returns the price as a float.  ``all_reduce`` (optional) sums a device
-    tensor across ranks; with it, the paths given here are this rank's shard.
+    Returns the price as a float.  With several ranks the paths given here are
+    this rank's shard and the per-date power sums are exchanged either inside the
+    kernel over NVLink peer memory (``peers=True``, after
+    ``engine.lsmc_peer_attach()``) or by ``all_reduce`` (sums a device tensor
+    across ranks in place, e.g. NCCL) between per-date launches.
     """
     if isinstance(stock_paths, DevicePathStore):
         h = stock_paths
@@ -50,8 +54,9 @@ def longstaff_schwartz_pricer(stock_paths, K, dt, r, is_call, degree, all_reduce
         store, ld = eng.lsmc_store(n_paths, n_steps)
         eng.lsmc_load(dev, n_paths, n_steps, store, ld)
         h = DevicePathStore(eng, store, ld, n_paths, n_steps, float(host[0, 0]))
-    if all_reduce is None:
-        n, s, _ = eng.lsmc(h.store, h.ld, h.n_paths, h.n_steps, K, bool(is_call), r, dt, degree)
+    if peers or all_reduce is None:
+        n, s, _ = eng.lsmc(h.store, h.ld, h.n_paths, h.n_steps, K, bool(is_call), r, dt, degree,
+                           peers=peers)
     else:
         n, s, _ = eng.lsmc_distributed(h.store, h.ld, h.n_paths, h.n_steps, K, bool(is_call), r,
                                        dt, degree, all_reduce)

@@ -37,15 +37,30 @@ for name, model in (("heston", ob.HestonModel()), ("bates", ob.BatesModel()),
         print(f"european {name:9s} world={world}: distributed {d:.12f} single {s:.12f} {'ok' if ok else 'MISMATCH'}")
     if not ok:
         fails.append(name)
+import time
 for name, model, deg in (("bsm", ob.BSMModel(), 3), ("heston", ob.HestonModel(), 2)):
     kw = dict(n_paths=(1 << 19) + 2, n_steps=20, seed=5, lsm_degree=deg)
-    d = ob.AmericanMonteCarloTechnique(**kw).price(aput, stock, model, rate).price
     s = ob.AmericanMonteCarloTechnique(distributed=False, **kw).price(aput, stock, model, rate).price
-    ok = abs(d - s) <= 1e-9 * abs(s)
+    for exchange in ("nvlink", "nccl", "nvlink"):
+        d = ob.AmericanMonteCarloTechnique(exchange=exchange, **kw).price(aput, stock, model, rate).price
+        ok = abs(d - s) <= 1e-9 * abs(s)
+        if rank == 0:
+            print(f"american {name:9s} world={world} {exchange:6s}: distributed {d:.12f} single {s:.12f} "
+                  f"{'ok' if ok else 'MISMATCH'}")
+        if not ok:
+            fails.append(f"lsmc_{name}_{exchange}")
+# timing of the two exchanges at BASELINE config 4 (2^22 paths x 50 dates, cubic basis)
+for exchange in ("nvlink", "nccl"):
+    t = ob.AmericanMonteCarloTechnique(n_paths=1 << 22, n_steps=50, seed=1, lsm_degree=3, exchange=exchange)
+    for _ in range(3):
+        p = t.price(aput, stock, ob.BSMModel(), rate).price
+    torch.cuda.synchronize(); dist.barrier(); t0 = time.perf_counter()
+    for _ in range(10):
+        p = t.price(aput, stock, ob.BSMModel(), rate).price
+    torch.cuda.synchronize(); dist.barrier(); ms = (time.perf_counter() - t0) * 100
     if rank == 0:
-        print(f"american {name:9s} world={world}: distributed {d:.12f} single {s:.12f} {'ok' if ok else 'MISMATCH'}")
-    if not ok:
-        fails.append("lsmc_" + name)
+        print(f"C4 american put 2^22 x 50 deg 3, world={world}, exchange={exchange}: {ms:.3f} ms per price "
+              f"({(1 << 22) * 50 / ms / 1e6:.1f} G path-steps/s), price {p:.4f}")
 t = torch.tensor([len(fails)], device="cuda")
 dist.all_reduce(t)
 dist.destroy_process_group()
