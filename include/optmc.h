@@ -40,7 +40,8 @@ enum optmc_model_kind {
     OPTMC_BATES = 3,     /* mc_kernels.py:127-177         path_kernels.py:130-180 */
     OPTMC_SABR = 4,      /* mc_kernels.py:186-218         path_kernels.py:189-217 */
     OPTMC_SABR_JUMP = 5, /* mc_kernels.py:227-276         path_kernels.py:225-274 */
-    OPTMC_KOU = 6        /* mc_kernels.py:285-329         path_kernels.py:277-324 */
+    OPTMC_KOU = 6,       /* mc_kernels.py:285-329         path_kernels.py:277-324 */
+    OPTMC_DUPIRE = 7     /* mc_kernels.py:340-359 (European only; see lv_* below)  */
 };
 
 /* The reference's kernel_params dict (monte_carlo.py:128-197), flattened.
@@ -55,6 +56,16 @@ typedef struct optmc_model {
     double alpha, beta; /* SABR */
     double lambda, mu_j, sigma_j;         /* Merton, Bates, SABR-jump */
     double p_up, eta1, eta2;              /* Kou */
+    /* Dupire local volatility.  The reference's dupire_kernel calls a Python
+       vol_surface_func(t_i, S) from inside the step loop (mc_kernels.py:351-357),
+       which cannot run on a device (nor, in fact, under numba's nopython mode).
+       Here the host samples that callable once per pricing into a device table
+       lv_table_dev[i * lv_n_s + j] = vol_surface(i * dt, exp(lv_log_s_lo + j / lv_inv_h)),
+       i < lv_n_t (>= n_steps: exactly the times the kernel evaluates), and the
+       step interpolates linearly in log S (flat beyond the ends). */
+    const double *lv_table_dev;
+    int32_t lv_n_s, lv_n_t;
+    double lv_log_s_lo, lv_inv_h;
 } optmc_model;
 
 /* How the two Brownian drivers of a variance model are mixed (Philox mode). */

@@ -13,7 +13,8 @@ Importing the package needs neither a GPU nor the built library; pricing does,
 and fails loudly without them (there is no CPU fallback).
 """
 from .atoms import ExerciseStyle, Option, OptionType, Rate, Stock
-from .models import (BatesModel, BSMModel, CEVModel, CGMYModel, HestonModel, HyperbolicModel,
+from .models import (BatesModel, BSMModel, CEVModel, CGMYModel, DupireLocalVolModel, HestonModel,
+                     HyperbolicModel,
                      KouModel, MertonJumpModel, NIGModel, SABRJumpModel, SABRModel,
                      VarianceGammaModel, levy_kind, model_kind)
 from .techniques import (AmericanMonteCarloTechnique, BaseTechnique, GreekMixin, IVMixin,
@@ -24,7 +25,7 @@ __version__ = "0.1.0"
 __all__ = [
     "Option", "OptionType", "ExerciseStyle", "Stock", "Rate",
     "BSMModel", "HestonModel", "MertonJumpModel", "BatesModel", "KouModel", "SABRModel",
-    "SABRJumpModel", "VarianceGammaModel", "NIGModel", "CGMYModel", "HyperbolicModel", "CEVModel",
+    "SABRJumpModel", "DupireLocalVolModel", "VarianceGammaModel", "NIGModel", "CGMYModel", "HyperbolicModel", "CEVModel",
     "model_kind", "levy_kind",
     "MonteCarloTechnique", "AmericanMonteCarloTechnique", "BaseTechnique", "GreekMixin",
     "IVMixin", "PricingResult", "crn",

@@ -17,7 +17,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("OPTMC_LIB") or os.path.join(_HERE, "liboptmc.so")
 
-KIND_CODES = {"bsm": 0, "heston": 1, "merton": 2, "bates": 3, "sabr": 4, "sabr_jump": 5, "kou": 6}
+KIND_CODES = {"bsm": 0, "heston": 1, "merton": 2, "bates": 3, "sabr": 4, "sabr_jump": 5, "kou": 6,
+              "dupire": 7}
 TWO_FACTOR = ("heston", "bates", "sabr", "sabr_jump")
 JUMP_KINDS = ("merton", "bates", "sabr_jump", "kou")
 SABR_KINDS = ("sabr", "sabr_jump")
@@ -44,7 +45,8 @@ class OptmcModel(ctypes.Structure):
                 ("rho", c_double), ("vol_of_vol", c_double), ("alpha", c_double),
                 ("beta", c_double), ("lambda_", c_double), ("mu_j", c_double),
                 ("sigma_j", c_double), ("p_up", c_double), ("eta1", c_double),
-                ("eta2", c_double)]
+                ("eta2", c_double), ("lv_table_dev", c_void_p), ("lv_n_s", c_i32),
+                ("lv_n_t", c_i32), ("lv_log_s_lo", c_double), ("lv_inv_h", c_double)]
 
 
 class OptmcSim(ctypes.Structure):
@@ -123,7 +125,51 @@ def load_library() -> ctypes.CDLL:
     return _lib
 
 
-def make_model(kind: str, params: dict, r: float, q: float, v0=None) -> OptmcModel:
+class LocalVolTable:
+    """
+    A Dupire local-vol surface sampled for one simulation: ``table`` is a device
+    tensor [n_t, n_s] with table[i, j] = vol_surface(i * dt, exp(lo + j * h)).
+    The model struct keeps a raw pointer into it, so hold on to this object for
+    as long as the struct is in use.
+    """
+
+    def __init__(self, table, lo: float, h: float):
+        self.table, self.lo, self.h = table, float(lo), float(h)
+        self.n_t, self.n_s = int(table.shape[0]), int(table.shape[1])
+
+
+def sample_local_vol(vol_surface, n_steps: int, dt: float, log_s0: float, r: float, q: float,
+                     n_s: int = 1024, half_width: float | None = None):
+    """
+    Host side of the Dupire kernel: evaluate ``vol_surface(t, S)`` -- the callable
+    the reference calls from inside its step loop (mc_kernels.py:351-357) -- at
+    the n_steps times the kernel uses and n_s spots equally spaced in log S.
+    Returns (numpy table [n_steps, n_s], lo, h).  The grid spans
+    log S0 +- half_width (default: 10 standard deviations of the largest
+    at-the-money vol plus the drift, at least 1.5); beyond it the surface is flat.
+    """
+    import math
+
+    T = n_steps * dt
+    times = [i * dt for i in range(n_steps)]
+    if half_width is None:
+        s0 = math.exp(log_s0)
+        atm = max(abs(float(np.max(np.asarray(vol_surface(t, np.array([s0])), dtype=float))))
+                  for t in times[:: max(1, n_steps // 16)])
+        half_width = max(1.5, 10.0 * atm * math.sqrt(T) + abs(r - q) * T)
+    lo, hi = log_s0 - half_width, log_s0 + half_width
+    grid = np.linspace(lo, hi, int(n_s))
+    spots = np.exp(grid)
+    table = np.empty((n_steps, int(n_s)))
+    for i, t in enumerate(times):
+        table[i] = np.broadcast_to(np.asarray(vol_surface(t, spots), dtype=float), spots.shape)
+    if not np.all(np.isfinite(table)):
+        raise ValueError("vol_surface returned non-finite local volatilities")
+    return table, lo, (hi - lo) / (int(n_s) - 1)
+
+
+def make_model(kind: str, params: dict, r: float, q: float, v0=None,
+               local_vol: LocalVolTable | None = None) -> OptmcModel:
     """
     Flatten the reference's ``kernel_params`` (monte_carlo.py:128-197) into
     struct optmc_model.  ``v0`` follows the reference: kwarg first, then
@@ -133,6 +179,13 @@ def make_model(kind: str, params: dict, r: float, q: float, v0=None) -> OptmcMod
     m.kind = KIND_CODES[kind]
     m.r, m.q = float(r), float(q)
     p = params
+    if kind == "dupire":
+        if local_vol is None:
+            raise ValueError("the Dupire kernel needs a sampled surface (sample_local_vol)")
+        m.lv_table_dev = local_vol.table.data_ptr()
+        m.lv_n_s, m.lv_n_t = local_vol.n_s, local_vol.n_t
+        m.lv_log_s_lo, m.lv_inv_h = local_vol.lo, 1.0 / local_vol.h
+        return m
     if kind in ("bsm", "merton", "kou"):
         m.sigma = float(p["sigma"])
     if kind in ("heston", "bates"):
@@ -295,6 +348,13 @@ class Engine:
         if not to_host:
             return mom
         return mom[: k.size * NMOM].cpu().numpy().reshape(k.size, NMOM)
+
+    def local_vol_table(self, vol_surface, n_steps, dt, log_s0, r, q, n_s=1024,
+                        half_width=None) -> LocalVolTable:
+        """Sample a Dupire surface on the host and place the table in HBM."""
+        table, lo, h = sample_local_vol(vol_surface, n_steps, dt, log_s0, r, q, n_s, half_width)
+        dev = self.torch.from_numpy(np.ascontiguousarray(table)).to(self.device)
+        return LocalVolTable(dev, lo, h)
 
     # -- single-step terminal samplers --------------------------------------
     def levy_terminal_async(self, levy: OptmcLevy, s0, drift, seed, offset, n_local, strikes,

@@ -96,7 +96,7 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
     // path kernels keep the per-step form.
     constexpr bool JUMPS_AT_END = JUMPS && !PER_STEP && KIND != OPTMC_SABR_JUMP;
     // terminal-only kernels of the log models defer the deterministic drift
-    constexpr bool DEFER = !PER_STEP && !kind_sabr(KIND);
+    constexpr bool DEFER = !PER_STEP && !kind_sabr(KIND) && KIND != OPTMC_DUPIRE;
     // SABR kinds with the hand-written maths: log-vol form, one exponential per step
     constexpr bool LOGV = kind_sabr(KIND) && NIMPL == 1;
     init_state<KIND, DEFER, LOGV>(sa, c);
@@ -126,16 +126,16 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
             normal_pair_fast<TWO>(w.x, w.y, w.z, z1, z2, tab);
         }
         if constexpr (TWO) {
-            step_diffusion<KIND, DEFER, LOGV>(sa, z1, z2, c, tab);
-            if constexpr (ANTI) step_diffusion<KIND, DEFER, LOGV>(sb, -z1, -z2, c, tab);
+            step_diffusion<KIND, DEFER, LOGV>(sa, z1, z2, c, tab, i);
+            if constexpr (ANTI) step_diffusion<KIND, DEFER, LOGV>(sb, -z1, -z2, c, tab, i);
         } else {
-            step_diffusion<KIND, DEFER>(sa, z1, 0.0, c, tab);
-            if constexpr (ANTI) step_diffusion<KIND, DEFER>(sb, -z1, 0.0, c, tab);
+            step_diffusion<KIND, DEFER>(sa, z1, 0.0, c, tab, i);
+            if constexpr (ANTI) step_diffusion<KIND, DEFER>(sb, -z1, 0.0, c, tab, i);
             if constexpr (SPC == 2) {
                 if constexpr (PER_STEP) sink(i, sa, sb);
                 if (i + 1 < A.n_steps) {
-                    step_diffusion<KIND, DEFER>(sa, z2, 0.0, c, tab);
-                    if constexpr (ANTI) step_diffusion<KIND, DEFER>(sb, -z2, 0.0, c, tab);
+                    step_diffusion<KIND, DEFER>(sa, z2, 0.0, c, tab, i + 1);
+                    if constexpr (ANTI) step_diffusion<KIND, DEFER>(sb, -z2, 0.0, c, tab, i + 1);
                     if constexpr (PER_STEP) sink(i + 1, sa, sb);
                 }
             }

@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(FED_P) k_fed(const FedArgs A) {
                 mix_fed(KIND, A.sign * t1[tid][j], A.sign * t2[tid][j], c, z1, cz);
             else
                 z1 = A.sign * t1[tid][j];
-            step_diffusion<KIND>(s, z1, cz, c, tv);
+            step_diffusion<KIND>(s, z1, cz, c, tv, t0 + j);
             if constexpr (JUMPS) {
                 int n = cnt[tid][j];
                 if (n > 0) {

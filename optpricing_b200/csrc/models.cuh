@@ -48,6 +48,11 @@ struct Consts {
     double mu_j, sigma_j;
     double p_up, inv_eta1, inv_eta2;
     uint32_t p_up_bits;
+    // Dupire: sigma(t_i, S) table, rows = steps, columns = nodes equally spaced in log S
+    const double *lv_table;
+    int lv_n_s;
+    double lv_lo, lv_inv_h, lv_max_u;
+    double rq;                // r - q
 };
 
 __host__ __device__ constexpr bool kind_two_factor(int k) {
@@ -121,6 +126,19 @@ __device__ __forceinline__ void finish_deferred(State &s, const Consts &c) {
     }
 }
 
+// dupire_kernel mc_kernels.py:351-357: local_vol = vol_surface(i dt, exp(log_s));
+// log_s += (r - q - local_vol^2 / 2) dt + local_vol dw.  The surface is the table
+// described in optmc.h, linear in log S between nodes, flat outside.
+__device__ __forceinline__ void step_dupire(State &s, double dw, int i, const Consts &c) {
+    const double *row = c.lv_table + (size_t)i * c.lv_n_s;
+    double u = fmin(fmax((s.x - c.lv_lo) * c.lv_inv_h, 0.0), c.lv_max_u);
+    int j = (int)u;                                   // lv_max_u < n_s - 1: j + 1 is a node
+    double f = u - (double)j;
+    double a = __ldg(row + j), b = __ldg(row + j + 1);
+    double vol = fma(f, b - a, a);
+    s.x += fma(vol, dw, fma(-0.5 * vol, vol, c.rq) * c.dt);
+}
+
 // s_pos ** beta (mc_kernels.py:211): exp(beta ln s) on the table-driven helpers,
 // with the exact special cases beta in {1, 0, 1/2}.
 __device__ __forceinline__ double sabr_pow(double s_pos, const Consts &c, RngView t) {
@@ -168,8 +186,10 @@ __device__ __forceinline__ void mix_fed(int kind, double dw1, double dw2, const 
 
 template <int KIND, bool DEFER = false, bool LOGV = false>
 __device__ __forceinline__ void step_diffusion(State &s, double z1, double cz, const Consts &c,
-                                               RngView t) {
-    if constexpr (KIND == OPTMC_HESTON || KIND == OPTMC_BATES)
+                                               RngView t, int i) {
+    if constexpr (KIND == OPTMC_DUPIRE)
+        step_dupire(s, z1, i, c);
+    else if constexpr (KIND == OPTMC_HESTON || KIND == OPTMC_BATES)
         step_heston<DEFER>(s, z1, cz, c);
     else if constexpr (kind_sabr(KIND))
         step_sabr<LOGV>(s, z1, cz, c, t);

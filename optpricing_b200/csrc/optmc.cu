@@ -138,7 +138,7 @@ extern "C" int optmc_ctx_create(int device, optmc_ctx **out) {
     cudaFuncSetAttribute(k_fed<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                          (int)fed_smem_bytes())
     FED_ATTR(OPTMC_HESTON); FED_ATTR(OPTMC_MERTON); FED_ATTR(OPTMC_BATES);
-    FED_ATTR(OPTMC_SABR); FED_ATTR(OPTMC_SABR_JUMP); FED_ATTR(OPTMC_KOU);
+    FED_ATTR(OPTMC_SABR); FED_ATTR(OPTMC_SABR_JUMP); FED_ATTR(OPTMC_KOU); FED_ATTR(OPTMC_DUPIRE);
 #undef FED_ATTR
     *out = ctx;
     return 0;
@@ -194,7 +194,12 @@ static int make_consts(optmc_ctx *ctx, const optmc_model *m, double x0, double d
                        int correlation, Consts *out) {
     Consts c;
     memset(&c, 0, sizeof c);
-    if (m->kind < OPTMC_BSM || m->kind > OPTMC_KOU) FAIL("unknown model kind");
+    if (m->kind < OPTMC_BSM || m->kind > OPTMC_DUPIRE) FAIL("unknown model kind");
+    if (m->kind == OPTMC_DUPIRE) {
+        if (!m->lv_table_dev) FAIL("Dupire needs lv_table_dev");
+        if (m->lv_n_s < 2 || !(m->lv_inv_h > 0.0)) FAIL("Dupire needs lv_n_s >= 2 and lv_inv_h > 0");
+        if (m->lv_n_t < n_steps) FAIL("Dupire table has fewer time rows than n_steps");
+    }
     if (!(dt > 0.0)) FAIL("dt must be positive");
     c.kind = m->kind;
     c.x0 = x0;
@@ -247,6 +252,12 @@ static int make_consts(optmc_ctx *ctx, const optmc_model *m, double x0, double d
         c.m21 *= c.xi;
         c.m22 *= c.xi;
     }
+    c.lv_table = m->lv_table_dev;
+    c.lv_n_s = m->lv_n_s;
+    c.lv_lo = m->lv_log_s_lo;
+    c.lv_inv_h = m->lv_inv_h;
+    c.lv_max_u = std::nextafter((double)(m->lv_n_s - 1), 0.0);
+    c.rq = m->r - m->q;
     c.lam_dt = m->lambda * dt;
     c.mu_j = m->mu_j;
     c.sigma_j = m->sigma_j;
@@ -308,6 +319,7 @@ static int euro_grid(optmc_ctx *ctx, K kernel, int64_t n_local) {
         case OPTMC_SABR: MACRO(OPTMC_SABR); break;             \
         case OPTMC_SABR_JUMP: MACRO(OPTMC_SABR_JUMP); break;   \
         case OPTMC_KOU: MACRO(OPTMC_KOU); break;               \
+        case OPTMC_DUPIRE: MACRO(OPTMC_DUPIRE); break;         \
         default: FAIL("unknown model kind");                   \
     }
 
@@ -633,6 +645,9 @@ extern "C" int optmc_lsmc_paths_async(optmc_ctx *ctx, const optmc_model *model,
     if (!ctx) return -2;
     CK(cudaSetDevice(ctx->device));
     if (!store_dev) FAIL("store_dev is null");
+    if (model && model->kind == OPTMC_DUPIRE)
+        FAIL("no path kernel for Dupire: American MC pricing requires an SDE model "
+             "(american_monte_carlo.py:75-150)");
     EuroArgs A;
     int rc = fill_euro_args(ctx, model, sim, &A);
     if (rc) return rc;

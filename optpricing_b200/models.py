@@ -243,6 +243,23 @@ def levy_kind(model) -> str | None:
     return _LEVY_KINDS.get(getattr(model, "name", None))
 
 
+class DupireLocalVolModel(SDEModel):
+    """models/dupire_local.py:13-43: params = {"vol_surface": callable(T, K) -> local vol}."""
+    name = "Dupire Local Volatility"
+    is_local_vol = True
+    default_params = {"vol_surface": lambda T, K: 0.2}
+    required = ("vol_surface",)
+
+    def __init__(self, params: dict | None = None):
+        super().__init__(params)
+        if not callable(self.params["vol_surface"]):
+            raise ValueError("Dupire model requires a callable 'vol_surface' in its parameters.")
+
+    def __repr__(self):
+        f = self.params["vol_surface"]
+        return f"{type(self).__name__}(vol_surface={getattr(f, '__name__', str(type(f)))})"
+
+
 def model_kind(model) -> str:
     """
     The reference's dispatch chain (monte_carlo.py:130-197) as a kernel name.

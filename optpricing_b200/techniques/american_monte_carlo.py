@@ -130,6 +130,8 @@ class AmericanMonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
         if self.rng_mode == "numpy":
             return self._simulate_full_sde_paths_numpy(model, S0, r, q, T, **kwargs)
         kind = model_kind(model)
+        if kind not in _PATH_KERNELS:                 # american_monte_carlo.py:149-150
+            raise TypeError("American MC pricing requires an SDE model.")
         eng = _engine.get_engine()
         num_draws = self.n_paths // 2 if self.antithetic else self.n_paths
         seed = int(self.rng.integers(0, 2**63 - 1, dtype=np.int64))

@@ -33,9 +33,9 @@ def jump_draws_kou(jump_counts, p_up, eta1, eta2):
 
 
 def run(kind, params, r, q, dt, x0, v0, dw1, dw2=None, jump_counts=None, jumps=None, *,
-        paths=False, sum_mode=0):
+        paths=False, sum_mode=0, local_vol=None):
     eng = get_engine()
-    model = make_model(kind, params, r, q, v0=v0)
+    model = make_model(kind, params, r, q, v0=v0, local_vol=local_vol)
     term, pth = eng.fed(kind, model, x0, dt, dw1, dw2, jump_counts, jumps, sign=1.0,
                         path_sum_mode=sum_mode, want_terminal=not paths, want_paths=paths)
     return pth if paths else term

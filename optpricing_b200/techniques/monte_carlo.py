@@ -193,6 +193,11 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
             kp.update(sigma=p["sigma"])
         elif kind == "bsm":
             kp["sigma"] = p.get("sigma")
+        elif kind == "dupire":
+            # the reference returns dupire_kernel without its vol_surface_func argument
+            # (monte_carlo.py:146-147), so its Dupire branch cannot run; the callable is
+            # what the kernel needs
+            kp["vol_surface_func"] = p["vol_surface"]
         if kind in ("sabr_jump", "bates", "merton"):
             kp.update(lambda_=p["lambda"], mu_j=p["mu_j"], sigma_j=p["sigma_j"])
         return _KERNELS[kind], kp
@@ -220,12 +225,10 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
         if self.rng_mode == "numpy":
             return self._simulate_sde_path_numpy(model, S0, r, q, T, **kwargs)
         kind = model_kind(model)
-        if kind == "dupire":
-            raise NotImplementedError("Dupire local vol is outside the GPU engine (SURVEY 8 f4)")
         eng = _engine.get_engine()
         num_draws = self.n_paths // 2 if self.antithetic else self.n_paths
         seed = int(self.rng.integers(0, 2**63 - 1, dtype=np.int64))
-        mdl = _engine.make_model(kind, model.params, r, q, v0=kwargs.get("v0"))
+        mdl, _keep = self._device_model(eng, kind, model, S0, r, q, T, **kwargs)
         corr = (_engine.CORR_REFERENCE_EUROPEAN if self.correlation == "reference"
                 else _engine.CORR_INDEPENDENT_DRAWS)
         rank, world, all_reduce = self._group()
@@ -245,6 +248,15 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
             all_reduce(dev[: _engine.NMOM])
             mom = dev[: _engine.NMOM].cpu().numpy()
         return DeviceTerminal(mom, kind, seed)
+
+    def _device_model(self, eng, kind, model, S0, r, q, T, **kwargs):
+        """struct optmc_model for one simulation (+ the object keeping its device table alive)."""
+        if kind != "dupire":
+            return _engine.make_model(kind, model.params, r, q, v0=kwargs.get("v0")), None
+        lv = eng.local_vol_table(model.params["vol_surface"], self.n_steps, T / self.n_steps,
+                                 math.log(S0), r, q, n_s=kwargs.get("lv_grid", 1024),
+                                 half_width=kwargs.get("lv_half_width"))
+        return _engine.make_model(kind, model.params, r, q, local_vol=lv), lv
 
     def _simulate_sde_path_numpy(self, model, S0, r, q, T, **kwargs):
         """The reference's host draw sequence (monte_carlo.py:209-257) on GPU fed kernels."""
@@ -277,8 +289,7 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
     def _philox_sde(self, model) -> bool:
         return (self.rng_mode == "philox" and model.supports_sde
                 and not getattr(model, "has_exact_sampler", False)
-                and not getattr(model, "is_pure_levy", False)
-                and model_kind(model) != "dupire")
+                and not getattr(model, "is_pure_levy", False))
 
     def _sweep(self, model, S0, r, q, T, strikes, calls, seed=None, **kwargs):
         """
@@ -291,7 +302,7 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
         num_draws = self.n_paths // 2 if self.antithetic else self.n_paths
         if seed is None:
             seed = int(self.rng.integers(0, 2**63 - 1, dtype=np.int64))
-        mdl = _engine.make_model(kind, model.params, r, q, v0=kwargs.get("v0"))
+        mdl, _keep = self._device_model(eng, kind, model, S0, r, q, T, **kwargs)
         corr = (_engine.CORR_REFERENCE_EUROPEAN if self.correlation == "reference"
                 else _engine.CORR_INDEPENDENT_DRAWS)
         rank, world, all_reduce = self._group()

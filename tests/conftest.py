@@ -38,3 +38,9 @@ def price_goldens():
 def levy_goldens():
     with open(os.path.join(GOLDEN, "levy_goldens.json")) as f:
         return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def dupire_vectors():
+    z = np.load(os.path.join(GOLDEN, "dupire_vectors.npz"))
+    return z, json.loads(str(z["meta"]))

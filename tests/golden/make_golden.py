@@ -289,7 +289,26 @@ def levy_goldens():
     return g
 
 
+# ---------------------------------------------------------------- Dupire
+def dupire_vectors():
+    """dupire_kernel (mc_kernels.py:340-359) cannot be compiled by numba with a Python
+    surface; its un-jitted body, dupire_kernel.py_func, is the reference's own code."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle.reference_mc import dupire_surfaces
+    rng = np.random.default_rng(2024)
+    n, m, dt = 257, 37, 1.0 / 37
+    dw = rng.standard_normal((n, m)) * math.sqrt(dt)
+    out = {"dw": dw, "meta": json.dumps(dict(n=n, m=m, dt=dt, log_s0=math.log(100.0), r=0.05, q=0.01))}
+    for name, f in dupire_surfaces().items():
+        out[name] = mc_kernels.dupire_kernel.py_func(n, m, math.log(100.0), 0.05, 0.01, dt, dw, f)
+    np.savez_compressed(os.path.join(HERE, "dupire_vectors.npz"), **out)
+    return out
+
+
 if __name__ == "__main__":
+    if "--dupire-only" in sys.argv:
+        print("dupire_vectors.npz:", sorted(dupire_vectors()))
+        raise SystemExit(0)
     if "--levy-only" in sys.argv:
         for k, v in levy_goldens().items():
             print(k, v)
@@ -301,3 +320,4 @@ if __name__ == "__main__":
         print(k, v)
     for k, v in levy_goldens().items():
         print(k, v)
+    print("dupire_vectors.npz:", sorted(dupire_vectors()))

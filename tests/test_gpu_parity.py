@@ -619,3 +619,61 @@ def test_cev_sample_terminal_spot_is_the_device_sampler(levy_goldens):
     call = ob.Option(strike=100.0, maturity=1.0, option_type=ob.OptionType.CALL)
     assert ob.MonteCarloTechnique(n_paths=10).price(call, STQ, m, RT).price == pytest.approx(
         20.0 * math.exp(-0.05))
+
+
+# ------------------------------------------------------------------ Dupire local volatility
+@pytest.mark.parametrize("surface", ("flat", "term"))
+def test_dupire_fed_kernel_matches_reference_body_when_the_table_is_exact(dupire_vectors, surface):
+    """Surfaces constant in S are represented exactly by the table: <= 1e-12 against the
+    reference's own (un-jitted) dupire_kernel on the same increments."""
+    z, meta = dupire_vectors
+    got = mc_kernels.dupire_kernel(meta["n"], meta["m"], meta["log_s0"], meta["r"], meta["q"],
+                                   meta["dt"], z["dw"], orc.dupire_surfaces()[surface])
+    np.testing.assert_allclose(got, z[surface], rtol=RTOL, atol=0)
+
+
+def test_dupire_fed_kernel_skew_surface(dupire_vectors):
+    """A surface curved in log S: the device step equals the numpy restatement of its own
+    interpolation rule to 1e-12, and the reference with the exact callable to the
+    interpolation error of the default 1024-node grid."""
+    from optpricing_b200._engine import sample_local_vol
+    z, meta = dupire_vectors
+    f = orc.dupire_surfaces()["skew"]
+    args = (meta["n"], meta["m"], meta["log_s0"], meta["r"], meta["q"], meta["dt"], z["dw"])
+    got = mc_kernels.dupire_kernel(*args, f)
+    table, lo, h = sample_local_vol(f, meta["m"], meta["dt"], meta["log_s0"], meta["r"], meta["q"])
+    want = orc.dupire_kernel(*args, orc.table_surface(table, lo, h, meta["dt"]))
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=0)
+    np.testing.assert_allclose(got, z["skew"], rtol=0, atol=2e-6)
+    fine = mc_kernels.dupire_kernel(*args, f, n_s=16384)
+    np.testing.assert_allclose(fine, z["skew"], rtol=0, atol=1e-8)
+
+
+def test_dupire_philox_prices(price_goldens):
+    call = ob.Option(strike=100.0, maturity=1.0, option_type=ob.OptionType.CALL)
+    # a flat surface is Black-Scholes: closed form within 3 standard errors
+    t = ob.MonteCarloTechnique(n_paths=1 << 22, n_steps=50, seed=12)
+    flat = ob.DupireLocalVolModel({"vol_surface": lambda T, K: 0.2})
+    p = t.price(call, ST, flat, RT).price
+    assert abs(p - price_goldens["G1_closed_form"]) < 3 * t.last_stats["stderr"] + 2e-3
+    # a skewed surface: within 3 combined standard errors of the oracle on its own draws
+    f = orc.dupire_surfaces()["skew"]
+    t = ob.MonteCarloTechnique(n_paths=1 << 21, n_steps=40, seed=3)
+    got = t.price(call, STQ, ob.DupireLocalVolModel({"vol_surface": f}), RT).price
+    rng = np.random.default_rng(5)
+    n, m, dt = 200_000, 40, 1.0 / 40
+    dw = rng.standard_normal((n, m)) * math.sqrt(dt)
+    a = np.exp(orc.dupire_kernel(n, m, math.log(100.0), 0.05, 0.01, dt, dw, f))
+    b = np.exp(orc.dupire_kernel(n, m, math.log(100.0), 0.05, 0.01, dt, -dw, f))
+    pair = 0.5 * (np.maximum(a - 100.0, 0) + np.maximum(b - 100.0, 0)) * math.exp(-0.05)
+    se = math.hypot(t.last_stats["stderr"], pair.std(ddof=1) / math.sqrt(n))
+    assert abs(got - pair.mean()) < 3 * se, (got, pair.mean(), se)
+    # the scheme is a martingale step by step
+    s = t.last_stats
+    assert abs(s["control_mean"] - s["control_expected"]) < 4 * s["control_stderr"]
+    # numpy mode runs the fed kernel on the reference's host draws
+    tn = ob.MonteCarloTechnique(n_paths=20000, n_steps=10, seed=0, rng_mode="numpy")
+    assert tn.price(call, ST, flat, RT).price == pytest.approx(price_goldens["G1_bsm_20000x10_seed0"],
+                                                               rel=1e-12)
+    with pytest.raises(TypeError, match="requires an SDE model"):
+        ob.AmericanMonteCarloTechnique(n_paths=100, n_steps=5).price(call, ST, flat, RT)

@@ -42,9 +42,27 @@ def test_library_exports_every_declared_symbol():
     assert lib.optmc_version() >= 100
 
 
-def test_struct_layout_matches_header():
-    assert ctypes_sizeof(_engine.OptmcModel) == 8 + 16 * 8
+def test_struct_layout_matches_header(tmp_path):
+    """ctypes mirrors against the C compiler's view of include/optmc.h."""
+    import shutil
+    import subprocess
+    assert ctypes_sizeof(_engine.OptmcModel) == 8 + 16 * 8 + 8 + 8 + 16
     assert ctypes_sizeof(_engine.OptmcSim) == 16 + 24 + 8 + 8 + 8
+    assert ctypes_sizeof(_engine.OptmcLevy) == 8 + 8 * _engine.LEVY_NPARAM
+    if shutil.which("gcc") is None:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "optmc.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %d %d\\n", sizeof(optmc_model), '
+                   'sizeof(optmc_sim), sizeof(optmc_levy), offsetof(optmc_model, lv_table_dev), '
+                   'offsetof(optmc_sim, seed), OPTMC_MAX_PEERS, OPTMC_IPC_HANDLE_BYTES);return 0;}\n')
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
+    assert got == [ctypes_sizeof(_engine.OptmcModel), ctypes_sizeof(_engine.OptmcSim),
+                   ctypes_sizeof(_engine.OptmcLevy), _engine.OptmcModel.lv_table_dev.offset,
+                   _engine.OptmcSim.seed.offset, _engine.MAX_PEERS, _engine.IPC_HANDLE_BYTES]
 
 
 def ctypes_sizeof(t):
