@@ -383,12 +383,20 @@ def run_secondary(args, name):
         models = (ob.SABRJumpModel(), ob.KouModel())
         techs = [ob.MonteCarloTechnique(n_paths=1 << 24, n_steps=365, seed=11, control_variate=True)
                  for _ in models]
-        units = 2 * (1 << 24) * 365
-        label = ("C5 SABR-with-jumps and Kou European call, 2^24 paths x 365 steps each, control "
-                 "variate (price only; the bump greeks re-price 2x each)")
+        # per step: price + delta + vega of both models on common random numbers.
+        # SABR-jump: 1 + 2 simulations (its vega is NaN as in the reference, greek_mixin.py:156-157);
+        # Kou: 1 + 2 + 2.  Every simulation is 2^24 paths x 365 steps.
+        units = 8 * (1 << 24) * 365
+        label = ("C5 SABR-with-jumps and Kou European call, 2^24 paths x 365 steps, control variate, "
+                 "price + bump-and-reprice delta and vega (8 simulations per step)")
+        extra["simulations_per_step"] = 8
 
         def step():
-            return [t.price(call, stock, m, rate).price for t, m in zip(techs, models)]
+            out = []
+            for t, m in zip(techs, models):
+                out += [t.price(call, stock, m, rate).price, t.delta(call, stock, m, rate),
+                        t.vega(call, stock, m, rate)]
+            return out
     else:
         raise SystemExit(name)
     for _ in range(max(args.warmup, 3)):
@@ -414,6 +422,12 @@ def run_secondary(args, name):
                     "h2d_bytes_per_step": 212, "d2h_bytes_per_step": 48, "api": "technique.price"},
             "gpu_launches": eng.launch_count() - launches0,
             "result_sample": (float(np.ravel(out)[0]) if not isinstance(out, float) else out)}
+    if name == "c5":
+        line["config"]["results"] = dict(zip(
+            ("sabr_jump_price", "sabr_jump_delta", "sabr_jump_vega", "kou_price", "kou_delta",
+             "kou_vega"), (None if (isinstance(x, float) and math.isnan(x)) else float(x) for x in out)))
+        # two launches (simulate + finish) per European simulation
+        line["config"]["simulations_counted"] = (eng.launch_count() - launches0) // 2 // args.steps
     if name == "c4":
         peaks = {}
         try:
@@ -431,7 +445,8 @@ def run_secondary(args, name):
             torch.cuda.synchronize()
             best = min(best, e0.elapsed_time(e1))
         ach = (1 << 22) * 50 * 32 / (best * 1e-3) / 1e9
-        line["roofline"] = {"bound": "hbm", "kernel": "k_lsmc_step<3> x 50 dates (induction only)",
+        line["roofline"] = {"bound": "hbm", "kernel": "k_lsmc_persistent<3>: 50 exercise dates in one "
+                                                      "launch (induction only)",
                             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                             "traffic": None, "per_unit": "32 B per path-date (SURVEY 8 d4)",
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",

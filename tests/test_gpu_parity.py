@@ -677,3 +677,22 @@ def test_dupire_philox_prices(price_goldens):
                                                                rel=1e-12)
     with pytest.raises(TypeError, match="requires an SDE model"):
         ob.AmericanMonteCarloTechnique(n_paths=100, n_steps=5).price(call, ST, flat, RT)
+
+
+# ------------------------------------------------------------------ two ranks on one box
+def test_two_ranks_match_one_gpu_nvlink_and_nccl_exchange():
+    """torchrun x 2 over tests/dist_gpu_check.py: European moments all-reduced by NCCL, the
+    LSMC Gram exchange both over NVLink peer memory inside the persistent kernel and as one
+    NCCL all-reduce per date; each must equal the single-GPU price to rounding."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs on the box")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                        "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port",
+                        "29533", os.path.join(root, "tests", "dist_gpu_check.py")],
+                       env={**os.environ, "DIST_CHECK_QUICK": "1"}, capture_output=True, text=True,
+                       timeout=600, cwd=root)
+    assert r.returncode == 0 and "dist_gpu_check: PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
