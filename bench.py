@@ -97,6 +97,9 @@ class ClockSampler:
         t0 = self.t0 if self.t0 is not None else 0.0
         # a sample printed at time t describes the interval just before t
         self.rows = [r for t, r in self.all_rows if t0 + 0.01 <= t <= self.t1 + 0.03]
+        if not self.rows:      # timed region shorter than the sampling period: nearest samples
+            self.rows = [r for t, r in self.all_rows if t >= t0 - 0.05][:3] or [
+                r for _, r in self.all_rows[-2:]]
         sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names)
