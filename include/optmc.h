@@ -287,8 +287,12 @@ int optmc_lsmc_peer_attach(optmc_ctx *ctx, int32_t rank, int32_t world, const vo
 /*
  * Diagnostics used by the tests and by bench.py's roofline.
  *   optmc_philox_raw     out_dev[4*i..] = Philox4x32-10(counter = (lo(i), hi(i), c2, c3), key = seed)
- *   optmc_normals        out_dev[2*i], out_dev[2*i+1] = the two N(0,1) the engine
- *                        derives for (draw i, step `step`)
+ *   optmc_normals        out_dev[2*i], out_dev[2*i+1] = the two N(0,1) of Box-Muller pair
+ *                        `step` of draw i: three Philox calls (c2 = 3g..3g+2) feed the four
+ *                        pairs 4g..4g+3; a pair drives one step of a two-factor model or two
+ *                        consecutive steps of a one-factor model (the per-step jump kernels
+ *                        -- SABR-jump, jump path kernels -- use one call per step instead:
+ *                        three words for the pair, the fourth for the Poisson draw)
  *   optmc_fp64_peak      runs a register-resident DFMA loop on every SM for
  *                        ~`iters` iterations and returns fp64 FMA instructions
  *                        per second (thread-level): the measured denominator of

@@ -106,15 +106,15 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
     // step per Philox call: every step needs its own Poisson word.
     constexpr int SPC = (TWO || (PER_STEP && JUMPS)) ? 1 : 2;
     const uint32_t id_lo = keep_u32((uint32_t)id), id_hi = keep_u32((uint32_t)(id >> 32));
-    OPTMC_UNROLL_STEPS
-    for (int i = 0; i < A.n_steps; i += SPC) {
-        uint4 w = philox4x32_10(make_uint4(id_lo, id_hi, (uint32_t)i, 0u), A.key);
+    // One Box-Muller pair (three Philox words: 64 bits of radius, 32 of angle) and the
+    // SPC steps it feeds, starting at step i.
+    auto advance = [&](uint32_t w0, uint32_t w1, uint32_t w2, int i) {
         // (z1, z2): two-factor models -- the mixed, scaled increments (dW_S, xi-weighted
         // dW_v); one-factor models -- sqrt(dt) N(0,1) for this step and the next.
         double z1, z2;
         if constexpr (NIMPL == 0) {
             double a, b;
-            normal_pair_lib(w.x, w.y, w.z, a, b);
+            normal_pair_lib(w0, w1, w2, a, b);
             if constexpr (TWO) {
                 z1 = fma(c.m12, b, c.m11 * a);
                 z2 = fma(c.m22, b, c.m21 * a);
@@ -123,7 +123,7 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
                 z2 = c.sqrt_dt * b;
             }
         } else {
-            normal_pair_fast<TWO>(w.x, w.y, w.z, z1, z2, tab);
+            normal_pair_fast<TWO>(w0, w1, w2, z1, z2, tab);
         }
         if constexpr (TWO) {
             step_diffusion<KIND, DEFER, LOGV>(sa, z1, z2, c, tab, i);
@@ -140,7 +140,37 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
                 }
             }
         }
-        if constexpr (JUMPS && !JUMPS_AT_END) {
+    };
+    // Kinds whose step loop needs no Poisson word use all 128 bits of a Philox call:
+    // three calls (c2 = 3g, 3g+1, 3g+2) feed four pairs, see philox_pair_words.
+    constexpr bool PACKED = !(JUMPS && !JUMPS_AT_END);
+    if constexpr (PACKED) {
+        uint32_t call = 0;
+        OPTMC_UNROLL_STEPS
+        for (int i = 0; i < A.n_steps; i += 4 * SPC, call += 3) {
+            const uint4 a = philox4x32_10(make_uint4(id_lo, id_hi, call, 0u), A.key);
+            advance(a.x, a.y, a.z, i);
+            if constexpr (PER_STEP && SPC == 1) sink(i, sa, sb);
+            if (i + SPC < A.n_steps) {
+                const uint4 b = philox4x32_10(make_uint4(id_lo, id_hi, call + 1u, 0u), A.key);
+                advance(a.w, b.x, b.y, i + SPC);
+                if constexpr (PER_STEP && SPC == 1) sink(i + SPC, sa, sb);
+                if (i + 2 * SPC < A.n_steps) {
+                    const uint4 d = philox4x32_10(make_uint4(id_lo, id_hi, call + 2u, 0u), A.key);
+                    advance(b.z, b.w, d.x, i + 2 * SPC);
+                    if constexpr (PER_STEP && SPC == 1) sink(i + 2 * SPC, sa, sb);
+                    if (i + 3 * SPC < A.n_steps) {
+                        advance(d.y, d.z, d.w, i + 3 * SPC);
+                        if constexpr (PER_STEP && SPC == 1) sink(i + 3 * SPC, sa, sb);
+                    }
+                }
+            }
+        }
+    } else {
+        OPTMC_UNROLL_STEPS
+        for (int i = 0; i < A.n_steps; i += SPC) {
+            const uint4 w = philox4x32_10(make_uint4(id_lo, id_hi, (uint32_t)i, 0u), A.key);
+            advance(w.x, w.y, w.z, i);
             // One Poisson draw for the steps this iteration covered; for the
             // additive-in-log one-factor models the split between the two
             // steps does not affect S_T.
@@ -154,8 +184,8 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
                 apply_jump<KIND, DEFER>(sa, J.x);
                 if constexpr (ANTI) apply_jump<KIND, DEFER>(sb, J.y);
             }
+            if constexpr (PER_STEP && SPC == 1) sink(i, sa, sb);
         }
-        if constexpr (PER_STEP && SPC == 1) sink(i, sa, sb);
     }
     if constexpr (JUMPS_AT_END) {
         uint4 e = philox4x32_10(make_uint4(id_lo, id_hi, 0xFFFFFFFFu, 0xFEu), A.key);

@@ -885,12 +885,13 @@ __global__ void k_normals(PhiloxKey key, int64_t n, int step, double *out) {
     __syncthreads();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint4 w = philox_draw(key, (uint64_t)i, (uint32_t)step, 0u);
+    uint32_t w0, w1, w2;
+    philox_pair_words(key, (uint64_t)i, (uint32_t)step, w0, w1, w2);
     double a, b;
     if constexpr (NIMPL == 0)
-        normal_pair_lib(w.x, w.y, w.z, a, b);
+        normal_pair_lib(w0, w1, w2, a, b);
     else
-        normal_pair_fast<false>(w.x, w.y, w.z, a, b, tv);
+        normal_pair_fast<false>(w0, w1, w2, a, b, tv);
     out[2 * i] = a;
     out[2 * i + 1] = b;
 }

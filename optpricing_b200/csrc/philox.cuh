@@ -59,6 +59,24 @@ __device__ __forceinline__ uint4 philox_draw(const PhiloxKey &k, uint64_t id, ui
     return philox4x32_10(make_uint4((uint32_t)id, (uint32_t)(id >> 32), c2, c3), k);
 }
 
+// The three words of Box-Muller pair `pair` of one draw under the packed layout
+// the step loops use (european.cuh): calls c2 = 3g, 3g+1, 3g+2 of stream 0 yield
+// twelve words = four pairs,
+//   pair 4g: a.x a.y a.z   4g+1: a.w b.x b.y   4g+2: b.z b.w d.x   4g+3: d.y d.z d.w
+// (first two words: the 64-bit radius uniform, third: the angle).
+__device__ __forceinline__ void philox_pair_words(const PhiloxKey &k, uint64_t id, uint32_t pair,
+                                                  uint32_t &w0, uint32_t &w1, uint32_t &w2) {
+    const uint32_t g = pair >> 2, slot = pair & 3u;
+    const uint4 a = philox_draw(k, id, 3u * g, 0u), b = philox_draw(k, id, 3u * g + 1u, 0u),
+                d = philox_draw(k, id, 3u * g + 2u, 0u);
+    switch (slot) {
+        case 0: w0 = a.x; w1 = a.y; w2 = a.z; break;
+        case 1: w0 = a.w; w1 = b.x; w2 = b.y; break;
+        case 2: w0 = b.z; w1 = b.w; w2 = d.x; break;
+        default: w0 = d.y; w1 = d.z; w2 = d.w;
+    }
+}
+
 // 64 random bits -> uniform double in (0, 1), 53 significant bits, never 0 or 1.
 __device__ __forceinline__ double u01_open(uint32_t lo, uint32_t hi) {
     uint64_t x = ((uint64_t)hi << 32) | lo;
