@@ -47,6 +47,13 @@ I64_PER_PATH_STEP = {"heston": 20.0, "bsm": 6.0}
 # Algorithmic flops per path-step (antithetic pairs share the draws)
 FLOPS_PER_PATH_STEP = {"heston": 28.0, "bsm": 6.0}
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
+# `ncu --set full` captures summarised in profiles/r01_ncu_heston_summary.md (r1d) and
+# profiles/r01_ncu_lsmc_summary.md (persistent): the European kernel reads its tables and code only;
+# the LSMC induction streams the 1.68 GB path store once (the 6.7 GB of algorithmic cashflow / row
+# re-reads are L2 hits at 2^22 paths).
+NCU_TRAFFIC_BYTES = {"heston_c2": 53_504 + 0, "lsmc_c4": 1_729_129_000 + 123_759_616}
+
 HESTON = {"v0": 0.04, "kappa": 2.0, "theta": 0.04, "rho": -0.7, "vol_of_vol": 0.5}
 WORKLOADS = {
     "c2": dict(kind="heston", params=HESTON, n_paths=1 << 24, n_steps=252, S0=100.0, K=100.0,
@@ -300,7 +307,10 @@ def run_ours(args, w):
     roofline = {
         "bound": "fp64", "kernel": f"k_european<{w['kind']}, antithetic, hand-written normals>",
         "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "G fp64-pipe instr/s",
-        "frac": achieved / peak, "traffic": None,
+        "frac": achieved / peak,
+        "traffic": NCU_TRAFFIC_BYTES["heston_c2"] if args.workload == "c2" and world == 1 else None,
+        "traffic_note": "bytes of DRAM read+written per launch, ncu capture of this workload on one "
+                        "GPU (profiles/r01_ncu_heston_summary.md); the kernel has no HBM operands",
         "per_unit": f"{i64} fp64-pipe instr per path-step (static SASS count of the step loop)",
         "peak_source": "optmc_fp64_peak DFMA loop measured in this run (MEASURED_PEAKS.json has "
                        "no fp64 figure); burst %.1f / sustained %.1f G/s" % (peak_burst / 1e9,
@@ -451,7 +461,12 @@ def run_secondary(args, name):
         line["roofline"] = {"bound": "hbm", "kernel": "k_lsmc_persistent<3>: 50 exercise dates in one "
                                                       "launch (induction only)",
                             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                            "traffic": None, "per_unit": "32 B per path-date (SURVEY 8 d4)",
+                            "traffic": NCU_TRAFFIC_BYTES["lsmc_c4"],
+                            "traffic_note": "DRAM bytes per launch (ncu, profiles/r01_ncu_lsmc_summary.md):"
+                                            " the 1.68 GB store once + cashflow write-backs; the other "
+                                            "3/4 of the 6.7 GB algorithmic bytes are L2 hits, so the "
+                                            "launch is bound by fp64 issue, not by HBM",
+                            "per_unit": "32 B per path-date (SURVEY 8 d4)",
                             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                             "kernel_ms": best}
     print(json.dumps(line), flush=True)
