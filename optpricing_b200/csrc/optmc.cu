@@ -762,6 +762,7 @@ static int lsmc_persistent(optmc_ctx *ctx, const double *store_dev, int64_t ld, 
     A.disc = disc;
     A.is_call = is_call;
     A.cashflow = cashflow_dev;
+    A.prefetch_next_row = (32.0 * (double)n_paths <= 96.0 * 1024 * 1024) ? 1 : 0;
     A.slots = ctx->lsmc_slots;
     A.nonce = (++ctx->lsmc_nonce) & 0xFFFFFu;      // tag 0 is never used: nonce >= 1
     if (A.nonce == 0) A.nonce = ctx->lsmc_nonce = 1;
