@@ -90,8 +90,15 @@ typedef struct optmc_sim {
     int32_t antithetic;   /* 1: each draw also yields its negated partner */
     uint64_t seed;        /* Philox4x32-10 key; the stream of draw g depends only on (seed, g) */
     int32_t correlation;  /* enum optmc_correlation */
-    int32_t reserved;
+    int32_t precision;    /* enum optmc_precision: arithmetic of the step loop (optmc_european*) */
 } optmc_sim;
+
+/* OPTMC_FP64 (default): everything in IEEE binary64.  OPTMC_FP32: the optional
+   single-precision mode -- path state, normals and per-step arithmetic in binary32
+   with the SFU approximations of log/exp/sin/cos/sqrt; the once-per-path finish
+   (drift, exp, payoff) and the moments stay binary64.  Statistical agreement only;
+   not available for Dupire, fed draws or the Longstaff-Schwartz path store. */
+enum optmc_precision { OPTMC_FP64 = 0, OPTMC_FP32 = 1 };
 
 /* Per contract, over this call's samples (a sample = one draw: the mean of the
    antithetic pair when antithetic, else one path; payoff p and control c = S_T

