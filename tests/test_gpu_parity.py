@@ -716,9 +716,9 @@ def test_fp32_mode_agrees_with_fp64_statistically(kind):
     s = t32.last_stats
     assert abs(s["control_mean"] - s["control_expected"]) < 4 * s["control_stderr"] + 1e-3, kind
     assert t32.price(put, STQ, model, RT).price != p32          # the stream advances as in fp64
-    np.testing.assert_allclose(t32.price_many([put, CALL], STQ, model, RT)[0],
-                               ob.MonteCarloTechnique(precision="fp32", **kw).price_many(
-                                   [put], STQ, model, RT)[0] if False else p32, rtol=0.05)
+    # the strike sweep on stored fp32-mode terminals reproduces the single-contract price
+    many = ob.MonteCarloTechnique(precision="fp32", **kw).price_many([put, CALL], STQ, model, RT)
+    assert many[0] == pytest.approx(p32, rel=1e-10)
 
 
 def test_fp32_mode_restrictions():
