@@ -171,6 +171,28 @@ int optmc_payoff_sweep_async(optmc_ctx *ctx, const double *terminal_dev, int64_t
                              double *moments_dev, void *stream);
 
 /*
+ * Vega from one simulation for the one-factor log-Euler models
+ * (BSM, Merton, Kou), whose terminal value is
+ *     log S_T = log S_0 + n drift(sigma) + sigma W + J,
+ * W = the path's Brownian sum, J = its summed log-jumps, neither depending on sigma.
+ *   optmc_european_aux_async  = optmc_european_async that also stores, per draw,
+ *                               aux_dev[g] = W, aux_dev[n_local + g] = J and (antithetic)
+ *                               aux_dev[2 n_local + g] = J of the partner, whose W is -W
+ *   optmc_sigma_sweep_async   payoff moments of up to 16 scenarios (a0 = log S_0 + n drift,
+ *                             sigma, strike, is_call) over the stored (W, J): what
+ *                             GreekMixin.vega's two re-pricings on common random numbers
+ *                             compute (greek_mixin.py:125-175), without re-simulating
+ */
+int optmc_european_aux_async(optmc_ctx *ctx, const optmc_model *model, const optmc_sim *sim,
+                             int32_t n_contracts, const double *strikes, const int32_t *is_call,
+                             double *moments_dev, double *terminal_dev, double *aux_dev,
+                             void *stream);
+int optmc_sigma_sweep_async(optmc_ctx *ctx, const double *aux_dev, int64_t n_local,
+                            int32_t antithetic, int32_t n_scenarios, const double *a0,
+                            const double *sigma, const double *strikes, const int32_t *is_call,
+                            double *moments_dev, void *stream);
+
+/*
  * Single-step terminal samplers: the pure-Levy and exact-sampler branches of
  * MonteCarloTechnique.price (monte_carlo.py:103-106) and _simulate_levy_terminal
  * (:259-280), which in the reference call each model's numpy/scipy sampler on

@@ -77,6 +77,11 @@ SIGNATURES = [
     ("optmc_fed_async", c_int, [c_void_p, ctypes.POINTER(OptmcModel), c_double, c_double, c_i64,
                                 c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_double,
                                 c_i32, c_void_p, c_void_p, c_void_p, c_i64, c_void_p]),
+    ("optmc_european_aux_async", c_int, [c_void_p, ctypes.POINTER(OptmcModel),
+                                         ctypes.POINTER(OptmcSim), c_i32, _dp, _ip, c_void_p,
+                                         c_void_p, c_void_p, c_void_p]),
+    ("optmc_sigma_sweep_async", c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i32, _dp, _dp, _dp,
+                                        _ip, c_void_p, c_void_p]),
     ("optmc_payoff_sweep_async", c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i32, _dp, _ip,
                                          c_void_p, c_void_p]),
     ("optmc_levy_gig_setup", c_int, [ctypes.POINTER(OptmcLevy)]),
@@ -266,6 +271,7 @@ class Engine:
             raise EngineError("optmc_ctx_create: " + self.lib.optmc_last_error(None).decode())
         self.ctx = ctx
         self._buffers = {}
+        self.n_simulations = 0      # European simulations launched (bench.py counts path-steps with it)
 
     # -- plumbing -----------------------------------------------------------
     def _check(self, rc, what):
@@ -319,6 +325,7 @@ class Engine:
 
     def european(self, model: OptmcModel, sim: OptmcSim, strikes, is_call, terminal=None):
         """optmc_european: host moments array (n_contracts, 6) after one sync."""
+        self.n_simulations += 1
         k, c, kp, cp = self._contracts(strikes, is_call)
         out = np.empty((k.size, NMOM))
         tptr = c_void_p(terminal.data_ptr()) if terminal is not None else None
@@ -330,14 +337,34 @@ class Engine:
                                             self.stream()), "optmc_european")
         return out
 
-    def european_async(self, model, sim, strikes, is_call, moments, terminal=None):
-        """optmc_european_async into the torch tensor ``moments`` (n_contracts*6 f64)."""
+    def european_async(self, model, sim, strikes, is_call, moments, terminal=None, aux=None):
+        """optmc_european[_aux]_async into the torch tensor ``moments`` (n_contracts*6 f64).
+        ``aux`` (3 * n_local f64, one-factor log models): receives W, J and the partner's J."""
+        self.n_simulations += 1
         k, c, kp, cp = self._contracts(strikes, is_call)
         tptr = c_void_p(terminal.data_ptr()) if terminal is not None else None
+        if aux is not None:
+            self._check(self.lib.optmc_european_aux_async(
+                self.ctx, ctypes.byref(model), ctypes.byref(sim), k.size, kp, cp,
+                c_void_p(moments.data_ptr()), tptr, c_void_p(aux.data_ptr()), self.stream()),
+                "optmc_european_aux_async")
+            return
         self._check(self.lib.optmc_european_async(self.ctx, ctypes.byref(model),
                                                   ctypes.byref(sim), k.size, kp, cp,
                                                   c_void_p(moments.data_ptr()), tptr,
                                                   self.stream()), "optmc_european_async")
+
+    def sigma_sweep(self, aux, n_local, antithetic, a0, sigma, strikes, is_call):
+        """optmc_sigma_sweep_async -> device tensor of n_scenarios * 6 moments."""
+        k, c, kp, cp = self._contracts(strikes, is_call)
+        a = np.ascontiguousarray(a0, dtype=np.float64)
+        sg = np.ascontiguousarray(sigma, dtype=np.float64)
+        mom = self.buffer("sigma_moments", k.size * NMOM)
+        self._check(self.lib.optmc_sigma_sweep_async(
+            self.ctx, c_void_p(aux.data_ptr()), int(n_local), 1 if antithetic else 0, k.size,
+            a.ctypes.data_as(_dp), sg.ctypes.data_as(_dp), kp, cp, c_void_p(mom.data_ptr()),
+            self.stream()), "optmc_sigma_sweep_async")
+        return mom
 
     def payoff_sweep(self, terminal, n_local, antithetic, strikes, is_call, to_host=True):
         k, c, kp, cp = self._contracts(strikes, is_call)

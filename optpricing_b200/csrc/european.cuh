@@ -39,6 +39,7 @@ struct EuroArgs {
     double pois_mu_path, pois_p0_path;   // lambda T and exp(-lambda T): whole-path jump count
     double *partials;   // [gridDim.x][NPART]
     double *terminal;   // optional [n_local * (anti ? 2 : 1)]
+    double *aux;        // optional, one-factor log models: [W | J | J partner], n_local each
 };
 
 // One jump size (rare path: CUDA math library, no table needed).
@@ -218,6 +219,15 @@ __global__ void __launch_bounds__(EURO_THREADS, OPTMC_EURO_MIN_BLOCKS) k_europea
         State sa, sb;
         simulate_draw<KIND, ANTI, NIMPL, false>(A, (uint64_t)(A.draw_offset + g), sa, sb, tv,
                                                 NoSink{});
+        if constexpr (!kind_two_factor(KIND) && KIND != OPTMC_DUPIRE) {
+            // log S_T = log S_0 + n drift(sigma) + sigma W + J: W and J do not depend on sigma,
+            // so sigma-bumped prices (vega) can be read off this one simulation
+            if (A.aux) {
+                A.aux[g] = sa.v;
+                A.aux[A.n_local + g] = sa.w;
+                if constexpr (ANTI) A.aux[2 * A.n_local + g] = sb.w;
+            }
+        }
         double ST = terminal_spot(KIND, sa);
         double pay = A.is_call ? ST - A.strike : A.strike - ST;   // monte_carlo.py:110-114
         pay = fmax(pay, 0.0);
@@ -298,6 +308,51 @@ __global__ void __launch_bounds__(256) k_payoff_sweep(const SweepArgs A) {
     block_sum<5>(acc, scratch);
     if (threadIdx.x == 0) {
         double *p = A.partials + ((size_t)cidx * gridDim.x + blockIdx.x) * NPART;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) p[k] = acc[k];
+    }
+}
+
+// Sigma sweep over the stored (W, J) of a one-factor log-Euler simulation:
+// scenario s has log S_T = a0[s] + sigma[s] * (+-W) + J with a0 = log S_0 + n drift(sigma).
+// Same block layout and partials as k_payoff_sweep (block.y = scenario).
+constexpr int SCEN_MAX = 16;
+struct SigmaSweepArgs {
+    const double *aux;
+    int64_t n_local;
+    int antithetic;
+    int n_scen;
+    double a0[SCEN_MAX], sigma[SCEN_MAX], strikes[SCEN_MAX];
+    unsigned char is_call[SCEN_MAX];
+    double *partials;         // [n_scen][gridDim.x][NPART]
+};
+
+__global__ void __launch_bounds__(256) k_sigma_sweep(const SigmaSweepArgs A) {
+    __shared__ double scratch[5 * 32];
+    const int sidx = blockIdx.y;
+    const double a0 = A.a0[sidx], sg = A.sigma[sidx], K = A.strikes[sidx];
+    const bool call = A.is_call[sidx] != 0;
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < A.n_local; g += stride) {
+        const double W = A.aux[g];
+        double ST = exp((a0 + sg * W) + A.aux[A.n_local + g]);
+        double pay = fmax(call ? ST - K : K - ST, 0.0);
+        double ctl = ST;
+        if (A.antithetic) {
+            double STb = exp((a0 - sg * W) + A.aux[2 * A.n_local + g]);
+            pay = 0.5 * (pay + fmax(call ? STb - K : K - STb, 0.0));
+            ctl = 0.5 * (ST + STb);
+        }
+        acc[0] += pay;
+        acc[1] = fma(pay, pay, acc[1]);
+        acc[2] += ctl;
+        acc[3] = fma(ctl, ctl, acc[3]);
+        acc[4] = fma(pay, ctl, acc[4]);
+    }
+    block_sum<5>(acc, scratch);
+    if (threadIdx.x == 0) {
+        double *p = A.partials + ((size_t)sidx * gridDim.x + blockIdx.x) * NPART;
 #pragma unroll
         for (int k = 0; k < 5; ++k) p[k] = acc[k];
     }

@@ -121,8 +121,10 @@ __device__ __forceinline__ void finish_deferred(State &s, const Consts &c) {
     if constexpr (DEFER) {
         if constexpr (KIND == OPTMC_HESTON || KIND == OPTMC_BATES)
             s.x = c.x0 + (c.n_rqc_dt + fma(s.w, c.neg_half_dt, s.x));
-        else
+        else {
+            s.v = s.x;                                           // keep the Brownian sum W (see k_sigma_sweep)
             s.x = (c.x0 + fma(c.sigma, s.x, c.n_drift)) + s.w;   // s.w: sum of log-jumps
+        }
     }
 }
 

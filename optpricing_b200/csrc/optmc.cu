@@ -427,12 +427,31 @@ static int sweep_launch(optmc_ctx *ctx, const double *terminal_dev, int64_t n_lo
     return 0;
 }
 
+extern "C" int optmc_european_aux_async(optmc_ctx *ctx, const optmc_model *model,
+                                        const optmc_sim *sim, int32_t n_contracts,
+                                        const double *strikes, const int32_t *is_call,
+                                        double *moments_dev, double *terminal_dev, double *aux_dev,
+                                        void *stream);
+
 extern "C" int optmc_european_async(optmc_ctx *ctx, const optmc_model *model, const optmc_sim *sim,
                                     int32_t n_contracts, const double *strikes,
                                     const int32_t *is_call, double *moments_dev,
                                     double *terminal_dev, void *stream) {
+    return optmc_european_aux_async(ctx, model, sim, n_contracts, strikes, is_call, moments_dev,
+                                    terminal_dev, nullptr, stream);
+}
+
+extern "C" int optmc_european_aux_async(optmc_ctx *ctx, const optmc_model *model,
+                                        const optmc_sim *sim, int32_t n_contracts,
+                                        const double *strikes, const int32_t *is_call,
+                                        double *moments_dev, double *terminal_dev, double *aux_dev,
+                                        void *stream) {
     if (!ctx) return -2;
     CK(cudaSetDevice(ctx->device));
+    if (aux_dev && model && !(model->kind == OPTMC_BSM || model->kind == OPTMC_MERTON ||
+                              model->kind == OPTMC_KOU))
+        FAIL("aux_dev (W, J) exists for the one-factor log-Euler models only (BSM, Merton, Kou)");
+    if (aux_dev && sim && sim->precision != OPTMC_FP64) FAIL("aux_dev needs the fp64 mode");
     if (n_contracts < 1 || !strikes || !is_call || !moments_dev) FAIL("bad contract arguments");
     if (n_contracts > 1 && !terminal_dev)
         FAIL("terminal_dev is required when n_contracts > 1 (strike sweep)");
@@ -444,6 +463,7 @@ extern "C" int optmc_european_async(optmc_ctx *ctx, const optmc_model *model, co
     A.is_call = is_call[0] ? 1 : 0;
     A.partials = reinterpret_cast<double *>(ctx->scratch);
     A.terminal = terminal_dev;
+    A.aux = aux_dev;
     int grid = 0;
     const bool anti = sim->antithetic != 0;
     if (sim->precision != OPTMC_FP64 && sim->precision != OPTMC_FP32) FAIL("unknown precision");
@@ -491,6 +511,40 @@ extern "C" int optmc_european(optmc_ctx *ctx, const optmc_model *model, const op
     CK(cudaMemcpyAsync(ctx->moments_host, ctx->moments_dev, bytes, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     memcpy(moments_host, ctx->moments_host, bytes);
+    return 0;
+}
+
+extern "C" int optmc_sigma_sweep_async(optmc_ctx *ctx, const double *aux_dev, int64_t n_local,
+                                       int32_t antithetic, int32_t n_scenarios, const double *a0,
+                                       const double *sigma, const double *strikes,
+                                       const int32_t *is_call, double *moments_dev, void *stream) {
+    if (!ctx) return -2;
+    CK(cudaSetDevice(ctx->device));
+    if (!aux_dev || !a0 || !sigma || !strikes || !is_call || !moments_dev) FAIL("null pointer");
+    if (n_scenarios < 1 || n_scenarios > SCEN_MAX) FAIL("n_scenarios must be in 1..16");
+    if (n_local < 0) FAIL("negative n_local");
+    SigmaSweepArgs S;
+    memset(&S, 0, sizeof S);
+    S.aux = aux_dev;
+    S.n_local = n_local;
+    S.antithetic = antithetic;
+    S.n_scen = n_scenarios;
+    for (int k = 0; k < n_scenarios; ++k) {
+        S.a0[k] = a0[k];
+        S.sigma[k] = sigma[k];
+        S.strikes[k] = strikes[k];
+        S.is_call[k] = is_call[k] ? 1 : 0;
+    }
+    S.partials = reinterpret_cast<double *>(ctx->scratch);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int gx = (int)std::max<int64_t>(
+        1, std::min<int64_t>((n_local + 255) / 256, (int64_t)ctx->sm_count * 2));
+    k_sigma_sweep<<<dim3(gx, n_scenarios), 256, 0, st>>>(S);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    k_finish_sweep<<<n_scenarios, 256, 0, st>>>(S.partials, gx, (double)n_local, moments_dev);
+    ctx->launches++;
+    CK(cudaGetLastError());
     return 0;
 }
 

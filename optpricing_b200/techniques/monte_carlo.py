@@ -374,7 +374,7 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
         """Spot / rate bumps can be read off ONE simulation: the log-Euler models'
         log S_T is (log S_0 + r T) plus a term that depends on neither."""
         return (self._philox_sde(model) and model_kind(model) in self._LOG_KINDS
-                and not self.control_variate)
+                and self.precision == "fp64")
 
     def _bumped_prices(self, option, stock, model, rate, spot_factors=(), rate_shifts=(), **kw):
         """
@@ -393,7 +393,17 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
             mom, _, _ = self._sweep(model, S0, r, q, T, strikes, [1 if call else 0] * len(scen),
                                     **kw)
         disc = math.exp(-r * T)
-        return [f * disc * m[1] / m[0] for (f, h), m in zip(scen, mom)]
+        if not self.control_variate:
+            return [f * disc * m[1] / m[0] for (f, h), m in zip(scen, mom)]
+        # control variate under the scaling: payoff and control both scale by g = f e^{hT},
+        # so beta is unchanged and the estimate of the base strike-K' problem scales by f
+        # (e^{-(r+h)T} g = f e^{-rT})
+        c_mean = control_mean(model_kind(model), model.params, S0, r, q, T, self.n_steps)
+        out = []
+        for (f, h), m in zip(scen, mom):
+            st = summarize(m, r, T, c_mean)
+            out.append(f * st.get("cv_price", st["price"]))
+        return out
 
     def delta(self, option, stock, model, rate, h_frac: float = 1e-3, **kwargs: Any) -> float:
         if not self._scaling_greeks_ok(model):
@@ -448,6 +458,57 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
         if all_reduce is not None:
             all_reduce(dev[: _engine.NMOM])
         return DeviceTerminal(dev[: _engine.NMOM].cpu().numpy(), kind, seed)
+
+    _ONE_FACTOR_KINDS = ("bsm", "merton", "kou")
+
+    def vega(self, option, stock, model, rate, h: float = 1e-4, **kw: Any) -> float:
+        """
+        GreekMixin.vega (greek_mixin.py:125-175): central difference in ``sigma`` on common
+        random numbers.  For the one-factor log-Euler models log S_T = log S_0 + n drift(sigma)
+        + sigma W + J with W, J independent of sigma, so both bumped prices are read off ONE
+        simulation that stores (W, J) per path; other models re-price twice as the reference.
+        """
+        if "sigma" not in model.params:
+            return np.nan
+        kind = model_kind(model) if self._philox_sde(model) else None
+        if kind not in self._ONE_FACTOR_KINDS or self.precision != "fp64":
+            return super().vega(option, stock, model, rate, h, **kw)
+        eng = _engine.get_engine()
+        S0, K, T = stock.spot, option.strike, option.maturity
+        r, q = rate.get_rate(T), stock.dividend
+        call = _is_call(option)
+        num_draws = self.n_paths // 2 if self.antithetic else self.n_paths
+        with crn(self.rng):                       # greeks do not advance the stream
+            seed = int(self.rng.integers(0, 2**63 - 1, dtype=np.int64))
+        mdl = _engine.make_model(kind, model.params, r, q)
+        rank, world, all_reduce = self._group()
+        off, cnt = shard_draws(num_draws, rank, world)
+        sim = eng.make_sim(float(S0), T, num_draws, self.n_steps, self.antithetic, seed,
+                           _engine.CORR_REFERENCE_EUROPEAN, off, cnt)
+        aux = eng.buffer("aux_wj", 3 * cnt)
+        eng.european_async(mdl, sim, [float(K)], [1 if call else 0],
+                           eng.buffer("moments", _engine.NMOM), aux=aux)
+        p = model.params
+        dt = T / self.n_steps
+        comp = 0.0
+        if kind == "merton":
+            comp = p["lambda"] * (math.exp(p["mu_j"] + 0.5 * p["sigma_j"] ** 2) - 1)
+        elif kind == "kou":
+            comp = p["lambda"] * ((p["p_up"] * p["eta1"] / (p["eta1"] - 1))
+                                  + ((1 - p["p_up"]) * p["eta2"] / (p["eta2"] + 1)) - 1)
+        sigmas = [p["sigma"] + h, p["sigma"] - h]
+        a0 = [math.log(S0) + self.n_steps * ((r - q - 0.5 * s * s - comp) * dt) for s in sigmas]
+        dev = eng.sigma_sweep(aux, cnt, self.antithetic, a0, sigmas, [float(K)] * 2,
+                              [1 if call else 0] * 2)
+        if all_reduce is not None:
+            all_reduce(dev[: 2 * _engine.NMOM])
+        mom = dev[: 2 * _engine.NMOM].cpu().numpy().reshape(2, _engine.NMOM)
+        c_mean = control_mean(kind, p, S0, r, q, T, self.n_steps)
+        prices = []
+        for row in mom:
+            st = summarize(row, r, T, c_mean)
+            prices.append(st["cv_price"] if self.control_variate and "cv_price" in st else st["price"])
+        return (prices[0] - prices[1]) / (2 * h)
 
     def _simulate_levy_terminal(self, model, S0: float, r: float, q: float, T: float):
         """

@@ -466,6 +466,35 @@ def test_fused_greeks_equal_bump_and_reprice(kind):
         assert a.price(opt, STQ, model, RT).price == b.price(opt, STQ, model, RT).price
 
 
+@pytest.mark.parametrize("cv", (False, True))
+@pytest.mark.parametrize("kind", ("bsm", "merton", "kou"))
+def test_one_simulation_vega_equals_bump_and_reprice(kind, cv):
+    """vega from the stored (W, J) of ONE simulation == GreekMixin.vega's two re-pricings on
+    common random numbers (greek_mixin.py:125-175), with and without the control variate."""
+    from optpricing_b200.techniques.base import GreekMixin
+    model = MODELS[kind]()
+    mk = lambda: ob.MonteCarloTechnique(n_paths=(1 << 18) + 2, n_steps=25, seed=8,  # noqa: E731
+                                        control_variate=cv)
+    for opt in (CALL, PUT):
+        a, b = mk(), mk()
+        launches0 = _engine.get_engine().launch_count()
+        got = a.vega(opt, STQ, model, RT)
+        assert _engine.get_engine().launch_count() - launches0 == 4     # 1 simulation + 1 sweep
+        assert got == pytest.approx(GreekMixin.vega(b, opt, STQ, model, RT), rel=1e-6)
+        assert a.price(opt, STQ, model, RT).price == b.price(opt, STQ, model, RT).price
+
+
+@pytest.mark.parametrize("kind", ("bsm", "heston", "kou"))
+def test_fused_greeks_with_control_variate(kind):
+    from optpricing_b200.techniques.base import GreekMixin
+    model = MODELS[kind]()
+    mk = lambda: ob.MonteCarloTechnique(n_paths=1 << 18, n_steps=24, seed=8,  # noqa: E731
+                                        control_variate=True)
+    a, b = mk(), mk()
+    assert a.delta(PUT, STQ, model, RT) == pytest.approx(GreekMixin.delta(b, PUT, STQ, model, RT), rel=1e-7)
+    assert a.rho(CALL, STQ, model, RT) == pytest.approx(GreekMixin.rho(b, CALL, STQ, model, RT), rel=1e-7)
+
+
 def test_sabr_greeks_fall_back_to_repricing():
     t = ob.MonteCarloTechnique(n_paths=1 << 18, n_steps=24, seed=8)
     d = t.delta(CALL, STQ, ob.SABRModel(), RT)
