@@ -337,7 +337,12 @@ int optmc_fp64_peak(optmc_ctx *ctx, int64_t iters, double *fma_per_sec, double *
    default 1), "euro_blocks_per_sm" (0 = occupancy API decides), "euro_threads"
    (threads per block of the European kernel: 64, 128 or 256), "lsmc_mode"
    (optmc_lsmc: 1 = every exercise date in one persistent cooperative launch,
-   default; 0 = one optmc_lsmc_step_async launch per date). */
+   default; 0 = one optmc_lsmc_step_async launch per date), "lsmc_use_peers"
+   (1 = the next optmc_lsmc calls are joint calls of the attached ranks, see
+   optmc_lsmc_peer_attach; 0 = local), "lsmc_timing_ptr" (diagnostics: a device
+   pointer, as an integer, to (n_steps + 1) * 4 uint64 that block 0 of the
+   persistent kernel fills with %globaltimer stamps per date; 0 = off --
+   tools/lsmc_phases.py). */
 int optmc_set_int(optmc_ctx *ctx, const char *key, int64_t value);
 
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
