@@ -19,7 +19,8 @@
  *   - functions whose name ends in _async only enqueue work on `stream`; the
  *     others synchronise the stream once before returning and write their
  *     results to host memory.
- *   - all floating point is IEEE binary64.
+ *   - all floating point is IEEE binary64 (the step loop of the European kernels
+ *     has an optional binary32 mode, optmc_sim.precision).
  */
 #ifndef OPTMC_H
 #define OPTMC_H
