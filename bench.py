@@ -463,6 +463,19 @@ def run_secondary(args, name):
                     "h2d_bytes_per_step": 212, "d2h_bytes_per_step": 48, "api": "technique.price"},
             "gpu_launches": eng.launch_count() - launches0,
             "result_sample": (float(np.ravel(out)[0]) if not isinstance(out, float) else out)}
+    if name == "c3" and world == 1:
+        # SURVEY 8 d2 asks for both forms: the batched sweep (the line's value) and the drop-in
+        # loop of 256 independent price() calls, each simulating its own 2^22 paths
+        t = {T: ob.MonteCarloTechnique(n_paths=1 << 22, n_steps=int(252 * T), seed=7) for T in mats}
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        loop_prices = [t[T].price(o, stock, model, rate).price for T in mats for o in opts[T]]
+        torch.cuda.synchronize()
+        loop_s = time.perf_counter() - t0
+        line["config"]["drop_in_loop"] = {
+            "calls": len(loop_prices), "seconds": loop_s,
+            "path_steps_per_s": 64 * units / loop_s,
+            "note": "256 technique.price() calls, one simulation of 2^22 paths each"}
     if name == "c5":
         line["config"]["results"] = dict(zip(
             ("sabr_jump_price", "sabr_jump_delta", "sabr_jump_vega", "kou_price", "kou_delta",
