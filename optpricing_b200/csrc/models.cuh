@@ -158,20 +158,35 @@ __device__ __forceinline__ double sabr_pow(double s_pos, const Consts &c, RngVie
 // ln v += a + alpha cz, and the diffusion coefficient v s^beta = exp(ln v + beta ln s)
 // costs ONE exponential per step instead of two (the same reals; rounding differs by
 // ~1e-16 per step, so the fed-draw parity kernels keep the literal form).
+// max(a, 1e-8) and max(a, -650) in ONE integer-pipe instruction each, like relu64
+// (fp64 max is DSETP + two selects here).  Doubles order like their high words:
+// signed for the positive floor, unsigned -- where every negative sorts above every
+// positive, by magnitude -- for the negative one.  The result can differ from the
+// exact max by the low word of `a` (relative 2^-20) only when `a` is within one
+// high-word step of the bound: the floor 1e-8 and the underflow guard -650 are
+// arbitrary at that level.
+__device__ __forceinline__ double floor_1e8(double a) {
+    return __hiloint2double(max(__double2hiint(a), 0x3E45798E), __double2loint(a));
+}
+__device__ __forceinline__ double floor_neg650(double a) {
+    return __hiloint2double((int)min((unsigned)__double2hiint(a), 0xC0845000u), __double2loint(a));
+}
+
 template <bool LOGV>
 __device__ __forceinline__ void step_sabr(State &s, double z1, double cz, const Consts &c,
                                           RngView t) {
-    double s_pos = fmax(s.x, 1e-8);
     if constexpr (LOGV) {
+        const double s_pos = floor_1e8(s.x);
         double coef;
         switch (c.beta_mode) {
-            case 1: coef = fast_exp(fmax(s.v, -650.0), t) * s_pos; break;
-            case 2: coef = fast_exp(fmax(s.v, -650.0), t); break;
-            default: coef = fast_exp(fmax(fma(c.beta, fast_log(s_pos, t), s.v), -650.0), t);
+            case 1: coef = fast_exp(floor_neg650(s.v), t) * s_pos; break;
+            case 2: coef = fast_exp(floor_neg650(s.v), t); break;
+            default: coef = fast_exp(floor_neg650(fma(c.beta, fast_log(s_pos, t), s.v)), t);
         }
         s.x += fma(coef, z1, c.rqc_dt * s_pos);
         s.v += fma(c.alpha, cz, c.neg_half_alpha2_dt);
     } else {
+        double s_pos = fmax(s.x, 1e-8);
         double v_pos = relu64(s.v);
         s.x += fma(v_pos * sabr_pow(s_pos, c, t), z1, c.rqc_dt * s_pos);
         s.v = s.v * fast_exp(fma(c.alpha, cz, c.neg_half_alpha2_dt), t);
