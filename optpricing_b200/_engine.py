@@ -366,14 +366,16 @@ class Engine:
             self.stream()), "optmc_sigma_sweep_async")
         return mom
 
-    def payoff_sweep(self, terminal, n_local, antithetic, strikes, is_call, to_host=True):
+    def payoff_sweep(self, terminal, n_local, antithetic, strikes, is_call, to_host=True, out=None):
+        """optmc_payoff_sweep_async; ``out`` (device tensor, n_contracts * 6 f64) receives the
+        moments without any synchronisation, else a cached buffer is used."""
         k, c, kp, cp = self._contracts(strikes, is_call)
-        mom = self.buffer("sweep_moments", k.size * NMOM)
+        mom = out if out is not None else self.buffer("sweep_moments", k.size * NMOM)
         self._check(self.lib.optmc_payoff_sweep_async(self.ctx, c_void_p(terminal.data_ptr()),
                                                       int(n_local), 1 if antithetic else 0,
                                                       k.size, kp, cp, c_void_p(mom.data_ptr()),
                                                       self.stream()), "optmc_payoff_sweep_async")
-        if not to_host:
+        if not to_host or out is not None:
             return mom
         return mom[: k.size * NMOM].cpu().numpy().reshape(k.size, NMOM)
 

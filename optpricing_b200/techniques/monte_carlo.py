@@ -298,44 +298,49 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
                 and not getattr(model, "has_exact_sampler", False)
                 and not getattr(model, "is_pure_levy", False))
 
-    def _sweep(self, model, S0, r, q, T, strikes, calls, seed=None, **kwargs):
+    def _sweep_async(self, model, S0, r, q, T, strikes, calls, out_dev, seed=None, **kwargs):
         """
-        ONE simulation to maturity T, payoff moments for every (strike, type):
-        the terminal spots stay in HBM (8 B per path) and a sweep kernel reduces
-        them per contract.  Returns (moments[n, 6], kind, seed).
+        Enqueue ONE simulation to maturity T and the payoff moments of every
+        (strike, type) into ``out_dev`` (device, 6 doubles per contract): the
+        terminal spots stay in HBM (8 B per path) and a sweep kernel reduces them
+        per contract.  Nothing is synchronised or all-reduced here.  Returns
+        (kind, seed, keepalive) -- hold ``keepalive`` until the stream has run.
         """
         eng = _engine.get_engine()
         kind = model_kind(model)
         num_draws = self.n_paths // 2 if self.antithetic else self.n_paths
         if seed is None:
             seed = int(self.rng.integers(0, 2**63 - 1, dtype=np.int64))
-        mdl, _keep = self._device_model(eng, kind, model, S0, r, q, T, **kwargs)
+        mdl, keep = self._device_model(eng, kind, model, S0, r, q, T, **kwargs)
         corr = (_engine.CORR_REFERENCE_EUROPEAN if self.correlation == "reference"
                 else _engine.CORR_INDEPENDENT_DRAWS)
-        rank, world, all_reduce = self._group()
+        rank, world, _ = self._group()
         off, cnt = shard_draws(num_draws, rank, world)
         sim = eng.make_sim(float(S0), T, num_draws, self.n_steps, self.antithetic, seed, corr,
                            off, cnt, precision=1 if self.precision == "fp32" else 0)
         strikes = np.ascontiguousarray(strikes, dtype=np.float64)
         calls = np.ascontiguousarray(calls, dtype=np.int32)
         term = eng.buffer("terminal", cnt * (2 if self.antithetic else 1))
-        out = np.empty((strikes.size, _engine.NMOM))
         for lo in range(0, strikes.size, 64):
             ks, cs = strikes[lo:lo + 64], calls[lo:lo + 64]
+            dst = out_dev[lo * _engine.NMOM:(lo + ks.size) * _engine.NMOM]
             if lo == 0:
-                if all_reduce is None:
-                    out[lo:lo + ks.size] = eng.european(mdl, sim, ks, cs, terminal=term)
-                    continue
-                dev = eng.buffer("moments_many", 64 * _engine.NMOM)
-                eng.european_async(mdl, sim, ks, cs, dev, terminal=term)
+                eng.european_async(mdl, sim, ks, cs, dst, terminal=term)
             else:                                   # further chunks reuse the stored terminals
-                if all_reduce is None:
-                    out[lo:lo + ks.size] = eng.payoff_sweep(term, cnt, self.antithetic, ks, cs)
-                    continue
-                dev = eng.payoff_sweep(term, cnt, self.antithetic, ks, cs, to_host=False)
-            all_reduce(dev[: ks.size * _engine.NMOM])
-            out[lo:lo + ks.size] = dev[: ks.size * _engine.NMOM].cpu().numpy().reshape(-1, 6)
-        return out, kind, seed
+                eng.payoff_sweep(term, cnt, self.antithetic, ks, cs, out=dst)
+        return kind, seed, keep
+
+    def _sweep(self, model, S0, r, q, T, strikes, calls, seed=None, **kwargs):
+        """One simulation, all contracts of one maturity -> (moments[n, 6], kind, seed)."""
+        eng = _engine.get_engine()
+        n = len(strikes)
+        dev = eng.buffer("moments_many", n * _engine.NMOM)
+        kind, seed, _keep = self._sweep_async(model, S0, r, q, T, strikes, calls,
+                                              dev[: n * _engine.NMOM], seed=seed, **kwargs)
+        _, _, all_reduce = self._group()
+        if all_reduce is not None:
+            all_reduce(dev[: n * _engine.NMOM])
+        return dev[: n * _engine.NMOM].cpu().numpy().reshape(n, _engine.NMOM), kind, seed
 
     def price_many(self, options, stock, model, rate, **kwargs: Any) -> np.ndarray:
         """
@@ -343,27 +348,42 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
         maturity share one simulation (BASELINE config 3: 64 strikes x 4
         maturities = 4 simulations instead of 256).  Equivalent to calling
         ``price`` per contract with common random numbers within a maturity.
+        All simulations and sweeps are enqueued back to back; there is ONE
+        all-reduce (several ranks) and ONE device-to-host copy for the whole batch.
         """
         options = list(options)
         if not self._philox_sde(model):
             return np.array([self.price(o, stock, model, rate, **kwargs).price for o in options])
+        eng = _engine.get_engine()
         prices = np.empty(len(options))
         self.last_stats_many = [None] * len(options)
         by_T: dict[float, list[int]] = {}
         for i, o in enumerate(options):
             by_T.setdefault(float(o.maturity), []).append(i)
         S0, q = stock.spot, stock.dividend
+        total = len(options)
+        dev = eng.buffer("moments_many", total * _engine.NMOM)
+        jobs, keep, pos = [], [], 0
         for T, idx in by_T.items():
             r = rate.get_rate(T)
-            mom, kind, seed = self._sweep(model, S0, r, q, T, [options[i].strike for i in idx],
-                                          [1 if _is_call(options[i]) else 0 for i in idx],
-                                          **kwargs)
+            out = dev[pos * _engine.NMOM:(pos + len(idx)) * _engine.NMOM]
+            kind, seed, k = self._sweep_async(
+                model, S0, r, q, T, [options[i].strike for i in idx],
+                [1 if _is_call(options[i]) else 0 for i in idx], out, **kwargs)
+            jobs.append((T, r, idx, pos, kind, seed))
+            keep.append(k)
+            pos += len(idx)
+        _, _, all_reduce = self._group()
+        if all_reduce is not None:
+            all_reduce(dev[: total * _engine.NMOM])
+        mom_all = dev[: total * _engine.NMOM].cpu().numpy().reshape(total, _engine.NMOM)
+        for T, r, idx, pos, kind, seed in jobs:
             c_mean = control_mean(kind, model.params, S0, r, q, T, self.n_steps)
-            for row, i in zip(mom, idx):
+            for row, i in zip(mom_all[pos:pos + len(idx)], idx):
                 st = summarize(row, r, T, c_mean)
                 st["seed"] = seed
                 self.last_stats_many[i] = st
-                use_cv = self.control_variate and "cv_price" in st
+                use_cv = self.control_variate and "cv_price" in st and math.isfinite(c_mean)
                 prices[i] = st["cv_price"] if use_cv else st["price"]
         return prices
 
