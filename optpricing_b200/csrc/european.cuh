@@ -283,33 +283,54 @@ struct SweepArgs {
     double *partials;         // [n_contracts][gridDim.x][NPART]
 };
 
+// Each thread reads a terminal pair once and prices SWEEP_G contracts on it (block.y =
+// group of SWEEP_G contracts): the terminal array crosses L2 n_contracts / SWEEP_G times
+// instead of n_contracts times.  The control sums do not depend on the contract.
+constexpr int SWEEP_G = 8;
+
 __global__ void __launch_bounds__(256) k_payoff_sweep(const SweepArgs A) {
-    __shared__ double scratch[5 * 32];
-    const int cidx = blockIdx.y;
-    const double K = A.strikes[cidx];
-    const bool call = A.is_call[cidx] != 0;
-    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    constexpr int NACC = 3 * SWEEP_G + 2;
+    __shared__ double scratch[NACC * 32];
+    const int c0 = blockIdx.y * SWEEP_G;
+    double K[SWEEP_G], sgn[SWEEP_G];
+#pragma unroll
+    for (int j = 0; j < SWEEP_G; ++j) {
+        const int cidx = min(c0 + j, A.n_contracts - 1);
+        K[j] = A.strikes[cidx];
+        sgn[j] = A.is_call[cidx] ? 1.0 : -1.0;          // payoff = max(sgn (S - K), 0)
+    }
+    double acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < A.n_local; g += stride) {
-        double ST = A.terminal[g];
-        double pay = fmax(call ? ST - K : K - ST, 0.0);
-        double ctl = ST;
-        if (A.antithetic) {
-            double STb = A.terminal[A.n_local + g];
-            pay = 0.5 * (pay + fmax(call ? STb - K : K - STb, 0.0));
-            ctl = 0.5 * (ST + STb);
-        }
-        acc[0] += pay;
-        acc[1] = fma(pay, pay, acc[1]);
-        acc[2] += ctl;
-        acc[3] = fma(ctl, ctl, acc[3]);
-        acc[4] = fma(pay, ctl, acc[4]);
-    }
-    block_sum<5>(acc, scratch);
-    if (threadIdx.x == 0) {
-        double *p = A.partials + ((size_t)cidx * gridDim.x + blockIdx.x) * NPART;
+        const double ST = A.terminal[g];
+        const double STb = A.antithetic ? A.terminal[A.n_local + g] : ST;
+        const double ctl = A.antithetic ? 0.5 * (ST + STb) : ST;
+        acc[3 * SWEEP_G] += ctl;
+        acc[3 * SWEEP_G + 1] = fma(ctl, ctl, acc[3 * SWEEP_G + 1]);
 #pragma unroll
-        for (int k = 0; k < 5; ++k) p[k] = acc[k];
+        for (int j = 0; j < SWEEP_G; ++j) {
+            double pay = fmax(sgn[j] * (ST - K[j]), 0.0);
+            if (A.antithetic) pay = 0.5 * (pay + fmax(sgn[j] * (STb - K[j]), 0.0));
+            acc[3 * j] += pay;
+            acc[3 * j + 1] = fma(pay, pay, acc[3 * j + 1]);
+            acc[3 * j + 2] = fma(pay, ctl, acc[3 * j + 2]);
+        }
+    }
+    block_sum<NACC>(acc, scratch);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < SWEEP_G; ++j) {
+            if (c0 + j < A.n_contracts) {
+                double *p = A.partials + ((size_t)(c0 + j) * gridDim.x + blockIdx.x) * NPART;
+                p[0] = acc[3 * j];
+                p[1] = acc[3 * j + 1];
+                p[2] = acc[3 * SWEEP_G];
+                p[3] = acc[3 * SWEEP_G + 1];
+                p[4] = acc[3 * j + 2];
+            }
+        }
     }
 }
 

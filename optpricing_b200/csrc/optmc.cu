@@ -416,7 +416,7 @@ static int sweep_launch(optmc_ctx *ctx, const double *terminal_dev, int64_t n_lo
             S.is_call[k] = is_call[c0 + k] ? 1 : 0;
         }
         S.partials = partials;
-        k_payoff_sweep<<<dim3(gx, S.n_contracts), 256, 0, st>>>(S);
+        k_payoff_sweep<<<dim3(gx, (S.n_contracts + SWEEP_G - 1) / SWEEP_G), 256, 0, st>>>(S);
         ctx->launches++;
         CK(cudaGetLastError());
         k_finish_sweep<<<S.n_contracts, 256, 0, st>>>(partials, gx, (double)n_local,
