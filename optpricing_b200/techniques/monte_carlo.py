@@ -98,6 +98,44 @@ def summarize(moments, r: float, T: float, c_mean: float) -> dict:
     return out
 
 
+def prices_from_moments(mom: np.ndarray, r: float, T: float, c_mean: float, use_cv: bool):
+    """Vectorised ``summarize`` for the price only: mom is (n, 6)."""
+    n, sp, spp, sc, scc, spc = (mom[:, k] for k in range(6))
+    disc = math.exp(-r * T)
+    mp, mc = sp / n, sc / n
+    price = disc * mp
+    if not (use_cv and math.isfinite(c_mean)):
+        return price
+    var_c = scc / n - mc * mc
+    cov = spc / n - mp * mc
+    ok = var_c > 0.0
+    beta = np.where(ok, cov / np.where(ok, var_c, 1.0), 0.0)
+    return np.where(ok, disc * (mp - beta * (mc - c_mean)), price)
+
+
+class LazyStats:
+    """``last_stats_many``: the per-contract statistics dict is built on access, so a
+    sweep over hundreds of contracts does not pay for dictionaries nobody reads."""
+
+    def __init__(self, n):
+        self._rows = [None] * n
+
+    def _set(self, i, row, r, T, c_mean, seed):
+        self._rows[i] = (row, r, T, c_mean, seed)
+
+    def __len__(self):
+        return len(self._rows)
+
+    def __getitem__(self, i):
+        row, r, T, c_mean, seed = self._rows[i]
+        st = summarize(row, r, T, c_mean)
+        st["seed"] = seed
+        return st
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
 class DeviceTerminal:
     """What the Philox path hands from the simulator to ``price``: the payoff
     moments of the hinted contract instead of a host array of terminal spots."""
@@ -356,7 +394,7 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
             return np.array([self.price(o, stock, model, rate, **kwargs).price for o in options])
         eng = _engine.get_engine()
         prices = np.empty(len(options))
-        self.last_stats_many = [None] * len(options)
+        self.last_stats_many = LazyStats(len(options))
         by_T: dict[float, list[int]] = {}
         for i, o in enumerate(options):
             by_T.setdefault(float(o.maturity), []).append(i)
@@ -379,12 +417,10 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
         mom_all = dev[: total * _engine.NMOM].cpu().numpy().reshape(total, _engine.NMOM)
         for T, r, idx, pos, kind, seed in jobs:
             c_mean = control_mean(kind, model.params, S0, r, q, T, self.n_steps)
-            for row, i in zip(mom_all[pos:pos + len(idx)], idx):
-                st = summarize(row, r, T, c_mean)
-                st["seed"] = seed
-                self.last_stats_many[i] = st
-                use_cv = self.control_variate and "cv_price" in st and math.isfinite(c_mean)
-                prices[i] = st["cv_price"] if use_cv else st["price"]
+            block = mom_all[pos:pos + len(idx)]
+            prices[idx] = prices_from_moments(block, r, T, c_mean, self.control_variate)
+            for row, i in zip(block, idx):
+                self.last_stats_many._set(i, row, r, T, c_mean, seed)
         return prices
 
     # ------------------------------------------------------ fused greeks

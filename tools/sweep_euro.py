@@ -16,7 +16,7 @@ params = {"heston": HESTON, "bsm": {"sigma": 0.2},
           "sabr": {"alpha": 0.5, "beta": 0.8, "rho": -0.6},
           "sabr_jump": {"alpha": 0.5, "beta": 0.8, "rho": -0.6, "lambda": 0.4, "mu_j": -0.1, "sigma_j": 0.15}}[kind]
 mdl = _engine.make_model(kind, params, 0.05, 0.0)
-n_paths, n_steps = 1 << 24, 252
+n_paths, n_steps = int(os.environ.get("N_PATHS", 1 << 24)), int(os.environ.get("N_STEPS", 252))
 mom = torch.zeros(6, dtype=torch.float64, device=eng.device)
 configs = [(int(a), int(b)) for a, b in (c.split("x") for c in sys.argv[1:])] or [(256, 0)]
 for threads, per_sm in configs:
@@ -35,5 +35,5 @@ for threads, per_sm in configs:
             best = min(best, a.elapsed_time(b))
     m = mom.cpu().numpy()
     print(f"{os.path.basename(_engine.LIB_PATH):22s} {'fp32' if os.environ.get('PRECISION') == '1' else 'fp64'} {kind} threads={threads:3d} blocks/SM={per_sm:2d}: "
-          f"{best:7.3f} ms  {n_paths * n_steps / best / 1e6:8.1f} G path-steps/s  price~{m[1] / m[0] * 0.951229:.4f}",
+          f"{n_paths}x{n_steps} {best:7.3f} ms  {n_paths * n_steps / best / 1e6:8.1f} G path-steps/s  price~{m[1] / m[0] * 0.951229:.4f}",
           flush=True)
