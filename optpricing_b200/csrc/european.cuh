@@ -42,16 +42,27 @@ struct EuroArgs {
     double *aux;        // optional, one-factor log models: [W | J | J partner], n_local each
 };
 
-// One jump size (rare path: CUDA math library, no table needed).
-template <int KIND>
-__device__ __forceinline__ double jump_size(uint4 w, const Consts &c) {
+// One jump size.  NIMPL 0: CUDA math library.  NIMPL 1: the block's tables -- the first
+// output of the step loop's own normal generator is sqrt(dt) N(0,1) for every kind (the
+// two-factor mixing row (m11, m12) has norm sqrt(dt) in both correlation modes), and
+// -ln u comes from the log table.  With lambda T of order one most warps reach this
+// epilogue, so it is not as rare as a single step's jump.
+template <int KIND, int NIMPL>
+__device__ __forceinline__ double jump_size(uint4 w, const Consts &c, RngView tab) {
     if constexpr (KIND == OPTMC_KOU) {
         // up w.p. p_up: +Exp(eta1), else -Exp(eta2)   (mc_kernels.py:314-317)
-        double e = -log(u01_open(w.x, w.y));
+        double e;
+        if constexpr (NIMPL == 0) e = -log(u01_open(w.x, w.y));
+        else e = 0.5 * neg2_log_u(w.x, w.y, tab);
         return w.w < c.p_up_bits ? e * c.inv_eta1 : -e * c.inv_eta2;
     } else {
         double z1, z2;
-        normal_pair_lib(w.x, w.y, w.z, z1, z2);
+        if constexpr (NIMPL == 0) {
+            normal_pair_lib(w.x, w.y, w.z, z1, z2);
+        } else {
+            normal_pair_fast<kind_two_factor(KIND)>(w.x, w.y, w.z, z1, z2, tab);
+            z1 *= c.inv_sqrt_dt;
+        }
         return fma(c.sigma_j, z1, c.mu_j);           // N(mu_j, sigma_j)  (mc_kernels.py:111)
     }
 }
@@ -63,19 +74,19 @@ __device__ __forceinline__ double jump_size(uint4 w, const Consts &c) {
 // passed by reference.  Inlined on purpose: an out-of-line call would force the
 // kernel parameters (constants, Philox key) to be copied to local memory so that
 // their address can be taken.
-template <int KIND, bool ANTI>
+template <int KIND, bool ANTI, int NIMPL = 0>
 __device__ __forceinline__ double2 jumps_slow(uint32_t w, double mu, double p0, const PhiloxKey &key,
                                            uint32_t id_lo, uint32_t id_hi, uint32_t step,
-                                           const Consts &c) {
+                                           const Consts &c, RngView tab = RngView{0u}) {
     uint4 e = philox4x32_10(make_uint4(id_lo, id_hi, step, 0xFFu), key);
     int n = poisson_slow(w, e.x, mu, p0);
     double2 acc = make_double2(0.0, 0.0);
     for (int j = 0; j < n; ++j) {
-        acc.x += jump_size<KIND>(
-            philox4x32_10(make_uint4(id_lo, id_hi, step, 1u | ((uint32_t)j << 8)), key), c);
+        acc.x += jump_size<KIND, NIMPL>(
+            philox4x32_10(make_uint4(id_lo, id_hi, step, 1u | ((uint32_t)j << 8)), key), c, tab);
         if constexpr (ANTI)
-            acc.y += jump_size<KIND>(
-                philox4x32_10(make_uint4(id_lo, id_hi, step, 2u | ((uint32_t)j << 8)), key), c);
+            acc.y += jump_size<KIND, NIMPL>(
+                philox4x32_10(make_uint4(id_lo, id_hi, step, 2u | ((uint32_t)j << 8)), key), c, tab);
     }
     return acc;
 }
@@ -177,9 +188,9 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
             // steps does not affect S_T.
             const bool two = (SPC == 2 && i + 1 < A.n_steps);
             if (__builtin_expect(poisson_maybe(w.w, two ? A.pois_p0_bits[1] : A.pois_p0_bits[0]), 0)) {
-                double2 J = jumps_slow<KIND, ANTI>(w.w, two ? A.pois_mu[1] : A.pois_mu[0],
-                                                   two ? A.pois_p0[1] : A.pois_p0[0], A.key, id_lo,
-                                                   id_hi, (uint32_t)i, c);
+                double2 J = jumps_slow<KIND, ANTI, NIMPL>(w.w, two ? A.pois_mu[1] : A.pois_mu[0],
+                                                          two ? A.pois_p0[1] : A.pois_p0[0], A.key,
+                                                          id_lo, id_hi, (uint32_t)i, c, tab);
                 // additive in log space (mc_kernels.py:115,174,323); multiplicative on S for
                 // SABR-jump (:274): the product of exp(J_j) is exp of the sum
                 apply_jump<KIND, DEFER>(sa, J.x);
@@ -191,8 +202,8 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
     if constexpr (JUMPS_AT_END) {
         uint4 e = philox4x32_10(make_uint4(id_lo, id_hi, 0xFFFFFFFFu, 0xFEu), A.key);
         if (poisson_maybe(e.x, (uint32_t)fmin(floor(A.pois_p0_path * 4294967296.0), 4294967295.0))) {
-            double2 J = jumps_slow<KIND, ANTI>(e.x, A.pois_mu_path, A.pois_p0_path, A.key, id_lo,
-                                               id_hi, 0xFFFFFFFFu, c);
+            double2 J = jumps_slow<KIND, ANTI, NIMPL>(e.x, A.pois_mu_path, A.pois_p0_path, A.key,
+                                                      id_lo, id_hi, 0xFFFFFFFFu, c, tab);
             apply_jump<KIND, DEFER>(sa, J.x);
             if constexpr (ANTI) apply_jump<KIND, DEFER>(sb, J.y);
         }

@@ -20,7 +20,7 @@ struct Consts {
     int beta_mode;            // SABR: 0 general pow, 1 beta==1, 2 beta==0, 3 beta==0.5
     double x0;                // log_s0, or s0 for SABR kinds        (monte_carlo.py:217-220)
     double v0;
-    double dt, sqrt_dt;
+    double dt, sqrt_dt, inv_sqrt_dt;
     double r, q;
     // one-factor log models
     double sigma;

@@ -207,6 +207,7 @@ static int make_consts(optmc_ctx *ctx, const optmc_model *m, double x0, double d
     c.v0 = m->v0;
     c.dt = dt;
     c.sqrt_dt = std::sqrt(dt);
+    c.inv_sqrt_dt = 1.0 / c.sqrt_dt;
     c.r = m->r;
     c.q = m->q;
     double comp = 0.0;
