@@ -566,6 +566,58 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
             prices.append(st["cv_price"] if self.control_variate and "cv_price" in st else st["price"])
         return (prices[0] - prices[1]) / (2 * h)
 
+    def implied_volatility(self, option, stock, model, rate, target_price: float,
+                           low: float = 1e-6, high: float = 5.0, tol: float = 1e-6,
+                           **kwargs: Any) -> float:
+        """
+        IVMixin.implied_volatility (iv_mixin.py:28-116): the Black-Scholes volatility at
+        which THIS technique reproduces ``target_price``.  The reference re-simulates at
+        every trial volatility with fresh draws, so its objective is noisy; here ONE
+        simulation stores the Brownian sums W and every trial sigma is a sweep over them
+        (log S_T = log S_0 + n drift(sigma) + sigma W): a smooth, monotone objective on
+        common random numbers, same brentq bracket and tolerance.  Falls back to the
+        mixin (re-simulation) outside the fp64 device-RNG mode.
+        """
+        if self.rng_mode != "philox" or self.precision != "fp64":
+            return super().implied_volatility(option, stock, model, rate, target_price, low, high,
+                                              tol, **kwargs)
+        from scipy.optimize import brentq
+
+        eng = _engine.get_engine()
+        S0, K, T = stock.spot, option.strike, option.maturity
+        r, q = rate.get_rate(T), stock.dividend
+        call = _is_call(option)
+        num_draws = self.n_paths // 2 if self.antithetic else self.n_paths
+        seed = int(self.rng.integers(0, 2**63 - 1, dtype=np.int64))     # one draw, like one price()
+        mdl = _engine.make_model("bsm", {"sigma": 0.3}, r, q)
+        rank, world, all_reduce = self._group()
+        off, cnt = shard_draws(num_draws, rank, world)
+        sim = eng.make_sim(float(S0), T, num_draws, self.n_steps, self.antithetic, seed,
+                           _engine.CORR_REFERENCE_EUROPEAN, off, cnt)
+        aux = eng.buffer("aux_wj", 3 * cnt)
+        eng.european_async(mdl, sim, [float(K)], [1 if call else 0],
+                           eng.buffer("moments", _engine.NMOM), aux=aux)
+        dt, disc = T / self.n_steps, math.exp(-r * T)
+
+        def gap(vol: float) -> float:
+            a0 = math.log(S0) + self.n_steps * ((r - q - 0.5 * vol * vol) * dt)
+            dev = eng.sigma_sweep(aux, cnt, self.antithetic, [a0], [vol], [float(K)],
+                                  [1 if call else 0])
+            if all_reduce is not None:
+                all_reduce(dev[: _engine.NMOM])
+            m = dev[: _engine.NMOM].cpu().numpy()
+            p = disc * m[1] / m[0]
+            return p - target_price if np.isfinite(p) else 1e6
+
+        try:
+            return brentq(gap, low, high, xtol=tol, disp=False)
+        except (ValueError, RuntimeError):
+            pass
+        try:
+            return self._secant_iv(gap, 0.2, tol, 100)
+        except (ValueError, RuntimeError):
+            return np.nan
+
     def _simulate_levy_terminal(self, model, S0: float, r: float, q: float, T: float):
         """
         Pure-Levy terminal sampling (monte_carlo.py:259-280).  The four laws the

@@ -758,3 +758,19 @@ def test_fp32_mode_restrictions():
     flat = ob.DupireLocalVolModel()
     with pytest.raises(_engine.EngineError, match="not available for Dupire"):
         ob.MonteCarloTechnique(precision="fp32", n_paths=1000, n_steps=4).price(CALL, ST, flat, RT)
+
+
+def test_implied_volatility_from_one_simulation(price_goldens):
+    """One simulation, every trial sigma a sweep over its Brownian sums: recovers the vol of a
+    Black-Scholes target to the Monte Carlo error, deterministically, with 2 + 2k launches."""
+    t = ob.MonteCarloTechnique(n_paths=1 << 22, n_steps=4, seed=6)
+    eng = _engine.get_engine()
+    sims0 = eng.n_simulations
+    iv = t.implied_volatility(CALL, ST, ob.BSMModel(), RT, target_price=price_goldens["G1_closed_form"])
+    assert eng.n_simulations - sims0 == 1
+    assert iv == pytest.approx(0.2, abs=3e-4)
+    t2 = ob.MonteCarloTechnique(n_paths=1 << 22, n_steps=4, seed=6)
+    assert t2.implied_volatility(CALL, ST, ob.BSMModel(), RT,
+                                 target_price=price_goldens["G1_closed_form"]) == iv
+    # an unreachable target has no root: NaN as in the reference (iv_mixin.py:81-116)
+    assert math.isnan(t.implied_volatility(CALL, ST, ob.BSMModel(), RT, target_price=1e9))
