@@ -486,9 +486,18 @@ class Engine:
         gathered = [self.torch.empty_like(t) for _ in range(world)]
         dist.all_gather(gathered, t, group=group)
         blob = bytes(self.torch.cat(gathered).cpu().numpy().tobytes())
-        self._check(self.lib.optmc_lsmc_peer_attach(self.ctx, rank, world, blob),
-                    "optmc_lsmc_peer_attach")
-        dist.barrier(group=group)          # every rank has mapped every buffer before first use
+        rc = self.lib.optmc_lsmc_peer_attach(self.ctx, rank, world, blob)
+        err = self.lib.optmc_last_error(self.ctx).decode() if rc else ""
+        # agree on the outcome (this all-reduce is also the barrier: every rank has mapped
+        # every buffer before anyone uses one): a rank without peer access must not leave
+        # the others waiting in the kernel
+        ok = self.torch.tensor([0 if rc else 1], dtype=self.torch.int32, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            self.lib.optmc_lsmc_peer_attach(self.ctx, 0, 1, None)
+            self._peer_key = None
+            raise EngineError("optmc_lsmc_peer_attach: peer mapping failed on at least one rank"
+                              + (f" (here: {err})" if err else ""))
         self._peer_key = key
         return rank, world
 

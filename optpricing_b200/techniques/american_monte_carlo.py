@@ -80,7 +80,13 @@ class AmericanMonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
 
         if dist.get_backend() != "nccl":
             return False
-        eng.lsmc_peer_attach()
+        try:
+            eng.lsmc_peer_attach()
+        except _engine.EngineError as exc:      # agreed on by all ranks (see lsmc_peer_attach)
+            import warnings
+            warnings.warn(f"NVLink exchange unavailable ({exc}); using one NCCL all-reduce per "
+                          "exercise date", RuntimeWarning, stacklevel=3)
+            return False
         return True
 
     def _group(self):
