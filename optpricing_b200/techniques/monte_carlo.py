@@ -83,6 +83,10 @@ def summarize(moments, r: float, T: float, c_mean: float) -> dict:
     """Price, standard error and control-variate estimate from (n, Sp, Spp, Sc, Scc, Spc)."""
     n, sp, spp, sc, scc, spc = (float(x) for x in moments)
     disc = math.exp(-r * T)
+    if n <= 0.0:        # no samples: the mean of an empty array, as np.mean gives the reference
+        return {"n_samples": 0.0, "price": float("nan"), "stderr": float("nan"),
+                "control_mean": float("nan"), "control_expected": c_mean,
+                "control_stderr": float("nan")}
     mp, mc = sp / n, sc / n
     var_p = max(spp / n - mp * mp, 0.0) * (n / (n - 1.0) if n > 1 else 1.0)
     out = {"n_samples": n, "price": disc * mp, "stderr": disc * math.sqrt(var_p / n),
@@ -102,7 +106,8 @@ def prices_from_moments(mom: np.ndarray, r: float, T: float, c_mean: float, use_
     """Vectorised ``summarize`` for the price only: mom is (n, 6)."""
     n, sp, spp, sc, scc, spc = (mom[:, k] for k in range(6))
     disc = math.exp(-r * T)
-    mp, mc = sp / n, sc / n
+    with np.errstate(divide="ignore", invalid="ignore"):      # n = 0 rows price to nan
+        mp, mc = sp / n, sc / n
     price = disc * mp
     if not (use_cv and math.isfinite(c_mean)):
         return price
@@ -269,6 +274,7 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
         """
         if self.rng_mode == "numpy":
             return self._simulate_sde_path_numpy(model, S0, r, q, T, **kwargs)
+        T / self.n_steps        # n_steps = 0 raises ZeroDivisionError, as the reference's dt (:209)
         kind = model_kind(model)
         eng = _engine.get_engine()
         num_draws = self.n_paths // 2 if self.antithetic else self.n_paths

@@ -198,6 +198,12 @@ def test_summarize_and_control_variate():
     assert s["cv_stderr"] < s["stderr"]
 
 
+def test_summarize_without_samples_is_nan():
+    st = mc_mod.summarize([0, 0, 0, 0, 0, 0], 0.05, 1.0, 105.0)
+    assert math.isnan(st["price"]) and st["n_samples"] == 0.0
+    assert np.all(np.isnan(mc_mod.prices_from_moments(np.zeros((2, 6)), 0.05, 1.0, 105.0, False)))
+
+
 def test_control_mean():
     f = mc_mod.control_mean
     assert f("heston", {}, 100.0, 0.05, 0.01, 2.0, 10) == pytest.approx(100 * math.exp(0.08))
