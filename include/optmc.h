@@ -342,7 +342,7 @@ int optmc_fp64_peak(optmc_ctx *ctx, int64_t iters, double *fma_per_sec, double *
    (1 = the next optmc_lsmc calls are joint calls of the attached ranks, see
    optmc_lsmc_peer_attach; 0 = local), "lsmc_timing_ptr" (diagnostics: a device
    pointer, as an integer, to (n_steps + 1) * 4 uint64 that block 0 of the
-   persistent kernel fills with %globaltimer stamps per date; 0 = off --
+   persistent kernel fills with clock64 stamps per date; 0 = off --
    tools/lsmc_phases.py). */
 int optmc_set_int(optmc_ctx *ctx, const char *key, int64_t value);
 

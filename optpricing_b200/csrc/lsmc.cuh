@@ -79,6 +79,21 @@ __global__ void __launch_bounds__(256) k_lsmc_load(const double *paths, int64_t 
 // Fully unrolled for the degree, so the factor lives in registers, and every
 // division by a pivot is a multiplication by its reciprocal square root: one
 // thread solves the system on the critical path between two exercise dates.
+// 1/sqrt(a) for a > 0 (normal range): MUFU.RSQ64H seed (2^-22) + two Newton steps, ~1 ulp.
+// The library rsqrt() costs ~300 dependent cycles a call; eight of them sat on the critical
+// path between two exercise dates.
+__device__ __forceinline__ double rsqrt_newton(double a) {
+    double y, h;
+    rsqrt_seed(a, y, h);
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const double e = fma(-(a * y), y, 1.0);      // 1 - a y^2
+        y = fma(h, e, y);                            // y + (y / 2) e
+        h = 0.5 * y;
+    }
+    return y;
+}
+
 template <int DEG>
 __device__ __forceinline__ bool lsmc_solve(const double *gram, double *beta) {
     constexpr int m = DEG + 1;
@@ -90,7 +105,7 @@ __device__ __forceinline__ bool lsmc_solve(const double *gram, double *beta) {
     for (int a = 0; a < m; ++a) {
         double diag = P[2 * a];
         if (!(diag > 0.0)) return false;
-        d[a] = rsqrt(diag);
+        d[a] = rsqrt_newton(diag);
     }
 #pragma unroll
     for (int a = 0; a < m; ++a) {
@@ -104,7 +119,7 @@ __device__ __forceinline__ bool lsmc_solve(const double *gram, double *beta) {
 #pragma unroll
         for (int k = 0; k < j; ++k) s = fma(-L[j][k], L[j][k], s);
         if (!(s > 1e-13)) return false;
-        inv[j] = rsqrt(s);
+        inv[j] = rsqrt_newton(s);
 #pragma unroll
         for (int i = j + 1; i < m; ++i) {
             double t = L[i][j];
@@ -321,13 +336,13 @@ struct LsmcPersistArgs {
     uint4 *peer_rank_slots[OPTMC_MAX_PEERS];
     unsigned int *error;       // set to 1 if an exchange times out
     double *gram;              // [n_steps][OPTMC_LSMC_GRAM], written by block 0
-    unsigned long long *timing;   // optional [n_steps + 1][4] globaltimer stamps of block 0 (ns)
+    unsigned long long *timing;   // optional [n_steps + 1][4] clock64 stamps of block 0 (SM cycles)
 };
 
+// SM cycle counter: block 0 stays on one SM for the whole launch, so differences of its
+// stamps are exact phase durations in SM clocks (%globaltimer only ticks every ~0.26 us).
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
+    return (unsigned long long)clock64();
 }
 
 __device__ __forceinline__ void ll_store(uint4 *slot, double v, uint32_t tag) {

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """GPU experiment: where one exercise date of k_lsmc_persistent spends its time.
-Block 0 stamps %globaltimer at four points per date (see lsmc.cuh); prints the
-median duration of each phase over the dates."""
+Block 0 stamps clock64 at four points per date (see lsmc.cuh); prints the median
+duration of each phase over the dates (SM cycles at 1.965 GHz -> microseconds)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -26,6 +26,6 @@ for n_paths in (1 << 18, 1 << 20, 1 << 22):
     sweep = rows[:, 3] - rows[:, 2]
     nxt = np.r_[rows[1:, 0], t[0, 0]]
     publish = nxt - rows[:, 3]
-    med = lambda a: float(np.median(a)) / 1e3
+    med = lambda a: float(np.median(a)) / 1965.0
     print(f"n_paths {n_paths}: per date [us] poll+sum {med(poll):.2f}  reduce+solve {med(solve):.2f}  "
           f"sweep {med(sweep):.2f}  block_sum+publish {med(publish):.2f}  total {med(poll+solve+sweep+publish):.2f}")
