@@ -68,8 +68,9 @@ class FakeEuropeanEngine:
     def european(self, mdl, sim, strikes, is_call, terminal=None):
         return self._moments(sim, strikes[0], bool(is_call[0]))[None, :]
 
-    def european_async(self, mdl, sim, strikes, is_call, moments, terminal=None):
-        moments[:6] = torch.from_numpy(self._moments(sim, strikes[0], bool(is_call[0])))
+    def european_async(self, mdl, sim, strikes, is_call, moments, terminal=None, aux=None):
+        for j, (k, c) in enumerate(zip(strikes, is_call)):          # strike sweep: 6 per contract
+            moments[6 * j:6 * j + 6] = torch.from_numpy(self._moments(sim, float(k), bool(c)))
 
 
 def _european_worker(rank, world, port, out):
@@ -84,6 +85,40 @@ def _european_worker(rank, world, port, out):
         out[rank] = (price, t.last_stats["n_samples"], t.last_stats["seed"])
     finally:
         dist.destroy_process_group()
+
+
+def _sweep_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        _engine.get_engine = lambda device=None: FakeEuropeanEngine()
+        _engine.make_model = lambda *a, **k: None
+        t = ob.MonteCarloTechnique(n_paths=N_PATHS, n_steps=N_STEPS, seed=11)
+        opts = [ob.Option(k, 1.0, ob.OptionType.CALL if k < 105 else ob.OptionType.PUT)
+                for k in (90.0, 100.0, 110.0)]
+        prices = t.price_many(opts, ob.Stock(100.0, dividend=0.01), ob.HestonModel(), ob.Rate(0.05))
+        out[rank] = (list(map(float, prices)), t.last_stats_many[1]["n_samples"],
+                     t.last_stats_many[0]["seed"])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_strike_sweep_one_allreduce_two_ranks():
+    """price_many under two ranks: every rank sweeps its own draws, ONE all-reduce of all
+    moments, and both ranks hold the whole-job prices."""
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_sweep_worker, args=(world, port, out), nprocs=world, join=True)
+        res = dict(out)
+    (p0, n0, s0), (p1, n1, s1) = res[0], res[1]
+    assert p0 == p1 and s0 == s1 and n0 == n1 == N_PATHS // 2
+    a, b = _job_terminals(s0 % 1000)
+    disc = math.exp(-0.05)
+    want = [disc * np.mean(0.5 * (np.maximum(a - 90, 0) + np.maximum(b - 90, 0))),
+            disc * np.mean(0.5 * (np.maximum(a - 100, 0) + np.maximum(b - 100, 0))),
+            disc * np.mean(0.5 * (np.maximum(110 - a, 0) + np.maximum(110 - b, 0)))]
+    assert p0 == pytest.approx(want, rel=1e-13)
 
 
 def test_european_moments_allreduce_two_ranks():
