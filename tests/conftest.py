@@ -44,3 +44,9 @@ def levy_goldens():
 def dupire_vectors():
     z = np.load(os.path.join(GOLDEN, "dupire_vectors.npz"))
     return z, json.loads(str(z["meta"]))
+
+
+@pytest.fixture(scope="session")
+def american_goldens():
+    with open(os.path.join(GOLDEN, "american_goldens.json")) as f:
+        return json.load(f)

@@ -14,6 +14,7 @@ import untouched.  Nothing here is read at test time except the files written:
     kernel_vectors.npz   inputs + outputs of the 7 terminal and 7 path kernels
     ls_vectors.npz       a path matrix + longstaff_schwartz_pricer outputs
     price_goldens.json   technique.price()/delta/gamma/vega values
+    american_goldens.json  American prices of all seven SDE models (numpy-mode parity)
     levy_goldens.json    single-step models (VG, NIG, CGMY, Hyperbolic, CEV): seeded prices,
                          large-sample prices / quantiles, FFT prices
 
@@ -289,6 +290,35 @@ def levy_goldens():
     return g
 
 
+# ---------------------------------------------------------------- American, all seven models
+def american_goldens():
+    """AmericanMonteCarloTechnique.price for every SDE model (american_monte_carlo.py:52-207),
+    seeded: Generator seed 9 for the increments / counts, numba's global RNG seeded per model
+    for the jump sizes.  Pins rng_mode="numpy" + the fed path kernels + the LS pricer together."""
+    aput = Option(strike=105.0, maturity=0.75, option_type=OptionType.PUT)
+    acall = Option(strike=95.0, maturity=0.75, option_type=OptionType.CALL)
+    stq = Stock(spot=100.0, dividend=0.03)
+    rt = Rate(rate=0.04)
+    models = {
+        "bsm": BSMModel(params={"sigma": 0.25}),
+        "heston": HestonModel(params=HestonModel.default_params),
+        "merton": MertonJumpModel(params=MertonJumpModel.default_params),
+        "bates": BatesModel(params=BatesModel.default_params),
+        "kou": KouModel(params=KouModel.default_params),
+        "sabr": SABRModel(params=SABRModel.default_params),
+        "sabr_jump": SABRJumpModel(params=SABRJumpModel.default_params),
+    }
+    g = {"_toolchain": dict(numpy=np.__version__, numba=numba.__version__)}
+    for name, mdl in models.items():
+        for tag, opt, deg in (("put_deg2", aput, 2), ("call_deg3", acall, 3)):
+            seed_numba(77)
+            t = AmericanMonteCarloTechnique(n_paths=6000, n_steps=15, seed=9, lsm_degree=deg)
+            g[f"{name}_{tag}"] = float(t.price(opt, stq, mdl, rt).price)
+    with open(os.path.join(HERE, "american_goldens.json"), "w") as f:
+        json.dump(g, f, indent=1, sort_keys=True)
+    return g
+
+
 # ---------------------------------------------------------------- Dupire
 def dupire_vectors():
     """dupire_kernel (mc_kernels.py:340-359) cannot be compiled by numba with a Python
@@ -306,6 +336,10 @@ def dupire_vectors():
 
 
 if __name__ == "__main__":
+    if "--american-only" in sys.argv:
+        for k, v in american_goldens().items():
+            print(k, v)
+        raise SystemExit(0)
     if "--dupire-only" in sys.argv:
         print("dupire_vectors.npz:", sorted(dupire_vectors()))
         raise SystemExit(0)
@@ -321,3 +355,5 @@ if __name__ == "__main__":
     for k, v in levy_goldens().items():
         print(k, v)
     print("dupire_vectors.npz:", sorted(dupire_vectors()))
+    for k, v in american_goldens().items():
+        print(k, v)

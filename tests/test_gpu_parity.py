@@ -241,6 +241,21 @@ def test_lsmc_persistent_launch_equals_per_date_launches(eng, n_paths, n_steps, 
         assert got[1] == pytest.approx(want, rel=1e-9)
 
 
+@pytest.mark.parametrize("kind", KINDS)
+def test_american_numpy_mode_all_models(american_goldens, kind):
+    """rng_mode="numpy": fed path kernels + persistent LS pricer reproduce the reference's
+    American price for every SDE model (put degree 2, call degree 3) from the same seeds."""
+    model = MODELS[kind]() if kind != "bsm" else ob.BSMModel({"sigma": 0.25})
+    stock, rate = ob.Stock(spot=100.0, dividend=0.03), ob.Rate(rate=0.04)
+    for tag, K, typ, deg in (("put_deg2", 105.0, ob.OptionType.PUT, 2),
+                             ("call_deg3", 95.0, ob.OptionType.CALL, 3)):
+        np.random.seed(77)
+        t = ob.AmericanMonteCarloTechnique(n_paths=6000, n_steps=15, seed=9, lsm_degree=deg,
+                                           rng_mode="numpy")
+        got = t.price(ob.Option(strike=K, maturity=0.75, option_type=typ), stock, model, rate).price
+        assert got == pytest.approx(american_goldens[f"{kind}_{tag}"], rel=1e-8), (kind, tag)
+
+
 def test_lsmc_high_degree_is_statistically_consistent():
     """degree 5: the reference itself is off by ~3e-3 from the stable solve."""
     rng = np.random.default_rng(11)
