@@ -50,3 +50,9 @@ def dupire_vectors():
 def american_goldens():
     with open(os.path.join(GOLDEN, "american_goldens.json")) as f:
         return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def european_goldens():
+    with open(os.path.join(GOLDEN, "european_goldens.json")) as f:
+        return json.load(f)

@@ -14,6 +14,7 @@ import untouched.  Nothing here is read at test time except the files written:
     kernel_vectors.npz   inputs + outputs of the 7 terminal and 7 path kernels
     ls_vectors.npz       a path matrix + longstaff_schwartz_pricer outputs
     price_goldens.json   technique.price()/delta/gamma/vega values
+    european_goldens.json  European puts of all seven SDE models on ragged shapes
     american_goldens.json  American prices of all seven SDE models (numpy-mode parity)
     levy_goldens.json    single-step models (VG, NIG, CGMY, Hyperbolic, CEV): seeded prices,
                          large-sample prices / quantiles, FFT prices
@@ -290,6 +291,34 @@ def levy_goldens():
     return g
 
 
+# ---------------------------------------------------------------- European, all seven models, ragged
+def european_goldens():
+    """MonteCarloTechnique.price for every SDE model on awkward shapes: a put with a dividend
+    yield, odd n_paths with antithetic (rounded up, monte_carlo.py:58-59) and without."""
+    put = Option(strike=105.0, maturity=0.5, option_type=OptionType.PUT)
+    stq = Stock(spot=100.0, dividend=0.02)
+    rt = Rate(rate=0.03)
+    models = {
+        "bsm": BSMModel(params={"sigma": 0.3}),
+        "heston": HestonModel(params=HestonModel.default_params),
+        "merton": MertonJumpModel(params=MertonJumpModel.default_params),
+        "bates": BatesModel(params=BatesModel.default_params),
+        "kou": KouModel(params=KouModel.default_params),
+        "sabr": SABRModel(params=SABRModel.default_params),
+        "sabr_jump": SABRJumpModel(params=SABRJumpModel.default_params),
+    }
+    g = {"_toolchain": dict(numpy=np.__version__, numba=numba.__version__)}
+    for name, mdl in models.items():
+        for tag, kw in (("anti_7001x13", dict(n_paths=7001, n_steps=13, antithetic=True)),
+                        ("noanti_5001x13", dict(n_paths=5001, n_steps=13, antithetic=False))):
+            seed_numba(55)
+            g[f"{name}_put_{tag}_seed21"] = float(
+                MonteCarloTechnique(seed=21, **kw).price(put, stq, mdl, rt).price)
+    with open(os.path.join(HERE, "european_goldens.json"), "w") as f:
+        json.dump(g, f, indent=1, sort_keys=True)
+    return g
+
+
 # ---------------------------------------------------------------- American, all seven models
 def american_goldens():
     """AmericanMonteCarloTechnique.price for every SDE model (american_monte_carlo.py:52-207),
@@ -336,6 +365,10 @@ def dupire_vectors():
 
 
 if __name__ == "__main__":
+    if "--european-only" in sys.argv:
+        for k, v in european_goldens().items():
+            print(k, v)
+        raise SystemExit(0)
     if "--american-only" in sys.argv:
         for k, v in american_goldens().items():
             print(k, v)
@@ -356,4 +389,6 @@ if __name__ == "__main__":
         print(k, v)
     print("dupire_vectors.npz:", sorted(dupire_vectors()))
     for k, v in american_goldens().items():
+        print(k, v)
+    for k, v in european_goldens().items():
         print(k, v)

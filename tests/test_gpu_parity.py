@@ -242,6 +242,20 @@ def test_lsmc_persistent_launch_equals_per_date_launches(eng, n_paths, n_steps, 
 
 
 @pytest.mark.parametrize("kind", KINDS)
+def test_european_numpy_mode_ragged_all_models(european_goldens, kind):
+    """rng_mode="numpy" on awkward shapes (put, dividend, odd n_paths, with / without antithetic)
+    for every SDE model: the reference's price to 1e-12."""
+    model = MODELS[kind]() if kind != "bsm" else ob.BSMModel({"sigma": 0.3})
+    put = ob.Option(strike=105.0, maturity=0.5, option_type=ob.OptionType.PUT)
+    stock, rate = ob.Stock(spot=100.0, dividend=0.02), ob.Rate(rate=0.03)
+    for tag, n, anti in (("anti_7001x13", 7001, True), ("noanti_5001x13", 5001, False)):
+        np.random.seed(55)
+        t = ob.MonteCarloTechnique(n_paths=n, n_steps=13, antithetic=anti, seed=21, rng_mode="numpy")
+        got = t.price(put, stock, model, rate).price
+        assert got == pytest.approx(european_goldens[f"{kind}_put_{tag}_seed21"], rel=RTOL), (kind, tag)
+
+
+@pytest.mark.parametrize("kind", KINDS)
 def test_american_numpy_mode_all_models(american_goldens, kind):
     """rng_mode="numpy": fed path kernels + persistent LS pricer reproduce the reference's
     American price for every SDE model (put degree 2, call degree 3) from the same seeds."""
