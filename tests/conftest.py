@@ -56,3 +56,9 @@ def american_goldens():
 def european_goldens():
     with open(os.path.join(GOLDEN, "european_goldens.json")) as f:
         return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def greek_goldens():
+    with open(os.path.join(GOLDEN, "greek_goldens.json")) as f:
+        return json.load(f)

@@ -14,6 +14,7 @@ import untouched.  Nothing here is read at test time except the files written:
     kernel_vectors.npz   inputs + outputs of the 7 terminal and 7 path kernels
     ls_vectors.npz       a path matrix + longstaff_schwartz_pricer outputs
     price_goldens.json   technique.price()/delta/gamma/vega values
+    greek_goldens.json   GreekMixin values (European BSM put, Heston call; American put)
     european_goldens.json  European puts of all seven SDE models on ragged shapes
     american_goldens.json  American prices of all seven SDE models (numpy-mode parity)
     levy_goldens.json    single-step models (VG, NIG, CGMY, Hyperbolic, CEV): seeded prices,
@@ -319,6 +320,31 @@ def european_goldens():
     return g
 
 
+# ---------------------------------------------------------------- greeks (GreekMixin on CRN)
+def greek_goldens():
+    """delta / gamma / vega / theta / rho of greek_mixin.py:29-265 for a European BSM put and a
+    Heston call (models without jumps: the re-pricings are reproducible from the Generator
+    alone), and delta / rho of an American put."""
+    put = Option(strike=105.0, maturity=0.5, option_type=OptionType.PUT)
+    call = Option(strike=100.0, maturity=1.0, option_type=OptionType.CALL)
+    stq = Stock(spot=100.0, dividend=0.02)
+    rt = Rate(rate=0.03)
+    g = {"_toolchain": dict(numpy=np.__version__, numba=numba.__version__)}
+    for name, opt, mdl in (("bsm_put", put, BSMModel(params={"sigma": 0.3})),
+                           ("heston_call", call, HestonModel(params=HestonModel.default_params))):
+        t = MonteCarloTechnique(n_paths=8000, n_steps=12, seed=33)
+        for greek in ("delta", "gamma", "vega", "theta", "rho"):
+            v = getattr(t, greek)(opt, stq, mdl, rt)
+            g[f"{name}_{greek}"] = None if np.isnan(v) else float(v)
+    a = AmericanMonteCarloTechnique(n_paths=6000, n_steps=15, seed=9)
+    aput = Option(strike=105.0, maturity=0.75, option_type=OptionType.PUT)
+    for greek in ("delta", "rho"):
+        g[f"american_bsm_put_{greek}"] = float(getattr(a, greek)(aput, stq, BSMModel(params={"sigma": 0.25}), rt))
+    with open(os.path.join(HERE, "greek_goldens.json"), "w") as f:
+        json.dump(g, f, indent=1, sort_keys=True)
+    return g
+
+
 # ---------------------------------------------------------------- American, all seven models
 def american_goldens():
     """AmericanMonteCarloTechnique.price for every SDE model (american_monte_carlo.py:52-207),
@@ -365,6 +391,10 @@ def dupire_vectors():
 
 
 if __name__ == "__main__":
+    if "--greeks-only" in sys.argv:
+        for k, v in greek_goldens().items():
+            print(k, v)
+        raise SystemExit(0)
     if "--european-only" in sys.argv:
         for k, v in european_goldens().items():
             print(k, v)
@@ -391,4 +421,6 @@ if __name__ == "__main__":
     for k, v in american_goldens().items():
         print(k, v)
     for k, v in european_goldens().items():
+        print(k, v)
+    for k, v in greek_goldens().items():
         print(k, v)

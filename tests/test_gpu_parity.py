@@ -174,6 +174,29 @@ def test_numpy_mode_reproduces_reference_greeks(price_goldens):
     assert np.isnan(t.vega(CALL, ST, ob.HestonModel(), RT))
 
 
+def test_numpy_mode_reproduces_all_five_reference_greeks(greek_goldens):
+    """delta / gamma / vega / theta / rho (greek_mixin.py:29-265) of a European BSM put and a
+    Heston call, and delta / rho of an American put, from the reference's seeds."""
+    g = greek_goldens
+    put = ob.Option(strike=105.0, maturity=0.5, option_type=ob.OptionType.PUT)
+    stock, rate = ob.Stock(spot=100.0, dividend=0.02), ob.Rate(rate=0.03)
+    tol = {"delta": 1e-8, "gamma": 1e-4, "vega": 1e-8, "theta": 1e-6, "rho": 1e-8}
+    for name, opt, model in (("bsm_put", put, ob.BSMModel({"sigma": 0.3})),
+                             ("heston_call", CALL, ob.HestonModel())):
+        t = ob.MonteCarloTechnique(n_paths=8000, n_steps=12, seed=33, rng_mode="numpy")
+        for greek, rel in tol.items():
+            got, want = getattr(t, greek)(opt, stock, model, rate), g[f"{name}_{greek}"]
+            if want is None:
+                assert math.isnan(got), (name, greek)
+            else:
+                assert got == pytest.approx(want, rel=rel), (name, greek)
+    a = ob.AmericanMonteCarloTechnique(n_paths=6000, n_steps=15, seed=9, rng_mode="numpy")
+    aput = ob.Option(strike=105.0, maturity=0.75, option_type=ob.OptionType.PUT)
+    for greek in ("delta", "rho"):
+        got = getattr(a, greek)(aput, stock, ob.BSMModel({"sigma": 0.25}), rate)
+        assert got == pytest.approx(g[f"american_bsm_put_{greek}"], rel=1e-6), greek
+
+
 # ------------------------------------------------------------------ LSMC
 @pytest.fixture
 def lsmc_mode(request, eng):
