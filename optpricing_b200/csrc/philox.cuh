@@ -6,9 +6,13 @@
 // materialised: every draw is a pure function of (seed, draw id, step, stream).
 //
 // Philox4x32-10 (Salmon et al., SC'11).  Counter layout used by the engine:
-//   c0, c1 = draw id (64 bit)        c2 = step index       c3 = stream tag
-// Stream tags (c3): 0 = Brownian pair + Poisson word of the step; 0xFF = extra
-//   Poisson bits; (1 + partner) | (jump index << 8) = jump-size draws.
+//   c0, c1 = draw id (64 bit)        c2 = call index       c3 = stream tag
+// Stream tags (c3): 0 = Brownian draws -- packed (philox_pair_words: calls 3g..3g+2
+//   feed pairs 4g..4g+3) where the step loop needs no Poisson word, else one call
+//   per step (three words for the pair, the fourth for the step's Poisson draw);
+//   0xFE = whole-path Poisson draw; 0xFF = extra Poisson bits;
+//   (1 + partner) | (jump index << 8) = jump-size draws; 0x40 = fp32-mode pairs;
+//   0x20.. = single-step samplers (levy.cuh).
 //
 // Instruction budget (B200: the fp64 pipe AND the integer ALU pipe are both
 // half-rate, 16 lanes per SM sub-partition; ncu on the first version of the
@@ -16,8 +20,8 @@
 // resource).  Hence: round keys are expanded once on the host (no per-round key
 // adds), polynomial coefficients live in the constant bank (no UMOV pairs), the
 // uniform's exponent comes from 12 dedicated bits (no 64-bit shifts), and the
-// transcendental parts use two 2 KB shared-memory tables so that each needs
-// only a short polynomial.
+// transcendental parts use shared-memory tables (512 x 16 B for the logarithm,
+// 1024 x 16 or 32 B for the angle) so that each needs only a short polynomial.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
