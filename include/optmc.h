@@ -340,11 +340,13 @@ int optmc_fp64_peak(optmc_ctx *ctx, int64_t iters, double *fma_per_sec, double *
    (optmc_lsmc: 1 = every exercise date in one persistent cooperative launch,
    default; 0 = one optmc_lsmc_step_async launch per date), "lsmc_use_peers"
    (1 = the next optmc_lsmc calls are joint calls of the attached ranks, see
-   optmc_lsmc_peer_attach; 0 = local), "lsmc_timing_ptr" (diagnostics: a device
-   pointer, as an integer, to (n_steps + 1) * 4 uint64 that block 0 of the
-   persistent kernel fills with clock64 stamps per date; 0 = off --
-   tools/lsmc_phases.py). */
+   optmc_lsmc_peer_attach; 0 = local). */
 int optmc_set_int(optmc_ctx *ctx, const char *key, int64_t value);
+
+/* Pointer-valued options: "lsmc_timing" (diagnostics: device memory for
+   (n_steps + 1) * 4 uint64 that block 0 of the persistent Longstaff-Schwartz kernel
+   fills with clock64 stamps per date; NULL = off -- tools/lsmc_phases.py). */
+int optmc_set_ptr(optmc_ctx *ctx, const char *key, void *value);
 
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 int64_t optmc_launch_count(const optmc_ctx *ctx);

@@ -102,6 +102,7 @@ SIGNATURES = [
     ("optmc_normals", c_int, [c_void_p, c_u64, c_i64, c_i32, c_void_p, c_void_p]),
     ("optmc_fp64_peak", c_int, [c_void_p, c_i64, _dp, _dp]),
     ("optmc_set_int", c_int, [c_void_p, ctypes.c_char_p, c_i64]),
+    ("optmc_set_ptr", c_int, [c_void_p, ctypes.c_char_p, c_void_p]),
     ("optmc_launch_count", c_i64, [c_void_p]),
 ]
 
@@ -293,6 +294,10 @@ class Engine:
 
     def set_int(self, key: str, value: int):
         self._check(self.lib.optmc_set_int(self.ctx, key.encode(), int(value)), "optmc_set_int")
+
+    def set_ptr(self, key: str, tensor_or_none):
+        ptr = c_void_p(tensor_or_none.data_ptr()) if tensor_or_none is not None else None
+        self._check(self.lib.optmc_set_ptr(self.ctx, key.encode(), ptr), "optmc_set_ptr")
 
     def launch_count(self) -> int:
         return int(self.lib.optmc_launch_count(self.ctx))

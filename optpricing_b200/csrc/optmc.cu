@@ -160,12 +160,17 @@ extern "C" void optmc_ctx_destroy(optmc_ctx *ctx) {
     delete ctx;
 }
 
-extern "C" int optmc_set_int(optmc_ctx *ctx, const char *key, int64_t value) {
+extern "C" int optmc_set_ptr(optmc_ctx *ctx, const char *key, void *value) {
     if (!ctx || !key) return -2;
-    if (!strcmp(key, "lsmc_timing_ptr")) {     // device buffer of (n_steps + 1) * 4 uint64, or 0
-        ctx->lsmc_timing = reinterpret_cast<unsigned long long *>((uintptr_t)value);
+    if (!strcmp(key, "lsmc_timing")) {         // device buffer of (n_steps + 1) * 4 uint64, or NULL
+        ctx->lsmc_timing = static_cast<unsigned long long *>(value);
         return 0;
     }
+    FAIL(std::string("unknown pointer option ") + key);
+}
+
+extern "C" int optmc_set_int(optmc_ctx *ctx, const char *key, int64_t value) {
+    if (!ctx || !key) return -2;
     if (!strcmp(key, "normals_impl")) {
         if (value != 0 && value != 1) FAIL("normals_impl must be 0 or 1");
         ctx->normals_impl = (int)value;

@@ -15,9 +15,9 @@ for n_paths in (1 << 18, 1 << 20, 1 << 22):
     eng.lsmc_fill_paths(mdl, sim, store, ld)
     tim = torch.zeros((n_steps + 1) * 4, dtype=torch.int64, device=eng.device)
     for rep in range(3):
-        eng.set_int("lsmc_timing_ptr", tim.data_ptr() if rep == 2 else 0)
+        eng.set_ptr("lsmc_timing", tim if rep == 2 else None)
         eng.lsmc(store, ld, n_paths, n_steps, 110.0, False, 0.05, 1.0 / n_steps, degree)
-    eng.set_int("lsmc_timing_ptr", 0)
+    eng.set_ptr("lsmc_timing", None)
     t = tim.cpu().numpy().reshape(n_steps + 1, 4).astype(np.float64)
     # row d+1 holds the stamps of the iteration that sweeps date d; iterations run d = n-1 .. 0
     rows = t[1:n_steps][::-1]            # dates n-2 .. 0 (skip the first: no exchange)
