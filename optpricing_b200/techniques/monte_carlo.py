@@ -28,6 +28,7 @@ Public surface, defaults and error messages follow the reference
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from typing import Any
 
@@ -153,7 +154,8 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
     def __init__(self, *, n_paths: int = 20_000, n_steps: int = 100, antithetic: bool = True,
                  seed: int | None = None, rng_mode: str = "philox",
                  correlation: str = "reference", control_variate: bool = False,
-                 distributed: bool | None = None, precision: str = "fp64"):
+                 distributed: bool | None = None, precision: str = "fp64",
+                 steps_per_year: int | None = None):
         if antithetic and n_paths % 2 != 0:
             n_paths += 1                       # monte_carlo.py:58-59
         if rng_mode not in ("philox", "numpy"):
@@ -173,11 +175,35 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
         self.control_variate = control_variate
         self.distributed = distributed
         self.precision = precision
+        self.steps_per_year = steps_per_year
         self.last_stats: dict = {}
         self._hint = None
 
+    @contextlib.contextmanager
+    def _steps_for(self, T: float):
+        """``steps_per_year`` (optional): the time grid follows the maturity,
+        n_steps = round(steps_per_year * T) -- BASELINE config 3's "n_steps = 252 T" --
+        so one technique prices a strike x maturity grid in ONE ``price_many`` call.
+        Without it ``n_steps`` is the reference's fixed count."""
+        if self.steps_per_year is None:
+            yield self.n_steps
+            return
+        saved = self.n_steps
+        self.n_steps = max(1, int(round(self.steps_per_year * T)))
+        try:
+            yield self.n_steps
+        finally:
+            self.n_steps = saved
+
     # ------------------------------------------------------------------ price
     def price(self, option, stock, model, rate, **kwargs: Any):
+        """``technique.price(option, stock, model, rate) -> PricingResult`` (monte_carlo.py:65-116)."""
+        if self.steps_per_year is not None and not isinstance(option, (list, tuple, np.ndarray)):
+            with self._steps_for(option.maturity):
+                return self._price_one(option, stock, model, rate, **kwargs)
+        return self._price_one(option, stock, model, rate, **kwargs)
+
+    def _price_one(self, option, stock, model, rate, **kwargs: Any):
         """
         Price one option -> PricingResult (monte_carlo.py:65-116).  A list / tuple /
         array of options (the ``Option | np.ndarray`` the reference's ABC hints at,
@@ -411,18 +437,19 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
         for T, idx in by_T.items():
             r = rate.get_rate(T)
             out = dev[pos * _engine.NMOM:(pos + len(idx)) * _engine.NMOM]
-            kind, seed, k = self._sweep_async(
-                model, S0, r, q, T, [options[i].strike for i in idx],
-                [1 if _is_call(options[i]) else 0 for i in idx], out, **kwargs)
-            jobs.append((T, r, idx, pos, kind, seed))
+            with self._steps_for(T) as steps:
+                kind, seed, k = self._sweep_async(
+                    model, S0, r, q, T, [options[i].strike for i in idx],
+                    [1 if _is_call(options[i]) else 0 for i in idx], out, **kwargs)
+            jobs.append((T, r, idx, pos, kind, seed, steps))
             keep.append(k)
             pos += len(idx)
         _, _, all_reduce = self._group()
         if all_reduce is not None:
             all_reduce(dev[: total * _engine.NMOM])
         mom_all = dev[: total * _engine.NMOM].cpu().numpy().reshape(total, _engine.NMOM)
-        for T, r, idx, pos, kind, seed in jobs:
-            c_mean = control_mean(kind, model.params, S0, r, q, T, self.n_steps)
+        for T, r, idx, pos, kind, seed, steps in jobs:
+            c_mean = control_mean(kind, model.params, S0, r, q, T, steps)
             block = mom_all[pos:pos + len(idx)]
             prices[idx] = prices_from_moments(block, r, T, c_mean, self.control_variate)
             for row, i in zip(block, idx):

@@ -826,3 +826,25 @@ def test_implied_volatility_from_one_simulation(price_goldens):
                                  target_price=price_goldens["G1_closed_form"]) == iv
     # an unreachable target has no root: NaN as in the reference (iv_mixin.py:81-116)
     assert math.isnan(t.implied_volatility(CALL, ST, ob.BSMModel(), RT, target_price=1e9))
+
+
+def test_steps_per_year_follows_the_maturity():
+    """steps_per_year=48: a 0.5-year option is priced on 24 steps, a 2-year one on 96, and one
+    price_many call over both maturities equals separate fixed-grid techniques (same seeds)."""
+    model = ob.HestonModel()
+    o_short = ob.Option(strike=100.0, maturity=0.5, option_type=ob.OptionType.CALL)
+    o_long = ob.Option(strike=95.0, maturity=2.0, option_type=ob.OptionType.PUT)
+    a = ob.MonteCarloTechnique(n_paths=1 << 16, steps_per_year=48, seed=4)
+    b = ob.MonteCarloTechnique(n_paths=1 << 16, n_steps=24, seed=4)
+    assert a.price(o_short, STQ, model, RT).price == b.price(o_short, STQ, model, RT).price
+    assert a.n_steps == 100                                   # the ctor default is untouched
+    many = ob.MonteCarloTechnique(n_paths=1 << 16, steps_per_year=48, seed=4).price_many(
+        [o_short, o_long], STQ, model, RT)
+    s1 = ob.MonteCarloTechnique(n_paths=1 << 16, n_steps=24, seed=4)
+    want_short = s1.price_many([o_short], STQ, model, RT)[0]
+    # the second maturity draws the technique's second seed: replay it on a 96-step grid
+    s2 = ob.MonteCarloTechnique(n_paths=1 << 16, n_steps=96, seed=4)
+    s2.rng.integers(0, 2**63 - 1, dtype=np.int64)
+    want_long = s2.price_many([o_long], STQ, model, RT)[0]
+    assert many[0] == pytest.approx(want_short, rel=1e-12)
+    assert many[1] == pytest.approx(want_long, rel=1e-12)
