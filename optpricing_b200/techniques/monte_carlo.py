@@ -21,6 +21,8 @@ Public surface, defaults and error messages follow the reference
   mc_kernels.py:67); ``"independent"`` gives corr(dW_S, dW_v) = rho.
 * ``precision="fp32"`` (optional, device RNG only): the step loop in single
   precision on the fp32 pipe, the per-path finish and the moments in fp64.
+* ``report_stats=True`` puts the standard error, a 95 % interval and the sample
+  count of the estimate into ``PricingResult.greeks`` (``last_stats`` always has them).
 * ``control_variate=True`` adds the discounted-terminal-spot control, whose mean
   under the simulated discrete scheme is known in closed form.
 * Under an initialised ``torch.distributed`` group the draws are partitioned by
@@ -155,7 +157,7 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
                  seed: int | None = None, rng_mode: str = "philox",
                  correlation: str = "reference", control_variate: bool = False,
                  distributed: bool | None = None, precision: str = "fp64",
-                 steps_per_year: int | None = None):
+                 steps_per_year: int | None = None, report_stats: bool = False):
         if antithetic and n_paths % 2 != 0:
             n_paths += 1                       # monte_carlo.py:58-59
         if rng_mode not in ("philox", "numpy"):
@@ -176,6 +178,7 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
         self.distributed = distributed
         self.precision = precision
         self.steps_per_year = steps_per_year
+        self.report_stats = report_stats
         self.last_stats: dict = {}
         self._hint = None
 
@@ -244,7 +247,13 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
             stats["seed"] = ST.seed
             self.last_stats = stats
             use_cv = self.control_variate and "cv_price" in stats and math.isfinite(c_mean)
-            return PricingResult(price=float(stats["cv_price"] if use_cv else stats["price"]))
+            price = float(stats["cv_price"] if use_cv else stats["price"])
+            if self.report_stats:       # the Monte Carlo error travels with the price
+                se = float(stats["cv_stderr"] if use_cv else stats["stderr"])
+                return PricingResult(price=price, greeks={
+                    "stderr": se, "ci95_low": price - 1.959963984540054 * se,
+                    "ci95_high": price + 1.959963984540054 * se, "n_samples": stats["n_samples"]})
+            return PricingResult(price=price)
 
         payoff = np.maximum(ST - K, 0) if call else np.maximum(K - ST, 0)
         self.last_stats = {"n_samples": float(np.size(payoff))}

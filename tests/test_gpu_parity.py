@@ -848,3 +848,14 @@ def test_steps_per_year_follows_the_maturity():
     want_long = s2.price_many([o_long], STQ, model, RT)[0]
     assert many[0] == pytest.approx(want_short, rel=1e-12)
     assert many[1] == pytest.approx(want_long, rel=1e-12)
+
+
+def test_report_stats_travel_with_the_price(price_goldens):
+    t = ob.MonteCarloTechnique(n_paths=1 << 20, n_steps=8, seed=2, report_stats=True)
+    res = t.price(CALL, ST, ob.BSMModel({"sigma": 0.2}), RT)
+    g = res.greeks
+    assert g["n_samples"] == (1 << 19) and 0 < g["stderr"] < 0.02
+    assert g["ci95_low"] < res.price < g["ci95_high"]
+    assert abs(res.price - price_goldens["G1_closed_form"]) < 4 * g["stderr"]
+    assert ob.MonteCarloTechnique(n_paths=1 << 12, n_steps=4, seed=2).price(
+        CALL, ST, ob.BSMModel(), RT).greeks == {}                     # default: the reference's result
