@@ -109,7 +109,7 @@ def test_fed_kernels_match_reference_vectors(kernel_vectors, case, kind):
 
 
 @pytest.mark.parametrize("kind", KINDS)
-@pytest.mark.parametrize("shape", ((1, 1), (63, 31), (65, 33), (1000, 70)))
+@pytest.mark.parametrize("shape", ((1, 1), (63, 31), (65, 33), (1000, 70), (200003, 37)))
 def test_fed_kernels_match_oracle_ragged_shapes(kernel_vectors, kind, shape):
     """Tile edges: path counts and step counts around the 64 x 32 staging tile."""
     _, meta = kernel_vectors
