@@ -1,4 +1,4 @@
-import sys, time, math
+import sys, time
 import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import optpricing_b200 as ob

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """GPU experiment: time the C2 Heston kernel over launch geometries (and library
 variants given as OPTMC_LIB).  Prints ms per 2^24 x 252 pricing and path-steps/s."""
-import os, sys, time
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from optpricing_b200 import _engine
