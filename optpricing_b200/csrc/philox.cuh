@@ -48,9 +48,12 @@ inline void philox_expand_key(uint64_t seed, PhiloxKey *k) {
     }
 }
 
+#ifndef OPTMC_PHILOX_ROUNDS
+#define OPTMC_PHILOX_ROUNDS 10      // experiments only (tools/): the engine ships Philox4x32-10
+#endif
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKey &k) {
 #pragma unroll
-    for (int i = 0; i < 10; ++i) {
+    for (int i = 0; i < OPTMC_PHILOX_ROUNDS; ++i) {
         uint32_t hi0 = __umulhi(PHILOX_M0, c.x), lo0 = PHILOX_M0 * c.x;
         uint32_t hi1 = __umulhi(PHILOX_M1, c.z), lo1 = PHILOX_M1 * c.z;
         c = make_uint4(hi1 ^ c.y ^ k.k0[i], lo1, hi0 ^ c.w ^ k.k1[i], lo0);
