@@ -474,6 +474,36 @@ def test_american_philox_all_models_run(kind):
     assert am > eu - 0.05 and am < eu + 5.0     # early-exercise premium is non-negative
 
 
+@pytest.mark.parametrize("kind", ("merton", "bates", "kou", "sabr_jump", "heston"))
+def test_philox_path_store_law(kind):
+    """The device-RNG path kernels, date by date: the scheme's martingale mean at EVERY exercise
+    date (jump timing and compensation), the antithetic layout, and the terminal column's
+    put price against the oracle's path kernel within 3 combined standard errors."""
+    from optpricing_b200.techniques.monte_carlo import control_mean
+    model = MODELS[kind]()
+    n, m, T, r, q = 1 << 19, 16, 1.0, 0.05, 0.01
+    t = ob.AmericanMonteCarloTechnique(n_paths=n, n_steps=m, seed=14)
+    opt = ob.Option(strike=105.0, maturity=T, option_type=ob.OptionType.PUT)
+    paths = np.asarray(t._simulate_full_sde_paths(opt, STQ, model, RT))
+    assert paths.shape == (n, m + 1) and np.all(paths[:, 0] == 100.0)
+    pair = 0.5 * (paths[: n // 2] + paths[n // 2:])
+    for i in (1, 2, m // 2, m):
+        want = control_mean(kind, model.params, 100.0, r, q, T * i / m, i)
+        se = pair[:, i].std(ddof=1) / math.sqrt(n // 2)
+        assert abs(pair[:, i].mean() - want) < 4.5 * se, (kind, i, pair[:, i].mean(), want, se)
+    pay = np.maximum(105.0 - paths[:, m], 0)
+    got, se_g = pay.mean(), 0.5 * (pay[: n // 2] + pay[n // 2:]).std(ddof=1) / math.sqrt(n // 2)
+    ref = orc.simulate_paths(kind, model.params, 100.0, r, q, T, 200_000, m, True,
+                             np.random.default_rng(3), np.random.RandomState(4))
+    pr = np.maximum(105.0 - ref[:, m], 0)
+    se_r = 0.5 * (pr[:100_000] + pr[100_000:]).std(ddof=1) / math.sqrt(100_000)
+    assert abs(got - pr.mean()) < 3 * math.hypot(se_g, se_r), (kind, got, pr.mean())
+    # second moment of the log-return at the first date: the jump sizes' law
+    lr = np.log(paths[:, 1] / 100.0)
+    lr_ref = np.log(ref[:, 1] / 100.0)
+    assert lr.var() == pytest.approx(lr_ref.var(), rel=0.05)
+
+
 # ------------------------------------------------------------------ batched contracts, fused greeks
 def test_price_many_equals_single_prices():
     """One simulation per maturity; each price equals price() on the same Philox key."""
