@@ -19,6 +19,7 @@ namespace optmc {
 #endif
 
 constexpr int EURO_THREADS = 256;
+constexpr int SCHED_SLOTS = 8;    // scheduled jump steps a path keeps in registers
 #ifndef OPTMC_EURO_MIN_BLOCKS
 #define OPTMC_EURO_MIN_BLOCKS 3   // resident 256-thread blocks per SM the register budget is
                                   // sized for (85 regs): no constant reloads in the step loop
@@ -37,6 +38,7 @@ struct EuroArgs {
     double pois_mu[2], pois_p0[2];
     uint32_t pois_p0_bits[2];
     double pois_mu_path, pois_p0_path;   // lambda T and exp(-lambda T): whole-path jump count
+    uint32_t pois_p0_path_bits;          // floor(exp(-lambda T) 2^32)
     double *partials;   // [gridDim.x][NPART]
     double *terminal;   // optional [n_local * (anti ? 2 : 1)]
     double *aux;        // optional, one-factor log models: [W | J | J partner], n_local each
@@ -93,7 +95,19 @@ __device__ __forceinline__ double2 jumps_slow(uint32_t w, double mu, double p0, 
 
 // Simulate one draw over all steps.  SINK(step_index, sa, sb) is called after
 // every completed step when PER_STEP (LSMC path store), never otherwise.
-template <int KIND, bool ANTI, int NIMPL, bool PER_STEP, class Sink>
+//
+// SCHED (path kernels of the jump models, whose jumps must act inside the step loop; the
+// European SABR-jump kernel could use it too but measured no faster): instead of one
+// Poisson(lambda dt) draw per step, the path draws
+// N ~ Poisson(lambda T) once and the N step indices floor(U n_steps) -- the arrival
+// times of a Poisson process given their number are iid uniform, so the per-step counts
+// have exactly the law of the reference's independent Poisson(lambda dt) draws
+// (monte_carlo.py:238-240).  The step loop then needs no Poisson word (the packed
+// Philox layout applies, one-factor path kernels use both normals of a pair) and the
+// divergent jump branch costs one integer compare per step.  Up to eight indices are
+// kept sorted in four registers; a path with more jumps (P = 2e-4 at lambda T = 2)
+// recomputes its indices at every step.  The host selects SCHED while lambda T <= 2.
+template <int KIND, bool ANTI, int NIMPL, bool PER_STEP, bool SCHED, class Sink>
 __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, State &sa, State &sb,
                                               RngView tab, Sink &&sink) {
     const Consts &c = A.c;
@@ -105,8 +119,11 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
     // the whole jump contribution to log S_T is drawn once after the last step --
     // the same law as the reference's per-step draws, without a divergent branch
     // inside the step loop.  SABR-jump (jumps act on S between Euler steps) and the
-    // path kernels keep the per-step form.
+    // path kernels keep jumps inside the loop.
     constexpr bool JUMPS_AT_END = JUMPS && !PER_STEP && KIND != OPTMC_SABR_JUMP;
+    constexpr bool STEP_JUMPS = JUMPS && !JUMPS_AT_END;
+    constexpr bool SCHEDULED = STEP_JUMPS && SCHED;       // pre-drawn jump schedule
+    constexpr bool LEGACY = STEP_JUMPS && !SCHED;         // one Poisson word per step
     // terminal-only kernels of the log models defer the deterministic drift
     constexpr bool DEFER = !PER_STEP && !kind_sabr(KIND) && KIND != OPTMC_DUPIRE;
     // SABR kinds with the hand-written maths: log-vol form, one exponential per step
@@ -114,10 +131,75 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
     init_state<KIND, DEFER, LOGV>(sa, c);
     init_state<KIND, DEFER, LOGV>(sb, c);
     // A Box-Muller pair feeds one step of a two-factor model, or two consecutive
-    // steps of a one-factor model.  The path kernels of the jump models keep one
-    // step per Philox call: every step needs its own Poisson word.
-    constexpr int SPC = (TWO || (PER_STEP && JUMPS)) ? 1 : 2;
+    // steps of a one-factor model (one step when every step needs its own Poisson word).
+    constexpr int SPC = (TWO || LEGACY) ? 1 : 2;
     const uint32_t id_lo = keep_u32((uint32_t)id), id_hi = keep_u32((uint32_t)(id >> 32));
+
+    // ---- jump schedule -------------------------------------------------------------
+    int n_j = 0, k_j = 0;                       // jumps of this path, ordinal of the next one
+    uint32_t sch[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};   // 8 sorted 16-bit step indices
+    auto sched_index = [&](int j) -> uint32_t {
+        const uint4 u = philox4x32_10(make_uint4(id_lo, id_hi, 0xFFFFFFFCu, (uint32_t)j), A.key);
+        return __umulhi(u.x, (uint32_t)A.n_steps);          // floor(U n_steps)
+    };
+    if constexpr (SCHEDULED) {
+        const uint4 e = philox4x32_10(make_uint4(id_lo, id_hi, 0xFFFFFFFFu, 0xFEu), A.key);
+        if (__builtin_expect(poisson_maybe(e.x, A.pois_p0_path_bits), 0)) {
+            const uint4 x = philox4x32_10(make_uint4(id_lo, id_hi, 0xFFFFFFFFu, 0xFFu), A.key);
+            n_j = poisson_slow(e.x, x.x, A.pois_mu_path, A.pois_p0_path);
+            if (n_j <= SCHED_SLOTS) {
+                // insertion sort of the n_j indices into 8 ascending 16-bit slots (0xFFFF = none)
+                uint32_t v[SCHED_SLOTS];
+#pragma unroll
+                for (int j = 0; j < SCHED_SLOTS; ++j) v[j] = 0xFFFFu;
+                for (int j = 0; j < n_j; ++j) {
+                    uint32_t x = sched_index(j);
+#pragma unroll
+                    for (int q = 0; q < SCHED_SLOTS; ++q) {        // bubble x through the sorted prefix
+                        const uint32_t lo = min(v[q], x);
+                        x = max(v[q], x);
+                        v[q] = lo;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) sch[q] = v[2 * q] | (v[2 * q + 1] << 16);
+            }
+        }
+    }
+    auto one_jump = [&](int ordinal) {
+        // sizes: fresh draws for the partner, as in the reference's second pass
+        const double Ja = jump_size<KIND, NIMPL>(
+            philox4x32_10(make_uint4(id_lo, id_hi, 0xFFFFFFFDu, 1u | ((uint32_t)ordinal << 8)), A.key),
+            c, tab);
+        apply_jump<KIND, DEFER>(sa, Ja);
+        if constexpr (ANTI) {
+            const double Jb = jump_size<KIND, NIMPL>(
+                philox4x32_10(make_uint4(id_lo, id_hi, 0xFFFFFFFDu, 2u | ((uint32_t)ordinal << 8)),
+                              A.key), c, tab);
+            apply_jump<KIND, DEFER>(sb, Jb);
+        }
+    };
+    // after the diffusion part of step i: scheduled jumps of that step, then the sink
+    auto after_step = [&](int i) {
+        if constexpr (SCHEDULED) {
+            if (__builtin_expect(n_j != 0, 0)) {
+                if (n_j <= SCHED_SLOTS) {
+                    while ((sch[0] & 0xFFFFu) == (uint32_t)i) {
+                        one_jump(k_j++);
+                        sch[0] = (sch[0] >> 16) | (sch[1] << 16);
+                        sch[1] = (sch[1] >> 16) | (sch[2] << 16);
+                        sch[2] = (sch[2] >> 16) | (sch[3] << 16);
+                        sch[3] = (sch[3] >> 16) | 0xFFFF0000u;
+                    }
+                } else {
+                    for (int j = 0; j < n_j; ++j)
+                        if (sched_index(j) == (uint32_t)i) one_jump(j);
+                }
+            }
+        }
+        if constexpr (PER_STEP) sink(i, sa, sb);
+    };
+
     // One Box-Muller pair (three Philox words: 64 bits of radius, 32 of angle) and the
     // SPC steps it feeds, starting at step i.
     auto advance = [&](uint32_t w0, uint32_t w1, uint32_t w2, int i) {
@@ -140,68 +222,81 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
         if constexpr (TWO) {
             step_diffusion<KIND, DEFER, LOGV>(sa, z1, z2, c, tab, i);
             if constexpr (ANTI) step_diffusion<KIND, DEFER, LOGV>(sb, -z1, -z2, c, tab, i);
+            if constexpr (!LEGACY) after_step(i);
         } else {
             step_diffusion<KIND, DEFER>(sa, z1, 0.0, c, tab, i);
             if constexpr (ANTI) step_diffusion<KIND, DEFER>(sb, -z1, 0.0, c, tab, i);
+            if constexpr (!LEGACY) after_step(i);
             if constexpr (SPC == 2) {
-                if constexpr (PER_STEP) sink(i, sa, sb);
                 if (i + 1 < A.n_steps) {
                     step_diffusion<KIND, DEFER>(sa, z2, 0.0, c, tab, i + 1);
                     if constexpr (ANTI) step_diffusion<KIND, DEFER>(sb, -z2, 0.0, c, tab, i + 1);
-                    if constexpr (PER_STEP) sink(i + 1, sa, sb);
+                    after_step(i + 1);
                 }
             }
         }
     };
-    // Kinds whose step loop needs no Poisson word use all 128 bits of a Philox call:
+    // Without a Poisson word per step all 128 bits of a Philox call are used:
     // three calls (c2 = 3g, 3g+1, 3g+2) feed four pairs, see philox_pair_words.
-    constexpr bool PACKED = !(JUMPS && !JUMPS_AT_END);
-    if constexpr (PACKED) {
+    if constexpr (SCHEDULED) {
+        // one copy of the step body (it carries the inlined jump code): the twelve words of
+        // three calls are handed out pair by pair
+        uint32_t call = 0;
+        uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a, d = a;
+        int slot = 0;
+#pragma unroll 1
+        for (int i = 0; i < A.n_steps; i += SPC, slot = (slot + 1) & 3) {
+            uint32_t w0, w1, w2;
+            if (slot == 0) {
+                a = philox4x32_10(make_uint4(id_lo, id_hi, call, 0u), A.key);
+                w0 = a.x; w1 = a.y; w2 = a.z;
+            } else if (slot == 1) {
+                b = philox4x32_10(make_uint4(id_lo, id_hi, call + 1u, 0u), A.key);
+                w0 = a.w; w1 = b.x; w2 = b.y;
+            } else if (slot == 2) {
+                d = philox4x32_10(make_uint4(id_lo, id_hi, call + 2u, 0u), A.key);
+                w0 = b.z; w1 = b.w; w2 = d.x;
+            } else {
+                w0 = d.y; w1 = d.z; w2 = d.w;
+                call += 3;
+            }
+            advance(w0, w1, w2, i);
+        }
+    } else if constexpr (!LEGACY) {
         uint32_t call = 0;
         OPTMC_UNROLL_STEPS
         for (int i = 0; i < A.n_steps; i += 4 * SPC, call += 3) {
             const uint4 a = philox4x32_10(make_uint4(id_lo, id_hi, call, 0u), A.key);
             advance(a.x, a.y, a.z, i);
-            if constexpr (PER_STEP && SPC == 1) sink(i, sa, sb);
             if (i + SPC < A.n_steps) {
                 const uint4 b = philox4x32_10(make_uint4(id_lo, id_hi, call + 1u, 0u), A.key);
                 advance(a.w, b.x, b.y, i + SPC);
-                if constexpr (PER_STEP && SPC == 1) sink(i + SPC, sa, sb);
                 if (i + 2 * SPC < A.n_steps) {
                     const uint4 d = philox4x32_10(make_uint4(id_lo, id_hi, call + 2u, 0u), A.key);
                     advance(b.z, b.w, d.x, i + 2 * SPC);
-                    if constexpr (PER_STEP && SPC == 1) sink(i + 2 * SPC, sa, sb);
-                    if (i + 3 * SPC < A.n_steps) {
-                        advance(d.y, d.z, d.w, i + 3 * SPC);
-                        if constexpr (PER_STEP && SPC == 1) sink(i + 3 * SPC, sa, sb);
-                    }
+                    if (i + 3 * SPC < A.n_steps) advance(d.y, d.z, d.w, i + 3 * SPC);
                 }
             }
         }
     } else {
         OPTMC_UNROLL_STEPS
-        for (int i = 0; i < A.n_steps; i += SPC) {
+        for (int i = 0; i < A.n_steps; ++i) {
             const uint4 w = philox4x32_10(make_uint4(id_lo, id_hi, (uint32_t)i, 0u), A.key);
             advance(w.x, w.y, w.z, i);
-            // One Poisson draw for the steps this iteration covered; for the
-            // additive-in-log one-factor models the split between the two
-            // steps does not affect S_T.
-            const bool two = (SPC == 2 && i + 1 < A.n_steps);
-            if (__builtin_expect(poisson_maybe(w.w, two ? A.pois_p0_bits[1] : A.pois_p0_bits[0]), 0)) {
-                double2 J = jumps_slow<KIND, ANTI, NIMPL>(w.w, two ? A.pois_mu[1] : A.pois_mu[0],
-                                                          two ? A.pois_p0[1] : A.pois_p0[0], A.key,
+            if (__builtin_expect(poisson_maybe(w.w, A.pois_p0_bits[0]), 0)) {
+                double2 J = jumps_slow<KIND, ANTI, NIMPL>(w.w, A.pois_mu[0], A.pois_p0[0], A.key,
                                                           id_lo, id_hi, (uint32_t)i, c, tab);
                 // additive in log space (mc_kernels.py:115,174,323); multiplicative on S for
                 // SABR-jump (:274): the product of exp(J_j) is exp of the sum
                 apply_jump<KIND, DEFER>(sa, J.x);
                 if constexpr (ANTI) apply_jump<KIND, DEFER>(sb, J.y);
             }
-            if constexpr (PER_STEP && SPC == 1) sink(i, sa, sb);
+            if constexpr (PER_STEP) sink(i, sa, sb);
         }
     }
     if constexpr (JUMPS_AT_END) {
         uint4 e = philox4x32_10(make_uint4(id_lo, id_hi, 0xFFFFFFFFu, 0xFEu), A.key);
-        if (poisson_maybe(e.x, (uint32_t)fmin(floor(A.pois_p0_path * 4294967296.0), 4294967295.0))) {
+        if (poisson_maybe(e.x, A.pois_p0_path_bits)) {
             double2 J = jumps_slow<KIND, ANTI, NIMPL>(e.x, A.pois_mu_path, A.pois_p0_path, A.key,
                                                       id_lo, id_hi, 0xFFFFFFFFu, c, tab);
             apply_jump<KIND, DEFER>(sa, J.x);
@@ -216,7 +311,7 @@ struct NoSink {
     __device__ __forceinline__ void operator()(int, const State &, const State &) const {}
 };
 
-template <int KIND, bool ANTI, int NIMPL>
+template <int KIND, bool ANTI, int NIMPL, bool SCHED = false>
 __global__ void __launch_bounds__(EURO_THREADS, OPTMC_EURO_MIN_BLOCKS) k_european(const EuroArgs A) {
     __shared__ RngShared<kind_two_factor(KIND)> tab;
     RngView tv{0u};
@@ -228,8 +323,8 @@ __global__ void __launch_bounds__(EURO_THREADS, OPTMC_EURO_MIN_BLOCKS) k_europea
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < A.n_local; g += stride) {
         State sa, sb;
-        simulate_draw<KIND, ANTI, NIMPL, false>(A, (uint64_t)(A.draw_offset + g), sa, sb, tv,
-                                                NoSink{});
+        simulate_draw<KIND, ANTI, NIMPL, false, SCHED>(A, (uint64_t)(A.draw_offset + g), sa, sb, tv,
+                                                       NoSink{});
         if constexpr (!kind_two_factor(KIND) && KIND != OPTMC_DUPIRE) {
             // log S_T = log S_0 + n drift(sigma) + sigma W + J: W and J do not depend on sigma,
             // so sigma-bumped prices (vega) can be read off this one simulation

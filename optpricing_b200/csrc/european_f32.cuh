@@ -134,8 +134,7 @@ __global__ void __launch_bounds__(EURO_THREADS, 4) k_european_f32(const EuroArgs
             double ja = 0.0, jb = 0.0;
             if constexpr (JUMPS) {                               // whole-path jump draw (european.cuh)
                 uint4 e = philox4x32_10(make_uint4(id_lo, id_hi, 0xFFFFFFFFu, 0xFEu), A.key);
-                if (poisson_maybe(e.x, (uint32_t)fmin(floor(A.pois_p0_path * 4294967296.0),
-                                                      4294967295.0))) {
+                if (poisson_maybe(e.x, A.pois_p0_path_bits)) {
                     double2 J = jumps_slow<KIND, ANTI>(e.x, A.pois_mu_path, A.pois_p0_path, A.key,
                                                        id_lo, id_hi, 0xFFFFFFFFu, c);
                     ja = J.x;

@@ -26,6 +26,7 @@ struct optmc_ctx {
     int euro_blocks_per_sm = 0; // 0: occupancy API decides
     int euro_threads = EURO_THREADS;
     int lsmc_mode = 1;          // 1: one persistent launch for all dates, 0: one launch per date
+    int jump_schedule = 1;      // 1: pre-drawn jump schedule where it applies, 0: Poisson word per step
     int64_t launches = 0;
     unsigned char *scratch = nullptr;  // device
     size_t scratch_bytes = 0;
@@ -180,6 +181,9 @@ extern "C" int optmc_set_int(optmc_ctx *ctx, const char *key, int64_t value) {
     } else if (!strcmp(key, "euro_threads")) {
         if (value != 64 && value != 128 && value != 256) FAIL("euro_threads must be 64, 128 or 256");
         ctx->euro_threads = (int)value;
+    } else if (!strcmp(key, "jump_schedule")) {
+        if (value != 0 && value != 1) FAIL("jump_schedule must be 0 or 1");
+        ctx->jump_schedule = (int)value;
     } else if (!strcmp(key, "lsmc_use_peers")) {
         if (value != 0 && value != 1) FAIL("lsmc_use_peers must be 0 or 1");
         if (value == 1 && ctx->peer_world < 2) FAIL("no peers attached (optmc_lsmc_peer_attach)");
@@ -282,6 +286,8 @@ static int make_consts(optmc_ctx *ctx, const optmc_model *m, double x0, double d
 static void poisson_consts(EuroArgs &A) {
     A.pois_mu_path = A.c.lam_dt * A.n_steps;
     A.pois_p0_path = std::exp(-A.pois_mu_path);
+    A.pois_p0_path_bits =
+        (uint32_t)std::min(std::floor(A.pois_p0_path * 4294967296.0), 4294967295.0);
     for (int two = 0; two < 2; ++two) {
         double mu = A.c.lam_dt * (two + 1);
         double p0 = std::exp(-mu);
@@ -330,9 +336,16 @@ static int euro_grid(optmc_ctx *ctx, K kernel, int64_t n_local) {
         default: FAIL("unknown model kind");                   \
     }
 
-template <int KIND, bool ANTI, int NIMPL>
+// Path kernels of the jump models: jumps from a pre-drawn schedule (european.cuh) while lambda T
+// is small enough for eight register slots to hold nearly every path's jumps, else a Poisson
+// word per step.
+static bool use_jump_schedule(const EuroArgs &A) {
+    return A.pois_mu_path <= 2.0 && A.n_steps < 65535;
+}
+
+template <int KIND, bool ANTI, int NIMPL, bool SCHED = false>
 static int launch_euro_t(optmc_ctx *ctx, EuroArgs &A, cudaStream_t st, int *grid_out) {
-    auto kern = k_european<KIND, ANTI, NIMPL>;
+    auto kern = k_european<KIND, ANTI, NIMPL, SCHED>;
     int grid = euro_grid(ctx, kern, A.n_local);
     kern<<<grid, ctx->euro_threads, 0, st>>>(A);
     ctx->launches++;
@@ -343,6 +356,9 @@ static int launch_euro_t(optmc_ctx *ctx, EuroArgs &A, cudaStream_t st, int *grid
 
 template <int KIND>
 static int launch_euro_k(optmc_ctx *ctx, EuroArgs &A, bool anti, cudaStream_t st, int *grid) {
+    // (the European SABR-jump kernel keeps one Poisson word per step: with the schedule its
+    // four-fold unrolled step body carries four copies of the jump code and measured 21 %
+    // slower, a single-copy loop no faster than the per-step form)
     if (ctx->normals_impl == 0)
         return anti ? launch_euro_t<KIND, true, 0>(ctx, A, st, grid)
                     : launch_euro_t<KIND, false, 0>(ctx, A, st, grid);
@@ -724,9 +740,9 @@ extern "C" int optmc_fed_async(optmc_ctx *ctx, const optmc_model *model, double 
 // ---------------------------------------------------------------------------
 // Longstaff-Schwartz
 // ---------------------------------------------------------------------------
-template <int KIND, bool ANTI, int NIMPL>
+template <int KIND, bool ANTI, int NIMPL, bool SCHED = false>
 static int launch_paths_t(optmc_ctx *ctx, EuroArgs &A, double *store, int64_t ld, cudaStream_t st) {
-    auto kern = k_lsmc_paths<KIND, ANTI, NIMPL>;
+    auto kern = k_lsmc_paths<KIND, ANTI, NIMPL, SCHED>;
     int per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EURO_THREADS, 0) != cudaSuccess ||
         per_sm < 1)
@@ -742,6 +758,15 @@ static int launch_paths_t(optmc_ctx *ctx, EuroArgs &A, double *store, int64_t ld
 template <int KIND>
 static int launch_paths_k(optmc_ctx *ctx, EuroArgs &A, bool anti, double *store, int64_t ld,
                           cudaStream_t st) {
+    if constexpr (kind_jumps(KIND)) {
+        if (use_jump_schedule(A) && ctx->jump_schedule) {
+            if (ctx->normals_impl == 0)
+                return anti ? launch_paths_t<KIND, true, 0, true>(ctx, A, store, ld, st)
+                            : launch_paths_t<KIND, false, 0, true>(ctx, A, store, ld, st);
+            return anti ? launch_paths_t<KIND, true, 1, true>(ctx, A, store, ld, st)
+                        : launch_paths_t<KIND, false, 1, true>(ctx, A, store, ld, st);
+        }
+    }
     if (ctx->normals_impl == 0)
         return anti ? launch_paths_t<KIND, true, 0>(ctx, A, store, ld, st)
                     : launch_paths_t<KIND, false, 0>(ctx, A, store, ld, st);

@@ -474,8 +474,17 @@ def test_american_philox_all_models_run(kind):
     assert am > eu - 0.05 and am < eu + 5.0     # early-exercise premium is non-negative
 
 
+@pytest.fixture(params=[1, 0], ids=["jump_schedule", "poisson_per_step"])
+def jump_schedule(request, eng):
+    """1 = the path kernels draw Poisson(lambda T) and the jump steps once (default),
+    0 = one Poisson(lambda dt) draw per step."""
+    eng.set_int("jump_schedule", request.param)
+    yield request.param
+    eng.set_int("jump_schedule", 1)
+
+
 @pytest.mark.parametrize("kind", ("merton", "bates", "kou", "sabr_jump", "heston"))
-def test_philox_path_store_law(kind):
+def test_philox_path_store_law(kind, jump_schedule):
     """The device-RNG path kernels, date by date: the scheme's martingale mean at EVERY exercise
     date (jump timing and compensation), the antithetic layout, and the terminal column's
     put price against the oracle's path kernel within 3 combined standard errors."""
