@@ -180,4 +180,82 @@ __global__ void __launch_bounds__(FED_P) k_fed(const FedArgs A) {
     if (A.terminal && live) A.terminal[p] = s.x;
 }
 
+// ---- streaming variant for the models without jumps -------------------------------
+// k_fed stages 64 x 32 tiles through shared memory with 64-thread blocks: 8 warps per SM,
+// so both HBM latency and the serial fp64 recurrence stay exposed (0.6-1.3 TB/s measured,
+// tools/bench_fed.py).  Without jumps nothing ties the paths of a block together, so here
+// a thread simply walks its own row: 32-byte chunks (two 16-byte loads per array: every
+// sector fetched is fully used, the other half of the 64-byte DRAM atom is the same
+// thread's next chunk and waits in L2), the next chunk in flight while the current one is
+// stepped, 1024 threads per SM.  Rows whose start is not 32-byte aligned (n_steps not a
+// multiple of 4) take up to three scalar steps first.  Same step functions, same order of
+// operations per path as k_fed.
+constexpr int FEDS_THREADS = 256;
+
+__device__ __forceinline__ void ld_chunk(const double *p, double (&v)[4]) {
+    const double2 a = __ldg(reinterpret_cast<const double2 *>(p));
+    const double2 b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(FEDS_THREADS, 4) k_fed_stream(const FedArgs A) {
+    static_assert(!kind_jumps(KIND), "jump models use k_fed (their jump buffer is block-ordered)");
+    constexpr bool TWO = kind_two_factor(KIND);
+    __shared__ MathShared math;                    // fast_log / fast_exp tables
+    const RngView tv = fill_math_shared(&math);
+    __syncthreads();
+    const Consts &c = A.c;
+    const int m = A.n_steps;
+    const size_t pld = (size_t)m + 1;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < A.n_paths; p += stride) {
+        State s;
+        s.x = c.x0;
+        s.v = c.v0;
+        const double *r1 = A.dw1 + (size_t)p * m;
+        const double *r2 = TWO ? A.dw2 + (size_t)p * m : nullptr;
+        double *out = A.paths ? A.paths + (size_t)p * pld : nullptr;
+        if (out) out[0] = kind_sabr(KIND) ? c.x0 : exp(c.x0);             // path_kernels.py:28
+        auto one = [&](double d1, double d2, int i) {
+            double z1, cz = 0.0;
+            if constexpr (TWO)
+                mix_fed(KIND, A.sign * d1, A.sign * d2, c, z1, cz);
+            else
+                z1 = A.sign * d1;
+            step_diffusion<KIND>(s, z1, cz, c, tv, i);
+            if (out) out[i + 1] = step_spot(KIND, s, tv);                  // path_kernels.py:34
+        };
+        int i = 0;
+        // scalar steps up to a 32-byte boundary of both rows (none when n_steps % 4 == 0)
+        while (i < m && (((uintptr_t)(r1 + i) | (TWO ? (uintptr_t)(r2 + i) : 0)) & 31u)) {
+            one(__ldg(r1 + i), TWO ? __ldg(r2 + i) : 0.0, i);
+            ++i;
+        }
+        double a[4], b[4] = {0.0, 0.0, 0.0, 0.0}, an[4], bn[4] = {0.0, 0.0, 0.0, 0.0};
+        if (i + 4 <= m) {
+            ld_chunk(r1 + i, a);
+            if constexpr (TWO) ld_chunk(r2 + i, b);
+        }
+        for (; i + 4 <= m; i += 4) {
+            const bool more = i + 8 <= m;
+            if (more) {                             // next chunk in flight during these 4 steps
+                ld_chunk(r1 + i + 4, an);
+                if constexpr (TWO) ld_chunk(r2 + i + 4, bn);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) one(a[k], b[k], i + k);
+            if (more) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    a[k] = an[k];
+                    b[k] = bn[k];
+                }
+            }
+        }
+        for (; i < m; ++i) one(__ldg(r1 + i), TWO ? __ldg(r2 + i) : 0.0, i);
+        if (A.terminal) A.terminal[p] = s.x;
+    }
+}
+
 }  // namespace optmc

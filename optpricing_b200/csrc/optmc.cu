@@ -27,6 +27,7 @@ struct optmc_ctx {
     int euro_threads = EURO_THREADS;
     int lsmc_mode = 1;          // 1: one persistent launch for all dates, 0: one launch per date
     int jump_schedule = 1;      // 1: pre-drawn jump schedule where it applies, 0: Poisson word per step
+    int fed_stream = 1;         // 1: k_fed_stream for the models without jumps, 0: tiled k_fed for all
     int64_t launches = 0;
     unsigned char *scratch = nullptr;  // device
     size_t scratch_bytes = 0;
@@ -181,6 +182,9 @@ extern "C" int optmc_set_int(optmc_ctx *ctx, const char *key, int64_t value) {
     } else if (!strcmp(key, "euro_threads")) {
         if (value != 64 && value != 128 && value != 256) FAIL("euro_threads must be 64, 128 or 256");
         ctx->euro_threads = (int)value;
+    } else if (!strcmp(key, "fed_stream")) {
+        if (value != 0 && value != 1) FAIL("fed_stream must be 0 or 1");
+        ctx->fed_stream = (int)value;
     } else if (!strcmp(key, "jump_schedule")) {
         if (value != 0 && value != 1) FAIL("jump_schedule must be 0 or 1");
         ctx->jump_schedule = (int)value;
@@ -728,6 +732,21 @@ extern "C" int optmc_fed_async(optmc_ctx *ctx, const optmc_model *model, double 
         k_scan_exclusive<<<1, 1024, 0, st>>>(A.base, A.n_blocks * (int64_t)n_steps);
         ctx->launches++;
         CK(cudaGetLastError());
+    }
+    if (!kind_jumps(model->kind) && ctx->fed_stream) {
+        // models without jumps: one thread streams one row (k_fed_stream)
+        const int64_t need = (n_paths + FEDS_THREADS - 1) / FEDS_THREADS;
+        const unsigned grid = (unsigned)std::max<int64_t>(
+            1, std::min<int64_t>(need, (int64_t)ctx->sm_count * 4 * 8));
+        switch (model->kind) {
+            case OPTMC_BSM: k_fed_stream<OPTMC_BSM><<<grid, FEDS_THREADS, 0, st>>>(A); break;
+            case OPTMC_HESTON: k_fed_stream<OPTMC_HESTON><<<grid, FEDS_THREADS, 0, st>>>(A); break;
+            case OPTMC_SABR: k_fed_stream<OPTMC_SABR><<<grid, FEDS_THREADS, 0, st>>>(A); break;
+            default: k_fed_stream<OPTMC_DUPIRE><<<grid, FEDS_THREADS, 0, st>>>(A); break;
+        }
+        ctx->launches++;
+        CK(cudaGetLastError());
+        return 0;
     }
 #define GO(K) k_fed<K><<<(unsigned)A.n_blocks, FED_P, fed_smem_bytes(), st>>>(A)
     DISPATCH_KIND(model->kind, GO)
