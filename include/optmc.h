@@ -343,8 +343,8 @@ int optmc_fp64_peak(optmc_ctx *ctx, int64_t iters, double *fma_per_sec, double *
    optmc_lsmc_peer_attach; 0 = local), "jump_schedule" (path kernels of the jump
    models, optmc_lsmc_paths_async: 1 = draw the path's Poisson(lambda T) count and its
    jump steps once, default while lambda T <= 2; 0 = one Poisson(lambda dt) draw per
-   step), "fed_stream" (optmc_fed_async for the models without jumps: 1 = one thread
-   streams one row, default; 0 = the shared-memory tiled kernel the jump models use). */
+   step), "fed_stream" (optmc_fed_async: 1 = one thread streams one row, default;
+   0 = the shared-memory tiled kernel). */
 int optmc_set_int(optmc_ctx *ctx, const char *key, int64_t value);
 
 /* Pointer-valued options: "lsmc_timing" (diagnostics: device memory for

@@ -180,16 +180,49 @@ __global__ void __launch_bounds__(FED_P) k_fed(const FedArgs A) {
     if (A.terminal && live) A.terminal[p] = s.x;
 }
 
-// ---- streaming variant for the models without jumps -------------------------------
+// Streaming version of k_fed_block_totals: a thread walks its own row of counts (32-byte
+// chunks) and adds the rare non-zero ones to tot[step][block of FED_P paths] atomically
+// (integer adds: the result does not depend on their order).  tot must be zero on entry.
+// Blocks are the 32-path groups one warp of k_fed_stream owns.
+__global__ void __launch_bounds__(256, 4) k_fed_block_totals_stream(const int64_t *counts,
+                                                                     int64_t n_paths, int n_steps,
+                                                                     int64_t n_blocks, int64_t *tot) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_paths; p += stride) {
+        const int64_t *row = counts + (size_t)p * n_steps;
+        const int64_t blk = p / 32;                // jump blocks of k_fed_stream: one warp
+        int i = 0;
+        auto add = [&](int64_t cnt, int step) {
+            if (cnt != 0)
+                atomicAdd(reinterpret_cast<unsigned long long *>(tot + (size_t)step * n_blocks + blk),
+                          (unsigned long long)cnt);
+        };
+        while (i < n_steps && ((uintptr_t)(row + i) & 31u)) {
+            add(__ldg(row + i), i);
+            ++i;
+        }
+        for (; i + 4 <= n_steps; i += 4) {
+            const longlong2 a = __ldg(reinterpret_cast<const longlong2 *>(row + i));
+            const longlong2 b = __ldg(reinterpret_cast<const longlong2 *>(row + i) + 1);
+            add(a.x, i); add(a.y, i + 1); add(b.x, i + 2); add(b.y, i + 3);
+        }
+        for (; i < n_steps; ++i) add(__ldg(row + i), i);
+    }
+}
+
+// ---- streaming variant ---------------------------------------------------------------
 // k_fed stages 64 x 32 tiles through shared memory with 64-thread blocks: 8 warps per SM,
 // so both HBM latency and the serial fp64 recurrence stay exposed (0.6-1.3 TB/s measured,
-// tools/bench_fed.py).  Without jumps nothing ties the paths of a block together, so here
-// a thread simply walks its own row: 32-byte chunks (two 16-byte loads per array: every
+// tools/bench_fed.py).  Here a thread simply walks its own row: 32-byte chunks (two 16-byte loads per array: every
 // sector fetched is fully used, the other half of the 64-byte DRAM atom is the same
 // thread's next chunk and waits in L2), the next chunk in flight while the current one is
 // stepped, 1024 threads per SM.  Rows whose start is not 32-byte aligned (n_steps not a
 // multiple of 4) take up to three scalar steps first.  Same step functions, same order of
 // operations per path as k_fed.
+// Jump models: the jump buffer is ordered by step, then path, then jump.  The offset of
+// (path p, step i) is base[i][p / 32] (totals of the 32-path group one warp owns + a scan,
+// as for k_fed) plus the counts of the lower lanes at step i: a warp ballot per step, and
+// a shuffle scan only when some path of the warp jumps (rare: lambda dt).
 constexpr int FEDS_THREADS = 256;
 
 __device__ __forceinline__ void ld_chunk(const double *p, double (&v)[4]) {
@@ -198,63 +231,115 @@ __device__ __forceinline__ void ld_chunk(const double *p, double (&v)[4]) {
     v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
 
+__device__ __forceinline__ void ld_chunk(const int64_t *p, int64_t (&v)[4]) {
+    const longlong2 a = __ldg(reinterpret_cast<const longlong2 *>(p));
+    const longlong2 b = __ldg(reinterpret_cast<const longlong2 *>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+
+// resident 256-thread blocks per SM: 4 (64 registers), 3 for the two-factor jump models
+__host__ __device__ constexpr int feds_min_blocks(int kind) {
+    return (kind_jumps(kind) && kind_two_factor(kind)) ? 3 : 4;
+}
+
 template <int KIND>
-__global__ void __launch_bounds__(FEDS_THREADS, 4) k_fed_stream(const FedArgs A) {
-    static_assert(!kind_jumps(KIND), "jump models use k_fed (their jump buffer is block-ordered)");
+__global__ void __launch_bounds__(FEDS_THREADS, feds_min_blocks(KIND)) k_fed_stream(const FedArgs A) {
     constexpr bool TWO = kind_two_factor(KIND);
+    constexpr bool JUMPS = kind_jumps(KIND);
     __shared__ MathShared math;                    // fast_log / fast_exp tables
     const RngView tv = fill_math_shared(&math);
     __syncthreads();
     const Consts &c = A.c;
     const int m = A.n_steps;
     const size_t pld = (size_t)m + 1;
+    const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < A.n_paths; p += stride) {
+    // Jump models keep the 32 lanes of a warp on the same step (chunks by step index, no
+    // per-row alignment prologue) because the jump offsets need a warp scan; rows that
+    // are not 32-byte aligned are then read with scalar loads.
+    const bool vec = (m % 4 == 0) && !(((uintptr_t)A.dw1 | (TWO ? (uintptr_t)A.dw2 : 0) |
+                                         (JUMPS ? (uintptr_t)A.counts : 0)) & 31u);
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p - lane < A.n_paths;
+         p += stride) {
+        const bool live = p < A.n_paths;
+        const int64_t pr = live ? p : 0;           // dead lanes of the last warp replay path 0
         State s;
         s.x = c.x0;
         s.v = c.v0;
-        const double *r1 = A.dw1 + (size_t)p * m;
-        const double *r2 = TWO ? A.dw2 + (size_t)p * m : nullptr;
-        double *out = A.paths ? A.paths + (size_t)p * pld : nullptr;
+        const double *r1 = A.dw1 + (size_t)pr * m;
+        const double *r2 = TWO ? A.dw2 + (size_t)pr * m : nullptr;
+        const int64_t *rc = JUMPS ? A.counts + (size_t)pr * m : nullptr;
+        double *out = (A.paths && live) ? A.paths + (size_t)p * pld : nullptr;
         if (out) out[0] = kind_sabr(KIND) ? c.x0 : exp(c.x0);             // path_kernels.py:28
-        auto one = [&](double d1, double d2, int i) {
+        const int64_t wblk = (p - lane) / 32;      // jump block of this warp: 32 consecutive paths
+        auto one = [&](double d1, double d2, int64_t cnt64, int i) {
             double z1, cz = 0.0;
             if constexpr (TWO)
                 mix_fed(KIND, A.sign * d1, A.sign * d2, c, z1, cz);
             else
                 z1 = A.sign * d1;
             step_diffusion<KIND>(s, z1, cz, c, tv, i);
+            if constexpr (JUMPS) {
+                const int cnt = live ? (int)cnt64 : 0;
+                if (__ballot_sync(0xffffffffu, cnt > 0)) {        // rare: some path of the warp jumps
+                    int incl = cnt;                               // inclusive scan over the lanes
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    if (cnt > 0) {
+                        const double *jb = A.jumps + A.base[(size_t)i * A.n_blocks + wblk] + (incl - cnt);
+                        if (KIND != OPTMC_SABR_JUMP && A.sum_mode) {
+                            double acc = 0.0;                     // np.sum(slice), path_kernels.py:116
+                            for (int k = 0; k < cnt; ++k) acc += jb[k];
+                            s.x += acc;
+                        } else {
+                            for (int k = 0; k < cnt; ++k) apply_jump<KIND>(s, jb[k]);
+                        }
+                    }
+                }
+            }
             if (out) out[i + 1] = step_spot(KIND, s, tv);                  // path_kernels.py:34
         };
         int i = 0;
-        // scalar steps up to a 32-byte boundary of both rows (none when n_steps % 4 == 0)
-        while (i < m && (((uintptr_t)(r1 + i) | (TWO ? (uintptr_t)(r2 + i) : 0)) & 31u)) {
-            one(__ldg(r1 + i), TWO ? __ldg(r2 + i) : 0.0, i);
-            ++i;
-        }
-        double a[4], b[4] = {0.0, 0.0, 0.0, 0.0}, an[4], bn[4] = {0.0, 0.0, 0.0, 0.0};
-        if (i + 4 <= m) {
-            ld_chunk(r1 + i, a);
-            if constexpr (TWO) ld_chunk(r2 + i, b);
-        }
-        for (; i + 4 <= m; i += 4) {
-            const bool more = i + 8 <= m;
-            if (more) {                             // next chunk in flight during these 4 steps
-                ld_chunk(r1 + i + 4, an);
-                if constexpr (TWO) ld_chunk(r2 + i + 4, bn);
+        if constexpr (!JUMPS) {
+            // scalar steps up to a 32-byte boundary of the rows (none when n_steps % 4 == 0)
+            while (i < m && (((uintptr_t)(r1 + i) | (TWO ? (uintptr_t)(r2 + i) : 0)) & 31u)) {
+                one(__ldg(r1 + i), TWO ? __ldg(r2 + i) : 0.0, 0, i);
+                ++i;
             }
+        }
+        if (!JUMPS || vec) {
+            double a[4], b[4] = {0.0, 0.0, 0.0, 0.0}, an[4], bn[4] = {0.0, 0.0, 0.0, 0.0};
+            int64_t n4[4] = {0, 0, 0, 0}, nn[4] = {0, 0, 0, 0};
+            if (i + 4 <= m) {
+                ld_chunk(r1 + i, a);
+                if constexpr (TWO) ld_chunk(r2 + i, b);
+                if constexpr (JUMPS) ld_chunk(rc + i, n4);
+            }
+            for (; i + 4 <= m; i += 4) {
+                const bool more = i + 8 <= m;
+                if (more) {                         // next chunk in flight during these 4 steps
+                    ld_chunk(r1 + i + 4, an);
+                    if constexpr (TWO) ld_chunk(r2 + i + 4, bn);
+                    if constexpr (JUMPS) ld_chunk(rc + i + 4, nn);
+                }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) one(a[k], b[k], i + k);
-            if (more) {
+                for (int k = 0; k < 4; ++k) one(a[k], b[k], n4[k], i + k);
+                if (more) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    a[k] = an[k];
-                    b[k] = bn[k];
+                    for (int k = 0; k < 4; ++k) {
+                        a[k] = an[k];
+                        b[k] = bn[k];
+                        n4[k] = nn[k];
+                    }
                 }
             }
         }
-        for (; i < m; ++i) one(__ldg(r1 + i), TWO ? __ldg(r2 + i) : 0.0, i);
-        if (A.terminal) A.terminal[p] = s.x;
+        for (; i < m; ++i)
+            one(__ldg(r1 + i), TWO ? __ldg(r2 + i) : 0.0, JUMPS ? __ldg(rc + i) : 0, i);
+        if (A.terminal && live) A.terminal[p] = s.x;
     }
 }
 

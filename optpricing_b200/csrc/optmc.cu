@@ -3,6 +3,7 @@
 // checks, constant folding in the reference's expression order, launch
 // geometry.  All arithmetic on paths happens in the kernels included below.
 #include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cmath>
@@ -683,7 +684,7 @@ extern "C" int optmc_levy_terminal_async(optmc_ctx *ctx, const optmc_levy *levy,
 // ---------------------------------------------------------------------------
 extern "C" int64_t optmc_fed_workspace_bytes(int32_t kind, int64_t n_paths, int32_t n_steps) {
     if (!kind_jumps(kind) || n_paths <= 0 || n_steps <= 0) return 8;
-    int64_t n_blocks = (n_paths + FED_P - 1) / FED_P;
+    int64_t n_blocks = (n_paths + 31) / 32;        // the finer of the two kernels' jump blocks
     return n_blocks * (int64_t)n_steps * (int64_t)sizeof(int64_t);
 }
 
@@ -719,31 +720,48 @@ extern "C" int optmc_fed_async(optmc_ctx *ctx, const optmc_model *model, double 
     A.sum_mode = path_sum_mode;
     A.terminal = terminal_dev;
     A.paths = paths_dev;
-    A.n_blocks = (n_paths + FED_P - 1) / FED_P;
-    if (A.n_blocks > 0x7fffffffLL) FAIL("too many paths for one fed call");
+    const int64_t tiled_blocks = (n_paths + FED_P - 1) / FED_P;
+    A.n_blocks = ctx->fed_stream ? (n_paths + 31) / 32 : tiled_blocks;     // jump blocks
+    if (tiled_blocks > 0x7fffffffLL) FAIL("too many paths for one fed call");
     if (kind_jumps(model->kind)) {
         int64_t need = optmc_fed_workspace_bytes(model->kind, n_paths, n_steps);
         if (!workspace_dev || workspace_bytes < need) FAIL("fed workspace too small");
         A.base = reinterpret_cast<int64_t *>(workspace_dev);
-        k_fed_block_totals<<<(unsigned)A.n_blocks, FED_P, 0, st>>>(counts_dev, n_paths, n_steps,
-                                                                   A.n_blocks, A.base);
+        if (ctx->fed_stream) {
+            CK(cudaMemsetAsync(A.base, 0, (size_t)(A.n_blocks * n_steps) * sizeof(int64_t), st));
+            const unsigned g = (unsigned)std::max<int64_t>(
+                1, std::min<int64_t>((n_paths + 255) / 256, (int64_t)ctx->sm_count * 32));
+            k_fed_block_totals_stream<<<g, 256, 0, st>>>(counts_dev, n_paths, n_steps, A.n_blocks,
+                                                         A.base);
+        } else {
+            k_fed_block_totals<<<(unsigned)A.n_blocks, FED_P, 0, st>>>(counts_dev, n_paths, n_steps,
+                                                                       A.n_blocks, A.base);
+        }
         ctx->launches++;
         CK(cudaGetLastError());
-        k_scan_exclusive<<<1, 1024, 0, st>>>(A.base, A.n_blocks * (int64_t)n_steps);
+        {
+            // exclusive scan over (step, block): a library device scan (temporary storage carved
+            // from the context's scratch), else the single-block kernel
+            const int64_t items = A.n_blocks * (int64_t)n_steps;
+            size_t tmp_bytes = 0;
+            cudaError_t qe = cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, A.base, A.base, items, st);
+            if (qe == cudaSuccess && tmp_bytes <= ctx->scratch_bytes && items < 0x7fffffffLL) {
+                CK(cub::DeviceScan::ExclusiveSum(ctx->scratch, tmp_bytes, A.base, A.base, items, st));
+            } else {
+                k_scan_exclusive<<<1, 1024, 0, st>>>(A.base, items);
+            }
+        }
         ctx->launches++;
         CK(cudaGetLastError());
     }
-    if (!kind_jumps(model->kind) && ctx->fed_stream) {
-        // models without jumps: one thread streams one row (k_fed_stream)
-        const int64_t need = (n_paths + FEDS_THREADS - 1) / FEDS_THREADS;
+    if (ctx->fed_stream) {
+        // one thread streams one row (k_fed_stream)
+        const int64_t nb = (n_paths + FEDS_THREADS - 1) / FEDS_THREADS;
         const unsigned grid = (unsigned)std::max<int64_t>(
-            1, std::min<int64_t>(need, (int64_t)ctx->sm_count * 4 * 8));
-        switch (model->kind) {
-            case OPTMC_BSM: k_fed_stream<OPTMC_BSM><<<grid, FEDS_THREADS, 0, st>>>(A); break;
-            case OPTMC_HESTON: k_fed_stream<OPTMC_HESTON><<<grid, FEDS_THREADS, 0, st>>>(A); break;
-            case OPTMC_SABR: k_fed_stream<OPTMC_SABR><<<grid, FEDS_THREADS, 0, st>>>(A); break;
-            default: k_fed_stream<OPTMC_DUPIRE><<<grid, FEDS_THREADS, 0, st>>>(A); break;
-        }
+            1, std::min<int64_t>(nb, (int64_t)ctx->sm_count * 4 * 8));
+#define GOS(K) k_fed_stream<K><<<grid, FEDS_THREADS, 0, st>>>(A)
+        DISPATCH_KIND(model->kind, GOS)
+#undef GOS
         ctx->launches++;
         CK(cudaGetLastError());
         return 0;

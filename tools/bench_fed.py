@@ -17,8 +17,18 @@ term = torch.empty(n, dtype=torch.float64, device=eng.device)
 paths = torch.empty((n, m + 1), dtype=torch.float64, device=eng.device)
 ws = torch.empty(1, dtype=torch.int64, device=eng.device)
 ptr = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
-for kind, params, two in (("bsm", {"sigma": 0.2}, False),
-                          ("heston", {"v0": 0.04, "kappa": 2.0, "theta": 0.04, "rho": -0.7, "vol_of_vol": 0.5}, True)):
+lam_dt = 0.5 * dt
+counts = torch.poisson(torch.full((n, m), lam_dt, dtype=torch.float64, device=eng.device), generator=g).to(torch.int64)
+n_jumps = int(counts.sum().item())
+jumps = torch.randn(max(n_jumps, 1), dtype=torch.float64, device=eng.device, generator=g) * 0.15 - 0.1
+HES = {"v0": 0.04, "kappa": 2.0, "theta": 0.04, "rho": -0.7, "vol_of_vol": 0.5}
+JMP = {"lambda": 0.5, "mu_j": -0.1, "sigma_j": 0.15}
+for kind, params, two in (("bsm", {"sigma": 0.2}, False), ("heston", HES, True),
+                          ("merton", {"sigma": 0.2, **JMP}, False), ("bates", {**HES, **JMP}, True)):
+    jump = kind in ("merton", "bates")
+    if jump:
+        ws = torch.empty(max(int(eng.lib.optmc_fed_workspace_bytes(_engine.KIND_CODES[kind], n, m)) // 8, 1),
+                         dtype=torch.int64, device=eng.device)
     mdl = _engine.make_model(kind, params, 0.05, 0.0, v0=0.04 if two else None)
     for want_paths in (False, True):
         best = 1e9
@@ -27,12 +37,14 @@ for kind, params, two in (("bsm", {"sigma": 0.2}, False),
             a.record()
             eng._check(eng.lib.optmc_fed_async(
                 eng.ctx, ctypes.byref(mdl), math.log(100.0), dt, n, m, ptr(dw1), ptr(dw2) if two else None,
-                None, None, 0, 1.0, 0, ptr(term) if not want_paths else None,
-                ptr(paths) if want_paths else None, ptr(ws), 8, eng.stream()), "optmc_fed_async")
+                ptr(counts) if jump else None, ptr(jumps) if jump else None, n_jumps if jump else 0,
+                1.0, 0, ptr(term) if not want_paths else None,
+                ptr(paths) if want_paths else None, ptr(ws), ws.numel() * 8, eng.stream()),
+                "optmc_fed_async")
             b.record()
             torch.cuda.synchronize()
             if rep:
                 best = min(best, a.elapsed_time(b))
-        bytes_ = n * m * 8 * ((2 if two else 1) + (1 if want_paths else 0))
+        bytes_ = n * m * 8 * ((2 if two else 1) + (1 if want_paths else 0) + (1 if jump else 0))
         print(f"k_fed<{kind}> {n} x {m} {'paths' if want_paths else 'terminal'}: {best:.3f} ms = "
               f"{bytes_ / best / 1e6:.0f} GB/s ({bytes_ / 2**30:.1f} GiB moved)", flush=True)
