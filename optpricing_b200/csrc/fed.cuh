@@ -237,13 +237,15 @@ __device__ __forceinline__ void ld_chunk(const int64_t *p, int64_t (&v)[4]) {
     v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
 }
 
-// resident 256-thread blocks per SM: 4 (64 registers), 3 for the two-factor jump models
-__host__ __device__ constexpr int feds_min_blocks(int kind) {
-    return (kind_jumps(kind) && kind_two_factor(kind)) ? 3 : 4;
+// resident 256-thread blocks per SM: 4 (64 registers); 3 for the two-factor jump models and
+// for the variants that also write the path matrix
+__host__ __device__ constexpr int feds_min_blocks(int kind, bool paths) {
+    return (paths || (kind_jumps(kind) && kind_two_factor(kind))) ? 3 : 4;
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(FEDS_THREADS, feds_min_blocks(KIND)) k_fed_stream(const FedArgs A) {
+template <int KIND, bool PATHS>
+__global__ void __launch_bounds__(FEDS_THREADS, feds_min_blocks(KIND, PATHS))
+k_fed_stream(const FedArgs A) {
     constexpr bool TWO = kind_two_factor(KIND);
     constexpr bool JUMPS = kind_jumps(KIND);
     __shared__ MathShared math;                    // fast_log / fast_exp tables
@@ -269,10 +271,13 @@ __global__ void __launch_bounds__(FEDS_THREADS, feds_min_blocks(KIND)) k_fed_str
         const double *r1 = A.dw1 + (size_t)pr * m;
         const double *r2 = TWO ? A.dw2 + (size_t)pr * m : nullptr;
         const int64_t *rc = JUMPS ? A.counts + (size_t)pr * m : nullptr;
-        double *out = (A.paths && live) ? A.paths + (size_t)p * pld : nullptr;
+        double *out = (PATHS && live) ? A.paths + (size_t)p * pld : nullptr;
         if (out) out[0] = kind_sabr(KIND) ? c.x0 : exp(c.x0);             // path_kernels.py:28
         const int64_t wblk = (p - lane) / 32;      // jump block of this warp: 32 consecutive paths
-        auto one = [&](double d1, double d2, int64_t cnt64, int i) {
+        // one step; with a path matrix requested returns the spot after the step and, when
+        // `put`, stores it (8 bytes) -- the chunked loop below collects four and stores
+        // aligned 32-byte quads instead
+        auto one = [&](double d1, double d2, int64_t cnt64, int i, bool put) -> double {
             double z1, cz = 0.0;
             if constexpr (TWO)
                 mix_fed(KIND, A.sign * d1, A.sign * d2, c, z1, cz);
@@ -300,13 +305,18 @@ __global__ void __launch_bounds__(FEDS_THREADS, feds_min_blocks(KIND)) k_fed_str
                     }
                 }
             }
-            if (out) out[i + 1] = step_spot(KIND, s, tv);                  // path_kernels.py:34
+            double spot = 0.0;
+            if (out) {
+                spot = step_spot(KIND, s, tv);                             // path_kernels.py:34
+                if (put) out[i + 1] = spot;
+            }
+            return spot;
         };
         int i = 0;
         if constexpr (!JUMPS) {
             // scalar steps up to a 32-byte boundary of the rows (none when n_steps % 4 == 0)
             while (i < m && (((uintptr_t)(r1 + i) | (TWO ? (uintptr_t)(r2 + i) : 0)) & 31u)) {
-                one(__ldg(r1 + i), TWO ? __ldg(r2 + i) : 0.0, 0, i);
+                one(__ldg(r1 + i), TWO ? __ldg(r2 + i) : 0.0, 0, i, true);
                 ++i;
             }
         }
@@ -318,6 +328,15 @@ __global__ void __launch_bounds__(FEDS_THREADS, feds_min_blocks(KIND)) k_fed_str
                 if constexpr (TWO) ld_chunk(r2 + i, b);
                 if constexpr (JUMPS) ld_chunk(rc + i, n4);
             }
+            // Path matrix: rows have stride n_steps + 1, so a row's 32-byte quads sit at a
+            // per-row phase r = (position of out[i + 1] in its quad).  Every chunk of four new
+            // spots completes exactly one aligned quad -- the last r spots of the previous
+            // chunk followed by the first 4 - r new ones -- written as two 16-byte stores
+            // (a full sector: no partial-sector write-backs); the first chunk's head and the
+            // last r spots go out as 8-byte stores.
+            const int r = out ? (int)(((uintptr_t)(out + i + 1) >> 3) & 3u) : 0;
+            double p0 = 0.0, p1 = 0.0, p2 = 0.0;      // the previous chunk's spots 1, 2, 3
+            bool head = true;
             for (; i + 4 <= m; i += 4) {
                 const bool more = i + 8 <= m;
                 if (more) {                         // next chunk in flight during these 4 steps
@@ -325,8 +344,24 @@ __global__ void __launch_bounds__(FEDS_THREADS, feds_min_blocks(KIND)) k_fed_str
                     if constexpr (TWO) ld_chunk(r2 + i + 4, bn);
                     if constexpr (JUMPS) ld_chunk(rc + i + 4, nn);
                 }
+                double o[4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) one(a[k], b[k], n4[k], i + k);
+                for (int k = 0; k < 4; ++k) o[k] = one(a[k], b[k], n4[k], i + k, false);
+                if (out) {
+                    if (head && r) {
+                        for (int t = 0; t < 4 - r; ++t) out[i + 1 + t] = o[t];
+                    } else {
+                        const double e0 = r == 0 ? o[0] : r == 1 ? p2 : r == 2 ? p1 : p0;
+                        const double e1 = r == 0 ? o[1] : r == 1 ? o[0] : r == 2 ? p2 : p1;
+                        const double e2 = r == 0 ? o[2] : r == 1 ? o[1] : r == 2 ? o[0] : p2;
+                        const double e3 = r == 0 ? o[3] : r == 1 ? o[2] : r == 2 ? o[1] : o[0];
+                        double2 *q = reinterpret_cast<double2 *>(out + i + 1 - r);
+                        q[0] = make_double2(e0, e1);
+                        q[1] = make_double2(e2, e3);
+                    }
+                    head = false;
+                    p0 = o[1]; p1 = o[2]; p2 = o[3];
+                }
                 if (more) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -336,9 +371,14 @@ __global__ void __launch_bounds__(FEDS_THREADS, feds_min_blocks(KIND)) k_fed_str
                     }
                 }
             }
+            if (out && !head) {                     // the last r spots of the last chunk
+                if (r >= 3) out[i - 2] = p0;
+                if (r >= 2) out[i - 1] = p1;
+                if (r >= 1) out[i] = p2;
+            }
         }
         for (; i < m; ++i)
-            one(__ldg(r1 + i), TWO ? __ldg(r2 + i) : 0.0, JUMPS ? __ldg(rc + i) : 0, i);
+            one(__ldg(r1 + i), TWO ? __ldg(r2 + i) : 0.0, JUMPS ? __ldg(rc + i) : 0, i, true);
         if (A.terminal && live) A.terminal[p] = s.x;
     }
 }

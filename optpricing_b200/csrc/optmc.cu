@@ -759,7 +759,9 @@ extern "C" int optmc_fed_async(optmc_ctx *ctx, const optmc_model *model, double 
         const int64_t nb = (n_paths + FEDS_THREADS - 1) / FEDS_THREADS;
         const unsigned grid = (unsigned)std::max<int64_t>(
             1, std::min<int64_t>(nb, (int64_t)ctx->sm_count * 4 * 8));
-#define GOS(K) k_fed_stream<K><<<grid, FEDS_THREADS, 0, st>>>(A)
+#define GOS(K)                                                          \
+    if (A.paths) k_fed_stream<K, true><<<grid, FEDS_THREADS, 0, st>>>(A);  \
+    else k_fed_stream<K, false><<<grid, FEDS_THREADS, 0, st>>>(A)
         DISPATCH_KIND(model->kind, GOS)
 #undef GOS
         ctx->launches++;
