@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """GPU experiment: time the C2 Heston kernel over launch geometries (and library
-variants given as OPTMC_LIB).  Prints ms per 2^24 x 252 pricing and path-steps/s."""
+variants given as OPTMC_LIB; KIND, N_PATHS, N_STEPS, PRECISION, JUMP_SCHEDULE from the environment).  Prints ms per 2^24 x 252 pricing and path-steps/s."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -15,9 +15,13 @@ params = {"heston": HESTON, "bsm": {"sigma": 0.2},
           "kou": {"sigma": 0.15, "lambda": 1.0, "p_up": 0.6, "eta1": 10.0, "eta2": 5.0},
           "sabr": {"alpha": 0.5, "beta": 0.8, "rho": -0.6},
           "sabr_jump": {"alpha": 0.5, "beta": 0.8, "rho": -0.6, "lambda": 0.4, "mu_j": -0.1, "sigma_j": 0.15}}[kind]
+if "LAMBDA" in os.environ and "lambda" in params:
+    params["lambda"] = float(os.environ["LAMBDA"])
 mdl = _engine.make_model(kind, params, 0.05, 0.0)
 n_paths, n_steps = int(os.environ.get("N_PATHS", 1 << 24)), int(os.environ.get("N_STEPS", 252))
 mom = torch.zeros(6, dtype=torch.float64, device=eng.device)
+if "JUMP_SCHEDULE" in os.environ:
+    eng.set_int("jump_schedule", int(os.environ["JUMP_SCHEDULE"]))
 configs = [(int(a), int(b)) for a, b in (c.split("x") for c in sys.argv[1:])] or [(256, 0)]
 for threads, per_sm in configs:
     eng.set_int("euro_threads", threads)
