@@ -37,6 +37,7 @@ from typing import Any
 import numpy as np
 
 from optpricing_b200 import _engine
+from optpricing_b200.atoms import Option, OptionType
 from optpricing_b200.atoms import is_call as _is_call
 from optpricing_b200.models import levy_kind, model_kind
 
@@ -464,6 +465,30 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
             for row, i in zip(block, idx):
                 self.last_stats_many._set(i, row, r, T, c_mean, seed)
         return prices
+
+    def price_frame(self, options_df, stock, model, rate, **kwargs: Any) -> np.ndarray:
+        """
+        Prices of the contracts of a DataFrame with ``strike``, ``maturity`` and
+        ``optionType`` ("call" / "put") columns, aligned with its row order -- the
+        Monte Carlo counterpart of ``price_options_vectorized``
+        (calibration/vectorized_pricer.py:20-28), which ``VolatilitySurface.
+        calculate_model_iv`` (calibration/iv_surface.py:104-150) and the calibrator
+        call and which needs a characteristic function; with this, models that have
+        none (SABR, SABR-jump) get a model surface.  One simulation per distinct
+        maturity (``price_many``).
+        """
+        strikes = np.asarray(options_df["strike"], dtype=np.float64)
+        mats = np.asarray(options_df["maturity"], dtype=np.float64)
+        kinds = np.asarray(options_df["optionType"])
+        bad = [k for k in np.unique(kinds) if str(k).lower() not in ("call", "put")]
+        if bad:
+            raise ValueError(f"optionType must be 'call' or 'put', got {bad}")
+        options = [Option(strike=float(k), maturity=float(t),
+                          option_type=OptionType.CALL if str(c).lower() == "call" else OptionType.PUT)
+                   for k, t, c in zip(strikes, mats, kinds)]
+        if not options:
+            return np.empty(0)
+        return self.price_many(options, stock, model, rate, **kwargs)
 
     # ------------------------------------------------------ fused greeks (SURVEY 8 f1)
     _LOG_KINDS = ("bsm", "heston", "merton", "bates", "kou")

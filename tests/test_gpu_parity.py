@@ -542,6 +542,38 @@ def test_price_many_equals_single_prices():
     assert t4.price(wide[120], STQ, ob.BSMModel(), RT).price == pytest.approx(w[120], rel=1e-12)
 
 
+def test_price_frame_is_the_mc_counterpart_of_the_vectorised_pricer():
+    """DataFrame in (strike, maturity, optionType), prices out in row order -- the shape of
+    price_options_vectorized (calibration/vectorized_pricer.py:20-28) -- for a model without
+    a characteristic function."""
+    import pandas as pd
+    rng = np.random.default_rng(3)
+    df = pd.DataFrame({"strike": rng.uniform(80, 120, 30), "maturity": rng.choice([0.5, 1.0, 2.0], 30),
+                       "optionType": rng.choice(["call", "put"], 30)})
+    df.index = rng.permutation(30) + 100                    # an arbitrary index must not matter
+    model = ob.SABRModel()
+    got = ob.MonteCarloTechnique(n_paths=1 << 16, n_steps=20, seed=4).price_frame(df, STQ, model, RT)
+    opts = [ob.Option(float(k), float(t), ob.OptionType.CALL if c == "call" else ob.OptionType.PUT)
+            for k, t, c in zip(df["strike"], df["maturity"], df["optionType"])]
+    want = ob.MonteCarloTechnique(n_paths=1 << 16, n_steps=20, seed=4).price_many(opts, STQ, model, RT)
+    assert got.shape == (30,) and np.array_equal(got, want)
+    # BSM: the surface of implied vols recovered from the frame's prices is flat at sigma
+    flat = pd.DataFrame({"strike": [90.0, 100.0, 110.0] * 2, "maturity": [0.5] * 3 + [1.0] * 3,
+                         "optionType": ["call", "put", "call"] * 2})
+    px = ob.MonteCarloTechnique(n_paths=1 << 20, n_steps=8, seed=9, control_variate=True).price_frame(
+        flat, STQ, ob.BSMModel(params={"sigma": 0.2}), RT)
+    from scipy.stats import norm
+
+    def black_scholes(k, t, call, s0=100.0, r=0.05, q=0.01, sig=0.2):
+        d1 = (math.log(s0 / k) + (r - q + 0.5 * sig * sig) * t) / (sig * math.sqrt(t))
+        d2 = d1 - sig * math.sqrt(t)
+        c = s0 * math.exp(-q * t) * norm.cdf(d1) - k * math.exp(-r * t) * norm.cdf(d2)
+        return c if call else c - s0 * math.exp(-q * t) + k * math.exp(-r * t)
+
+    for p, k, t, c in zip(px, flat["strike"], flat["maturity"], flat["optionType"]):
+        assert p == pytest.approx(black_scholes(k, t, c == "call"), abs=0.02)
+
+
 @pytest.mark.parametrize("kind", ("bsm", "heston", "merton", "bates", "kou"))
 def test_fused_greeks_equal_bump_and_reprice(kind):
     """delta/gamma/rho read off one simulation == GreekMixin's re-pricings on CRN."""

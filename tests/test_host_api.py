@@ -306,3 +306,16 @@ def test_philox_reference_known_answers():
     for c, k, want in KAT:
         got = philox4x32_10(*[np.array([x], dtype=np.uint32) for x in c], *k)[0]
         assert [int(x) for x in got] == list(want)
+
+
+def test_price_frame_validates_without_a_gpu():
+    """price_frame (the MC counterpart of price_options_vectorized): bad option types raise,
+    an empty frame prices to an empty array -- both before any device work."""
+    import pandas as pd
+    t = ob.MonteCarloTechnique(n_paths=100, n_steps=2, seed=1)
+    stock, rate = ob.Stock(100.0), ob.Rate(0.05)
+    bad = pd.DataFrame({"strike": [100.0], "maturity": [1.0], "optionType": ["straddle"]})
+    with pytest.raises(ValueError, match="optionType"):
+        t.price_frame(bad, stock, ob.BSMModel(), rate)
+    empty = pd.DataFrame({"strike": [], "maturity": [], "optionType": []})
+    assert t.price_frame(empty, stock, ob.BSMModel(), rate).shape == (0,)
