@@ -205,6 +205,15 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
     auto advance = [&](uint32_t w0, uint32_t w1, uint32_t w2, int i) {
         // (z1, z2): two-factor models -- the mixed, scaled increments (dW_S, xi-weighted
         // dW_v); one-factor models -- sqrt(dt) N(0,1) for this step and the next.
+        // Heston / Bates on the hand-written maths: the parts of the pair, one root per path
+        if constexpr (NIMPL == 1 && (KIND == OPTMC_HESTON || KIND == OPTMC_BATES)) {
+            double L, t1, t2;
+            normal_parts_fast<true>(w0, w1, w2, L, t1, t2, tab);
+            step_heston_parts<DEFER>(sa, L, t1, t2, c);
+            if constexpr (ANTI) step_heston_parts<DEFER>(sb, L, -t1, -t2, c);
+            if constexpr (!LEGACY) after_step(i);
+            return;
+        }
         double z1, z2;
         if constexpr (NIMPL == 0) {
             double a, b;

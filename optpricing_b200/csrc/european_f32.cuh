@@ -40,7 +40,7 @@ __device__ __forceinline__ float sqrt_approx(float a) {
 // Two N(0,1) from two Philox words.
 __device__ __forceinline__ void normal_pair_f32(uint32_t wr, uint32_t wa, float &z1, float &z2) {
     const float u = ((float)(wr >> 8) + 0.5f) * 0x1.0p-24f;               // exact, in (0, 1)
-    const float rad = sqrt_approx(-2.0f * __logf(u));
+    const float rad = sqrt_approx(fmaxf(-2.0f * __logf(u), 0.0f));   // __logf is an approximation near 1
     float s, c;
     __sincosf((float)(int32_t)wa * (3.14159265358979f * 0x1.0p-31f), &s, &c);   // angle in [-pi, pi)
     z1 = rad * c;

@@ -65,14 +65,6 @@ __host__ __device__ constexpr bool kind_sabr(int k) {
     return k == OPTMC_SABR || k == OPTMC_SABR_JUMP;
 }
 
-// max(a, 0) in ONE integer-pipe instruction: clamp the high word at 0.  A
-// negative a becomes (0, lo): a positive denormal below 2^-1042 instead of an
-// exact 0 -- a difference of < 1e-313, which no product or sum in the step can
-// turn into anything representable next to the quantities it meets.
-__device__ __forceinline__ double relu64(double a) {
-    return __hiloint2double(max(__double2hiint(a), 0), __double2loint(a));
-}
-
 struct State {
     double x;  // log S (S for SABR kinds); with DEFER: the stochastic part only
     double v;  // variance (Heston/Bates, stored before the floor) or vol (SABR)
@@ -114,6 +106,27 @@ __device__ __forceinline__ void step_heston(State &s, double z1, double czx, con
         s.x += fma(sq, z1, fma(vp, c.neg_half_dt, c.rqc_dt));
     }
     s.v = fma(sq, czx, fma(vp, c.one_minus_kappa_dt, c.kappa_theta_dt));
+}
+
+// The same step on the device RNG, from the parts of a Box-Muller pair (philox.cuh:
+// z1 = sqrt(L) t1, czx = sqrt(L) t2): the step uses the normals only as sqrt(v+) z, and
+// sqrt(v+) sqrt(L) = sqrt(v+ L) is ONE root per path instead of one per path plus the
+// pair's radius.  The partner path passes (-t1, -t2).
+template <bool DEFER>
+__device__ __forceinline__ void step_heston_parts(State &s, double L, double t1, double t2,
+                                                  const Consts &c) {
+    double vp = relu64(s.v);
+    // v_sqrt * radius, to the accuracy the Box-Muller radius always had here (one Newton
+    // correction, rel. 1e-12: a perturbation of a N(0,1) draw no price can see); the
+    // fed-draw parity kernels take step_heston with its < 1 ulp root
+    double rq = sqrt_nonneg_fast(vp * L);
+    if constexpr (DEFER) {
+        s.x = fma(rq, t1, s.x);
+        s.w += vp;
+    } else {
+        s.x += fma(rq, t1, fma(vp, c.neg_half_dt, c.rqc_dt));
+    }
+    s.v = fma(rq, t2, fma(vp, c.one_minus_kappa_dt, c.kappa_theta_dt));
 }
 
 template <int KIND, bool DEFER>

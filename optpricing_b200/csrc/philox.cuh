@@ -90,6 +90,14 @@ __device__ __forceinline__ double u01_open(uint32_t lo, uint32_t hi) {
     return ((double)(x >> 11) + 0.5) * 0x1.0p-53;
 }
 
+// max(a, 0) as ONE integer-pipe instruction on the high word (fp64 max is DSETP + two
+// selects here).  A negative a becomes a non-negative number below 2^-1022 instead of an
+// exact 0 -- a difference no product or sum in a step loop can turn into anything
+// representable next to the quantities it meets.
+__device__ __forceinline__ double relu64(double a) {
+    return __hiloint2double(max(__double2hiint(a), 0), __double2loint(a));
+}
+
 // MUFU.RSQ64H seed for a >= 0: y ~ 1/sqrt(a) to ~2^-22 relative, finite (huge)
 // for a == 0.  Also returns h = y/2, formed by decrementing the exponent field
 // on the integer pipe (y's low word is zero, so this is exact and costs no
@@ -322,13 +330,18 @@ __device__ __forceinline__ void normal_pair_lib(uint32_t w0, uint32_t w1, uint32
 }
 
 // Hand-written pair.  angle = a_i + d: the top 10 bits of w2 pick the bucket, the
-// low 22 bits the offset d in (-h/2, h/2).
-//   MIXED = false: (z1, z2) = s R (cos, sin)(angle)
-//   MIXED = true : (z1, z2) = M R (cos, sin)(angle)^T
+// low 22 bits the offset d in (-h/2, h/2).  normal_parts_fast returns the squared radius
+// L = -2 ln u >= 0 and the direction,
+//   MIXED = false: (t1, t2) = s (cos, sin)(angle)
+//   MIXED = true : (t1, t2) = M (cos, sin)(angle)^T
+// and the pair is (z1, z2) = sqrt(L) (t1, t2).  Heston's step needs the normals only as
+// sqrt(v) z, so it takes the parts and draws ONE root, sqrt(v L) (models.cuh).
+// L is floored at 0: for the two largest u of the top binade the table + polynomial
+// value of -2 ln u (abs. error 5e-16 there) comes out at -2e-16 instead of +2e-16.
 template <bool MIXED>
-__device__ __forceinline__ void normal_pair_fast(uint32_t w0, uint32_t w1, uint32_t w2, double &z1,
-                                                 double &z2, RngView t) {
-    double rad = sqrt_nonneg_fast(neg2_log_u(w0, w1, t));
+__device__ __forceinline__ void normal_parts_fast(uint32_t w0, uint32_t w1, uint32_t w2, double &L,
+                                                  double &t1, double &t2, RngView t) {
+    L = relu64(neg2_log_u(w0, w1, t));
     int fine = (int)((w2 & 0x3FFFFFu) * 2u) - 0x3FFFFF;            // odd, in (-2^22, 2^22)
     double d = (double)fine * C_FINE;
     double d2 = d * d;
@@ -337,13 +350,23 @@ __device__ __forceinline__ void normal_pair_fast(uint32_t w0, uint32_t w1, uint3
     if constexpr (MIXED) {
         uint32_t row = t.base + TRIG_OFF + ((w2 >> 17) & ((TRIG_N - 1) * 32u));
         double2 r1 = lds_f64x2(row), r2 = lds_f64x2(row + 16u);
-        z1 = rad * fma(r1.x, cd, r1.y * sd);
-        z2 = rad * fma(r2.x, cd, r2.y * sd);
+        t1 = fma(r1.x, cd, r1.y * sd);
+        t2 = fma(r2.x, cd, r2.y * sd);
     } else {
         double2 cs = lds_f64x2(t.base + TRIG_OFF + ((w2 >> 18) & ((TRIG_N - 1) * 16u)));
-        z1 = rad * fma(cs.x, cd, -(cs.y * sd));
-        z2 = rad * fma(cs.y, cd, cs.x * sd);
+        t1 = fma(cs.x, cd, -(cs.y * sd));
+        t2 = fma(cs.y, cd, cs.x * sd);
     }
+}
+
+template <bool MIXED>
+__device__ __forceinline__ void normal_pair_fast(uint32_t w0, uint32_t w1, uint32_t w2, double &z1,
+                                                 double &z2, RngView t) {
+    double L, t1, t2;
+    normal_parts_fast<MIXED>(w0, w1, w2, L, t1, t2, t);
+    double rad = sqrt_nonneg_fast(L);
+    z1 = rad * t1;
+    z2 = rad * t2;
 }
 
 // Poisson(mu) by inversion, mu small (lambda * dt).  `w` is the 32-bit word of
