@@ -48,11 +48,11 @@ I64_PER_PATH_STEP = {"heston": 16.5, "bsm": 6.0}
 FLOPS_PER_PATH_STEP = {"heston": 28.0, "bsm": 6.0}
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
-# `ncu --set full` captures summarised in profiles/r01_ncu_heston_summary.md (r1e) and
+# `ncu --set full` captures summarised in profiles/r01_ncu_heston_summary.md (r1f) and
 # profiles/r01_ncu_lsmc_summary.md (persistent): the European kernel reads its tables and code only;
 # the LSMC induction streams the 1.68 GB path store once (the 6.7 GB of algorithmic cashflow / row
 # re-reads are L2 hits at 2^22 paths).
-NCU_TRAFFIC_BYTES = {"heston_c2": 52_992 + 0, "lsmc_c4": 1_729_129_000 + 123_759_616}
+NCU_TRAFFIC_BYTES = {"heston_c2": 52_736 + 0, "lsmc_c4": 1_729_129_000 + 123_759_616}
 
 HESTON = {"v0": 0.04, "kappa": 2.0, "theta": 0.04, "rho": -0.7, "vol_of_vol": 0.5}
 WORKLOADS = {
