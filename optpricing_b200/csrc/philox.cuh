@@ -120,8 +120,10 @@ __device__ __forceinline__ double sqrt_nonneg(double a) {
     return fma(e, h, g);
 }
 
-// One correction only (relative error <= 1.5 * 2^-44 = 9e-14): used for the
-// Box-Muller radius, where that is far below anything a price can see.
+// One correction only: the seed is good to 2^-20 (measured, profiles/r01_sqrt_probe.log),
+// so the result to 1.5 * 2^-40 = 1.4e-12 relative (measured 1.3e-12).  Used where the root
+// scales a N(0,1) draw -- the Box-Muller radius, Heston's sqrt(v+ * (-2 ln u)) -- where
+// that is far below anything a price can see.
 __device__ __forceinline__ double sqrt_nonneg_fast(double a) {
     double y, h;
     rsqrt_seed(a, y, h);
