@@ -364,8 +364,22 @@ struct NoSink {
     __device__ __forceinline__ void operator()(int, const State &, const State &) const {}
 };
 
+// Resident 256-thread blocks per SM the register budget is sized for.  Heston / Bates: three
+// (85 registers; with four the step loop reloads 19 constants per four steps and runs 1 %
+// slower).  The one-factor models and the SABR kinds: four (63 registers, no spills; 2 - 3 %
+// faster than three, profiles/r01_sweep_launch_geometry.log).
+__host__ __device__ constexpr int euro_min_blocks(int kind, int nimpl) {
+#ifdef OPTMC_EURO_MIN_BLOCKS_ALL
+    return OPTMC_EURO_MIN_BLOCKS_ALL;
+#else
+    return (kind == OPTMC_HESTON || kind == OPTMC_BATES || kind == OPTMC_DUPIRE || nimpl == 0)
+               ? OPTMC_EURO_MIN_BLOCKS : 4;      // (the library-maths variants spill at 64)
+#endif
+}
+
 template <int KIND, bool ANTI, int NIMPL, bool SCHED = false>
-__global__ void __launch_bounds__(EURO_THREADS, OPTMC_EURO_MIN_BLOCKS) k_european(const EuroArgs A) {
+__global__ void __launch_bounds__(EURO_THREADS, euro_min_blocks(KIND, NIMPL))
+k_european(const EuroArgs A) {
     __shared__ RngShared<kind_two_factor(KIND)> tab;
     RngView tv{0u};
     __shared__ double scratch[5 * 32];
