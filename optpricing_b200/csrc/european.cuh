@@ -109,7 +109,7 @@ __device__ __forceinline__ double2 jumps_slow(uint32_t w, double mu, double p0, 
 // divergent jump branch costs one integer compare per step.  Up to eight indices are
 // kept sorted in four registers; a path with more jumps (P = 2e-4 at lambda T = 2)
 // recomputes its indices at every step.  The host selects SCHED while lambda T <= 2.
-template <int KIND, bool ANTI, int NIMPL, bool PER_STEP, bool SCHED, class Sink>
+template <int KIND, bool ANTI, int NIMPL, bool PER_STEP, bool SCHED, bool BGEN = false, class Sink>
 __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, State &sa, State &sb,
                                               RngView tab, Sink &&sink) {
     const Consts &c = A.c;
@@ -129,7 +129,8 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
     // terminal-only kernels of the log models defer the deterministic drift
     constexpr bool DEFER = !PER_STEP && !kind_sabr(KIND) && KIND != OPTMC_DUPIRE;
     // SABR kinds with the hand-written maths: log-vol form, one exponential per step
-    constexpr bool LOGV = kind_sabr(KIND) && NIMPL == 1;
+    // (BGEN: the host has seen that beta is neither 0 nor 1 -- no switch in the step)
+    constexpr int LOGV = (kind_sabr(KIND) && NIMPL == 1) ? (BGEN ? 2 : 1) : 0;
     init_state<KIND, DEFER, LOGV>(sa, c);
     init_state<KIND, DEFER, LOGV>(sb, c);
     // A Box-Muller pair feeds one step of a two-factor model, or two consecutive
@@ -377,7 +378,7 @@ __host__ __device__ constexpr int euro_min_blocks(int kind, int nimpl) {
 #endif
 }
 
-template <int KIND, bool ANTI, int NIMPL, bool SCHED = false>
+template <int KIND, bool ANTI, int NIMPL, bool SCHED = false, bool BGEN = false>
 __global__ void __launch_bounds__(EURO_THREADS, euro_min_blocks(KIND, NIMPL))
 k_european(const EuroArgs A) {
     __shared__ RngShared<kind_two_factor(KIND)> tab;
@@ -390,7 +391,7 @@ k_european(const EuroArgs A) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < A.n_local; g += stride) {
         State sa, sb;
-        simulate_draw<KIND, ANTI, NIMPL, false, SCHED>(A, (uint64_t)(A.draw_offset + g), sa, sb, tv,
+        simulate_draw<KIND, ANTI, NIMPL, false, SCHED, BGEN>(A, (uint64_t)(A.draw_offset + g), sa, sb, tv,
                                                        NoSink{});
         if constexpr (!kind_two_factor(KIND) && KIND != OPTMC_DUPIRE) {
             // log S_T = log S_0 + n drift(sigma) + sigma W + J: W and J do not depend on sigma,

@@ -185,16 +185,23 @@ __device__ __forceinline__ double floor_neg650(double a) {
     return __hiloint2double((int)min((unsigned)__double2hiint(a), 0xC0845000u), __double2loint(a));
 }
 
-template <bool LOGV>
+// LOGV: 0 = literal form; 1 = log-vol form, beta_mode read at run time; 2 = log-vol form
+// for a beta that is neither 0 nor 1, chosen by the host -- the step loop then carries one
+// code path instead of three and no switch.
+template <int LOGV>
 __device__ __forceinline__ void step_sabr(State &s, double z1, double cz, const Consts &c,
                                           RngView t) {
-    if constexpr (LOGV) {
+    if constexpr (LOGV != 0) {
         const double s_pos = floor_1e8(s.x);
         double coef;
-        switch (c.beta_mode) {
-            case 1: coef = fast_exp(floor_neg650(s.v), t) * s_pos; break;
-            case 2: coef = fast_exp(floor_neg650(s.v), t); break;
-            default: coef = fast_exp(floor_neg650(fma(c.beta, fast_log(s_pos, t), s.v)), t);
+        if constexpr (LOGV == 2) {
+            coef = fast_exp(floor_neg650(fma(c.beta, fast_log(s_pos, t), s.v)), t);
+        } else {
+            switch (c.beta_mode) {
+                case 1: coef = fast_exp(floor_neg650(s.v), t) * s_pos; break;
+                case 2: coef = fast_exp(floor_neg650(s.v), t); break;
+                default: coef = fast_exp(floor_neg650(fma(c.beta, fast_log(s_pos, t), s.v)), t);
+            }
         }
         s.x += fma(coef, z1, c.rqc_dt * s_pos);
         s.v += fma(c.alpha, cz, c.neg_half_alpha2_dt);
@@ -214,7 +221,7 @@ __device__ __forceinline__ void mix_fed(int kind, double dw1, double dw2, const 
     if (kind == OPTMC_HESTON || kind == OPTMC_BATES) cz *= c.xi;
 }
 
-template <int KIND, bool DEFER = false, bool LOGV = false>
+template <int KIND, bool DEFER = false, int LOGV = 0>
 __device__ __forceinline__ void step_diffusion(State &s, double z1, double cz, const Consts &c,
                                                RngView t, int i) {
     if constexpr (KIND == OPTMC_DUPIRE)
@@ -229,10 +236,10 @@ __device__ __forceinline__ void step_diffusion(State &s, double z1, double cz, c
 
 // Initial state.  With DEFER the log-spot accumulator starts at 0 and log S_0 is
 // added by finish_deferred; jumps (additive in log space) accumulate in x too.
-template <int KIND, bool DEFER, bool LOGV = false>
+template <int KIND, bool DEFER, int LOGV = 0>
 __device__ __forceinline__ void init_state(State &s, const Consts &c) {
     s.x = (DEFER && !kind_sabr(KIND)) ? 0.0 : c.x0;
-    s.v = (LOGV && kind_sabr(KIND)) ? c.log_v0 : c.v0;
+    s.v = (LOGV != 0 && kind_sabr(KIND)) ? c.log_v0 : c.v0;
     s.w = 0.0;
 }
 

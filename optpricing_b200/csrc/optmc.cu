@@ -348,9 +348,9 @@ static bool use_jump_schedule(const EuroArgs &A) {
     return A.pois_mu_path <= 2.0 && A.n_steps < 65535;
 }
 
-template <int KIND, bool ANTI, int NIMPL, bool SCHED = false>
+template <int KIND, bool ANTI, int NIMPL, bool SCHED = false, bool BGEN = false>
 static int launch_euro_t(optmc_ctx *ctx, EuroArgs &A, cudaStream_t st, int *grid_out) {
-    auto kern = k_european<KIND, ANTI, NIMPL, SCHED>;
+    auto kern = k_european<KIND, ANTI, NIMPL, SCHED, BGEN>;
     int grid = euro_grid(ctx, kern, A.n_local);
     kern<<<grid, ctx->euro_threads, 0, st>>>(A);
     ctx->launches++;
@@ -367,6 +367,12 @@ static int launch_euro_k(optmc_ctx *ctx, EuroArgs &A, bool anti, cudaStream_t st
     if (ctx->normals_impl == 0)
         return anti ? launch_euro_t<KIND, true, 0>(ctx, A, st, grid)
                     : launch_euro_t<KIND, false, 0>(ctx, A, st, grid);
+    if constexpr (kind_sabr(KIND)) {
+        // beta neither 0 nor 1: the variant whose step has the general exp(ln v + beta ln s) only
+        if (A.c.beta_mode != 1 && A.c.beta_mode != 2)
+            return anti ? launch_euro_t<KIND, true, 1, false, true>(ctx, A, st, grid)
+                        : launch_euro_t<KIND, false, 1, false, true>(ctx, A, st, grid);
+    }
     return anti ? launch_euro_t<KIND, true, 1>(ctx, A, st, grid)
                 : launch_euro_t<KIND, false, 1>(ctx, A, st, grid);
 }
