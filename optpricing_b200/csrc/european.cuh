@@ -126,6 +126,10 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
     constexpr bool STEP_JUMPS = JUMPS && !JUMPS_AT_END;
     constexpr bool SCHEDULED = STEP_JUMPS && SCHED;       // pre-drawn jump schedule
     constexpr bool LEGACY = STEP_JUMPS && !SCHED;         // one Poisson word per step
+    // terminal-only kernel with scheduled jumps (SABR-jump): groups of four steps; groups in
+    // which no path of the warp jumps run the packed, unrolled body of plain SABR
+    constexpr bool GROUPJ = SCHEDULED && !PER_STEP;
+    static_assert(!GROUPJ || TWO, "group-wise jumps: one step per Box-Muller pair");
     // terminal-only kernels of the log models defer the deterministic drift
     constexpr bool DEFER = !PER_STEP && !kind_sabr(KIND) && KIND != OPTMC_DUPIRE;
     // SABR kinds with the hand-written maths: log-vol form, one exponential per step
@@ -145,12 +149,17 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
         const uint4 u = philox4x32_10(make_uint4(id_lo, id_hi, 0xFFFFFFFCu, (uint32_t)j), A.key);
         return __umulhi(u.x, (uint32_t)A.n_steps);          // floor(U n_steps)
     };
+    // GROUPJ keeps two registers per path: the jump count and the step of the next jump
+    // (0xFFFFFFFF: none); the indices are recomputed when a jump group is reached
+    uint32_t nxt = 0xFFFFFFFFu;
     if constexpr (SCHEDULED) {
         const uint4 e = philox4x32_10(make_uint4(id_lo, id_hi, 0xFFFFFFFFu, 0xFEu), A.key);
         if (__builtin_expect(poisson_maybe(e.x, A.pois_p0_path_bits), 0)) {
             const uint4 x = philox4x32_10(make_uint4(id_lo, id_hi, 0xFFFFFFFFu, 0xFFu), A.key);
             n_j = poisson_slow(e.x, x.x, A.pois_mu_path, A.pois_p0_path);
-            if (n_j <= SCHED_SLOTS) {
+            if constexpr (GROUPJ) {
+                for (int j = 0; j < n_j; ++j) nxt = min(nxt, sched_index(j));
+            } else if (n_j <= SCHED_SLOTS) {
                 // insertion sort of the n_j indices into 8 ascending 16-bit slots (0xFFFF = none)
                 uint32_t v[SCHED_SLOTS];
 #pragma unroll
@@ -182,9 +191,50 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
             apply_jump<KIND, DEFER>(sb, Jb);
         }
     };
-    // after the diffusion part of step i: scheduled jumps of that step, then the sink
-    auto after_step = [&](int i) {
-        if constexpr (SCHEDULED) {
+    // GROUPJ: what the jumps of the four steps from `first` do to S, per step and path -- the
+    // product of exp(J) over the step's jumps (mc_kernels.py:274), 1 where there is none
+    double ja[4], jb[4];
+    auto group_jumps = [&](int first) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) ja[t] = jb[t] = 1.0;
+        if (nxt < (uint32_t)(first + 4)) {
+            uint32_t later = 0xFFFFFFFFu;
+            for (int j = 0; j < n_j; ++j) {
+                const uint32_t at = sched_index(j);
+                if (at >= (uint32_t)(first + 4)) later = min(later, at);
+                if (at < (uint32_t)first || at >= (uint32_t)(first + 4)) continue;
+                // sizes: fresh draws for the partner, as in the reference's second pass; the
+                // draw index labels the jump
+                const double fa = exp(jump_size<KIND, NIMPL>(
+                    philox4x32_10(make_uint4(id_lo, id_hi, 0xFFFFFFFDu, 1u | ((uint32_t)j << 8)), A.key),
+                    c, tab));
+                double fb = 1.0;
+                if constexpr (ANTI)
+                    fb = exp(jump_size<KIND, NIMPL>(
+                        philox4x32_10(make_uint4(id_lo, id_hi, 0xFFFFFFFDu, 2u | ((uint32_t)j << 8)),
+                                      A.key), c, tab));
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    if (at == (uint32_t)(first + t)) {
+                        ja[t] *= fa;
+                        jb[t] *= fb;
+                    }
+                }
+            }
+            nxt = later;
+        }
+    };
+    // after the diffusion part of step i: scheduled jumps of that step, then the sink.
+    // `slot` (GROUPJ): position of the step in a jump group, -1 in a jump-free group.
+    auto after_step = [&](int i, auto slot) {
+        if constexpr (GROUPJ) {
+            constexpr int T = decltype(slot)::value;
+            if constexpr (T >= 0) {
+                static_assert(KIND == OPTMC_SABR_JUMP, "multiplicative jumps");
+                sa.x *= ja[T];
+                if constexpr (ANTI) sb.x *= jb[T];
+            }
+        } else if constexpr (SCHEDULED) {
             if (__builtin_expect(n_j != 0, 0)) {
                 if (n_j <= SCHED_SLOTS) {
                     while ((sch[0] & 0xFFFFu) == (uint32_t)i) {
@@ -206,7 +256,7 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
     // One Box-Muller pair (three Philox words: 64 bits of radius, 32 of angle) and the
     // SPC steps it feeds, starting at step i.
     // `whole` (a std::bool_constant): the caller knows that step i + 1 exists too
-    auto advance = [&](uint32_t w0, uint32_t w1, uint32_t w2, int i, auto whole) {
+    auto advance = [&](uint32_t w0, uint32_t w1, uint32_t w2, int i, auto whole, auto slot) {
         // (z1, z2): two-factor models -- the mixed, scaled increments (dW_S, xi-weighted
         // dW_v); one-factor models -- sqrt(dt) N(0,1) for this step and the next.
         // Heston / Bates on the hand-written maths: the parts of the pair, one root per path
@@ -215,7 +265,7 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
             normal_parts_fast<true>(w0, w1, w2, L, t1, t2, tab);
             step_heston_parts<DEFER>(sa, L, t1, t2, c);
             if constexpr (ANTI) step_heston_parts<DEFER>(sb, L, -t1, -t2, c);
-            if constexpr (!LEGACY) after_step(i);
+            if constexpr (!LEGACY) after_step(i, slot);
             return;
         }
         double z1, z2;
@@ -235,25 +285,70 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
         if constexpr (TWO) {
             step_diffusion<KIND, DEFER, LOGV>(sa, z1, z2, c, tab, i);
             if constexpr (ANTI) step_diffusion<KIND, DEFER, LOGV>(sb, -z1, -z2, c, tab, i);
-            if constexpr (!LEGACY) after_step(i);
+            if constexpr (!LEGACY) after_step(i, slot);
         } else {
             step_diffusion<KIND, DEFER>(sa, z1, 0.0, c, tab, i);
             if constexpr (ANTI) step_diffusion<KIND, DEFER>(sb, -z1, 0.0, c, tab, i);
-            if constexpr (!LEGACY) after_step(i);
+            if constexpr (!LEGACY) after_step(i, slot);
             if constexpr (SPC == 2) {
                 if (decltype(whole)::value || i + 1 < A.n_steps) {
                     step_diffusion<KIND, DEFER>(sa, z2, 0.0, c, tab, i + 1);
                     if constexpr (ANTI) step_diffusion<KIND, DEFER>(sb, -z2, 0.0, c, tab, i + 1);
-                    after_step(i + 1);
+                    after_step(i + 1, slot);
                 }
             }
         }
     };
     constexpr std::true_type WHOLE{};
     constexpr std::false_type RAGGED{};
+    constexpr std::integral_constant<int, -1> NOSLOT{};
     // Without a Poisson word per step all 128 bits of a Philox call are used:
     // three calls (c2 = 3g, 3g+1, 3g+2) feed four pairs, see philox_pair_words.
-    if constexpr (SCHEDULED) {
+    if constexpr (GROUPJ) {
+        // The warp finds the first group of four steps in which one of its paths jumps (one
+        // min-reduction), runs the groups before it through the jump-free body -- a loop with a
+        // warp-uniform trip count and no jump code -- and that one group through a second copy
+        // of the body in which every step is followed by its jump factor; the warp stays in
+        // lockstep throughout.
+        const unsigned lanes = __activemask();      // the lanes of this warp that simulate a draw
+        uint32_t call = 0;
+        int i = 0;
+        while (i < A.n_steps) {
+            const uint32_t hit_group = __reduce_min_sync(lanes, nxt >> 2);
+            const int stop = (int)min((uint64_t)A.n_steps, (uint64_t)hit_group * 4u);
+            for (; i < stop; i += 4, call += 3) {
+                const uint4 a = philox4x32_10(make_uint4(id_lo, id_hi, call, 0u), A.key);
+                advance(a.x, a.y, a.z, i, RAGGED, NOSLOT);
+                if (i + 1 < A.n_steps) {
+                    const uint4 b = philox4x32_10(make_uint4(id_lo, id_hi, call + 1u, 0u), A.key);
+                    advance(a.w, b.x, b.y, i + 1, RAGGED, NOSLOT);
+                    if (i + 2 < A.n_steps) {
+                        const uint4 d = philox4x32_10(make_uint4(id_lo, id_hi, call + 2u, 0u), A.key);
+                        advance(b.z, b.w, d.x, i + 2, RAGGED, NOSLOT);
+                        if (i + 3 < A.n_steps) advance(d.y, d.z, d.w, i + 3, RAGGED, NOSLOT);
+                    }
+                }
+            }
+            if (i >= A.n_steps) break;
+            group_jumps(i);
+            {
+                const uint4 a = philox4x32_10(make_uint4(id_lo, id_hi, call, 0u), A.key);
+                advance(a.x, a.y, a.z, i, RAGGED, std::integral_constant<int, 0>{});
+                if (i + 1 < A.n_steps) {
+                    const uint4 b = philox4x32_10(make_uint4(id_lo, id_hi, call + 1u, 0u), A.key);
+                    advance(a.w, b.x, b.y, i + 1, RAGGED, std::integral_constant<int, 1>{});
+                    if (i + 2 < A.n_steps) {
+                        const uint4 d = philox4x32_10(make_uint4(id_lo, id_hi, call + 2u, 0u), A.key);
+                        advance(b.z, b.w, d.x, i + 2, RAGGED, std::integral_constant<int, 2>{});
+                        if (i + 3 < A.n_steps)
+                            advance(d.y, d.z, d.w, i + 3, RAGGED, std::integral_constant<int, 3>{});
+                    }
+                }
+            }
+            i += 4;
+            call += 3;
+        }
+    } else if constexpr (SCHEDULED) {
         // one copy of the step body (it carries the inlined jump code): the twelve words of
         // three calls are handed out pair by pair
         uint32_t call = 0;
@@ -275,7 +370,7 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
                 w0 = d.y; w1 = d.z; w2 = d.w;
                 call += 3;
             }
-            advance(w0, w1, w2, i, RAGGED);
+            advance(w0, w1, w2, i, RAGGED, NOSLOT);
         }
     } else if constexpr (!LEGACY && TWO) {
         // (the bounds tests between the pairs also keep the compiler from hoisting all three
@@ -285,14 +380,14 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
         OPTMC_UNROLL_STEPS
         for (int i = 0; i < A.n_steps; i += 4 * SPC, call += 3) {
             const uint4 a = philox4x32_10(make_uint4(id_lo, id_hi, call, 0u), A.key);
-            advance(a.x, a.y, a.z, i, RAGGED);
+            advance(a.x, a.y, a.z, i, RAGGED, NOSLOT);
             if (i + SPC < A.n_steps) {
                 const uint4 b = philox4x32_10(make_uint4(id_lo, id_hi, call + 1u, 0u), A.key);
-                advance(a.w, b.x, b.y, i + SPC, RAGGED);
+                advance(a.w, b.x, b.y, i + SPC, RAGGED, NOSLOT);
                 if (i + 2 * SPC < A.n_steps) {
                     const uint4 d = philox4x32_10(make_uint4(id_lo, id_hi, call + 2u, 0u), A.key);
-                    advance(b.z, b.w, d.x, i + 2 * SPC, RAGGED);
-                    if (i + 3 * SPC < A.n_steps) advance(d.y, d.z, d.w, i + 3 * SPC, RAGGED);
+                    advance(b.z, b.w, d.x, i + 2 * SPC, RAGGED, NOSLOT);
+                    if (i + 3 * SPC < A.n_steps) advance(d.y, d.z, d.w, i + 3 * SPC, RAGGED, NOSLOT);
                 }
             }
         }
@@ -305,12 +400,12 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
         OPTMC_UNROLL_STEPS
         for (; i + GS <= A.n_steps; i += GS, call += 3) {
             const uint4 a = philox4x32_10(make_uint4(id_lo, id_hi, call, 0u), A.key);
-            advance(a.x, a.y, a.z, i, WHOLE);
+            advance(a.x, a.y, a.z, i, WHOLE, NOSLOT);
             const uint4 b = philox4x32_10(make_uint4(id_lo, id_hi, call + 1u, 0u), A.key);
-            advance(a.w, b.x, b.y, i + SPC, WHOLE);
+            advance(a.w, b.x, b.y, i + SPC, WHOLE, NOSLOT);
             const uint4 d = philox4x32_10(make_uint4(id_lo, id_hi, call + 2u, 0u), A.key);
-            advance(b.z, b.w, d.x, i + 2 * SPC, WHOLE);
-            advance(d.y, d.z, d.w, i + 3 * SPC, WHOLE);
+            advance(b.z, b.w, d.x, i + 2 * SPC, WHOLE, NOSLOT);
+            advance(d.y, d.z, d.w, i + 3 * SPC, WHOLE, NOSLOT);
         }
         if (i < A.n_steps) {
             uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a, d = a;
@@ -329,14 +424,14 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
                 } else {
                     w0 = d.y; w1 = d.z; w2 = d.w;
                 }
-                advance(w0, w1, w2, i, RAGGED);
+                advance(w0, w1, w2, i, RAGGED, NOSLOT);
             }
         }
     } else {
         OPTMC_UNROLL_STEPS
         for (int i = 0; i < A.n_steps; ++i) {
             const uint4 w = philox4x32_10(make_uint4(id_lo, id_hi, (uint32_t)i, 0u), A.key);
-            advance(w.x, w.y, w.z, i, RAGGED);
+            advance(w.x, w.y, w.z, i, RAGGED, NOSLOT);
             if (__builtin_expect(poisson_maybe(w.w, A.pois_p0_bits[0]), 0)) {
                 double2 J = jumps_slow<KIND, ANTI, NIMPL>(w.w, A.pois_mu[0], A.pois_p0[0], A.key,
                                                           id_lo, id_hi, (uint32_t)i, c, tab);
@@ -369,17 +464,20 @@ struct NoSink {
 // (85 registers; with four the step loop reloads 19 constants per four steps and runs 1 %
 // slower).  The one-factor models and the SABR kinds: four (63 registers, no spills; 2 - 3 %
 // faster than three, profiles/r01_sweep_launch_geometry.log).
-__host__ __device__ constexpr int euro_min_blocks(int kind, int nimpl) {
+__host__ __device__ constexpr int euro_min_blocks(int kind, int nimpl, bool sched) {
 #ifdef OPTMC_EURO_MIN_BLOCKS_ALL
     return OPTMC_EURO_MIN_BLOCKS_ALL;
 #else
-    return (kind == OPTMC_HESTON || kind == OPTMC_BATES || kind == OPTMC_DUPIRE || nimpl == 0)
-               ? OPTMC_EURO_MIN_BLOCKS : 4;      // (the library-maths variants spill at 64)
+    // (the library-maths variants and the scheduled SABR-jump kernel, which keeps eight jump
+    // factors in its jump groups, spill at 64 registers)
+    return (kind == OPTMC_HESTON || kind == OPTMC_BATES || kind == OPTMC_DUPIRE || nimpl == 0 ||
+            (kind == OPTMC_SABR_JUMP && sched))
+               ? OPTMC_EURO_MIN_BLOCKS : 4;
 #endif
 }
 
 template <int KIND, bool ANTI, int NIMPL, bool SCHED = false, bool BGEN = false>
-__global__ void __launch_bounds__(EURO_THREADS, euro_min_blocks(KIND, NIMPL))
+__global__ void __launch_bounds__(EURO_THREADS, euro_min_blocks(KIND, NIMPL, SCHED))
 k_european(const EuroArgs A) {
     __shared__ RngShared<kind_two_factor(KIND)> tab;
     RngView tv{0u};

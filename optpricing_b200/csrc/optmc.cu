@@ -361,15 +361,23 @@ static int launch_euro_t(optmc_ctx *ctx, EuroArgs &A, cudaStream_t st, int *grid
 
 template <int KIND>
 static int launch_euro_k(optmc_ctx *ctx, EuroArgs &A, bool anti, cudaStream_t st, int *grid) {
-    // (the European SABR-jump kernel keeps one Poisson word per step: with the schedule its
-    // four-fold unrolled step body carries four copies of the jump code and measured 21 %
-    // slower, a single-copy loop no faster than the per-step form)
     if (ctx->normals_impl == 0)
         return anti ? launch_euro_t<KIND, true, 0>(ctx, A, st, grid)
                     : launch_euro_t<KIND, false, 0>(ctx, A, st, grid);
     if constexpr (kind_sabr(KIND)) {
         // beta neither 0 nor 1: the variant whose step has the general exp(ln v + beta ln s) only
-        if (A.c.beta_mode != 1 && A.c.beta_mode != 2)
+        const bool bgen = A.c.beta_mode != 1 && A.c.beta_mode != 2;
+        // SABR-jump (jumps act on S inside the step loop): the jump schedule while lambda T is small
+        if constexpr (KIND == OPTMC_SABR_JUMP) {
+            if (ctx->jump_schedule && use_jump_schedule(A)) {
+                if (bgen)
+                    return anti ? launch_euro_t<KIND, true, 1, true, true>(ctx, A, st, grid)
+                                : launch_euro_t<KIND, false, 1, true, true>(ctx, A, st, grid);
+                return anti ? launch_euro_t<KIND, true, 1, true, false>(ctx, A, st, grid)
+                            : launch_euro_t<KIND, false, 1, true, false>(ctx, A, st, grid);
+            }
+        }
+        if (bgen)
             return anti ? launch_euro_t<KIND, true, 1, false, true>(ctx, A, st, grid)
                         : launch_euro_t<KIND, false, 1, false, true>(ctx, A, st, grid);
     }

@@ -513,6 +513,35 @@ def test_philox_path_store_law(kind, jump_schedule):
     assert lr.var() == pytest.approx(lr_ref.var(), rel=0.05)
 
 
+@pytest.mark.parametrize("n_steps,antithetic,lam", [(37, True, 1.5), (64, False, 0.4), (3, True, 0.9),
+                                                    (50, True, 0.05)])
+def test_european_sabr_jump_schedule_matches_per_step_poisson(eng, n_steps, antithetic, lam):
+    """European SABR-jump (jumps act on S inside the step loop): the group-wise jump schedule
+    and the per-step Poisson draw are two samplers of one law -- prices, second moments and the
+    martingale mean of S_T agree within 4 combined standard errors; ragged last groups, no
+    antithetic partner, many and few jumps."""
+    params = dict(ob.SABRJumpModel().params)
+    params["lambda"] = lam
+    model = ob.SABRJumpModel(params=params)
+    out = {}
+    try:
+        for mode in (1, 0):
+            eng.set_int("jump_schedule", mode)
+            t = ob.MonteCarloTechnique(n_paths=1 << 21, n_steps=n_steps, antithetic=antithetic, seed=5)
+            p = t.price(CALL, STQ, model, RT).price
+            st = t.last_stats
+            out[mode] = (p, st["stderr"], st["control_mean"], st["control_stderr"])
+            fwd = st["control_expected"]          # the scheme's own E[S_T]
+    finally:
+        eng.set_int("jump_schedule", 1)
+    (p1, e1, c1, s1), (p0, e0, c0, s0) = out[1], out[0]
+    assert abs(p1 - p0) < 4 * math.hypot(e1, e0), out
+    # the sample mean of S_T: the two samplers against each other and against the scheme's
+    # own mean
+    assert abs(c1 - c0) < 4 * math.hypot(s1, s0), out
+    assert abs(c1 - fwd) < 4 * s1 + 1e-4 * fwd and abs(c0 - fwd) < 4 * s0 + 1e-4 * fwd, (out, fwd)
+
+
 # ------------------------------------------------------------------ batched contracts, fused greeks
 def test_price_many_equals_single_prices():
     """One simulation per maturity; each price equals price() on the same Philox key."""
