@@ -340,10 +340,11 @@ int optmc_fp64_peak(optmc_ctx *ctx, int64_t iters, double *fma_per_sec, double *
    (optmc_lsmc: 1 = every exercise date in one persistent cooperative launch,
    default; 0 = one optmc_lsmc_step_async launch per date), "lsmc_use_peers"
    (1 = the next optmc_lsmc calls are joint calls of the attached ranks, see
-   optmc_lsmc_peer_attach; 0 = local), "jump_schedule" (path kernels of the jump
-   models, optmc_lsmc_paths_async: 1 = draw the path's Poisson(lambda T) count and its
-   jump steps once, default while lambda T <= 2; 0 = one Poisson(lambda dt) draw per
-   step), "fed_stream" (optmc_fed_async: 1 = one thread streams one row, default;
+   optmc_lsmc_peer_attach; 0 = local), "jump_schedule" (kernels whose jumps act
+   inside the step loop -- the path kernels of the jump models, optmc_lsmc_paths_async,
+   and European SABR-jump, optmc_european*: 1 = draw the path's Poisson(lambda T) count
+   and its jump steps once, default while lambda T <= 2; 0 = one Poisson(lambda dt) draw
+   per step; two samplers of the same law), "fed_stream" (optmc_fed_async: 1 = one thread streams one row, default;
    0 = the shared-memory tiled kernel). */
 int optmc_set_int(optmc_ctx *ctx, const char *key, int64_t value);
 
