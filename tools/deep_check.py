@@ -3,7 +3,11 @@
 schemes sample the exact terminal law, so the Monte Carlo price must agree with the reference's
 closed-form price (tests/golden/price_goldens.json; Kou: Gil-Pelaez quadrature) to within its standard error -- here
 with 2^32 paths per model, i.e. standard errors of ~1e-4 on a price of ~10.  A bias in the
-device normals, the Poisson draw or the jump sizes at the 1e-5 level would show as |z| >> 3."""
+device normals, the Poisson draw or the jump sizes at the 1e-5 level would show as |z| >> 3.
+Heston with vol_of_vol -> 0 (1e-9 here: the model wants it positive) and v0 = theta has a constant variance, so its log-Euler scheme is exact
+for ANY number of steps and must reproduce the Black-Scholes price with sigma = sqrt(v0): that
+holds the two-factor step -- the mixed Box-Muller direction and the one-root sqrt(v+ * (-2 ln u))
+-- to the same resolution (8 steps, both correlation conventions)."""
 import json, math, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import optpricing_b200 as ob
@@ -45,3 +49,17 @@ for name, model, want in (("bsm", ob.BSMModel({"sigma": 0.2}), g["G1_closed_form
         price, se = s / n_chunks, math.sqrt(ss) / n_chunks
         print(f"{name:7s} {precision}: {n_chunks} x 2^28 paths  price {price:.6f} +- {se:.6f}  "
               f"exact {want:.6f}  z = {(price - want) / se:+.2f}", flush=True)
+
+hes = ob.HestonModel({"v0": 0.04, "kappa": 2.0, "theta": 0.04, "rho": -0.7, "vol_of_vol": 1e-9})
+for corr in ("reference", "independent"):
+    for precision in ("fp64", "fp32"):
+        t = ob.MonteCarloTechnique(n_paths=1 << 28, n_steps=8, seed=77, precision=precision,
+                                   correlation=corr)
+        s = ss = 0.0
+        for _ in range(n_chunks):
+            s += t.price(call, stock, hes, rate).price
+            ss += t.last_stats["stderr"] ** 2
+        price, se = s / n_chunks, math.sqrt(ss) / n_chunks
+        print(f"heston xi=0 ({corr[:5]}) {precision}: {n_chunks} x 2^28 paths x 8 steps  price {price:.6f} "
+              f"+- {se:.6f}  exact {g['G1_closed_form']:.6f}  z = {(price - g['G1_closed_form']) / se:+.2f}",
+              flush=True)
