@@ -94,11 +94,7 @@ __device__ __forceinline__ void step_one_factor(State &s, double dw, const Const
 template <bool DEFER>
 __device__ __forceinline__ void step_heston(State &s, double z1, double czx, const Consts &c) {
     double vp = relu64(s.v);                       // v_pos = max(v, 0)
-#ifdef OPTMC_FAST_VSQRT
-    double sq = sqrt_nonneg_fast(vp);
-#else
-    double sq = sqrt_nonneg(vp);                   // v_sqrt
-#endif
+    double sq = sqrt_nonneg(vp);                   // v_sqrt, < 1 ulp: the fed-draw parity step
     if constexpr (DEFER) {
         s.x = fma(sq, z1, s.x);
         s.w += vp;
