@@ -98,9 +98,8 @@ __device__ __forceinline__ double2 jumps_slow(uint32_t w, double mu, double p0, 
 // Simulate one draw over all steps.  SINK(step_index, sa, sb) is called after
 // every completed step when PER_STEP (LSMC path store), never otherwise.
 //
-// SCHED (path kernels of the jump models, whose jumps must act inside the step loop; the
-// European SABR-jump kernel could use it too but measured no faster): instead of one
-// Poisson(lambda dt) draw per step, the path draws
+// SCHED (kernels whose jumps must act inside the step loop: the path kernels of the jump
+// models and European SABR-jump): instead of one Poisson(lambda dt) draw per step, the path draws
 // N ~ Poisson(lambda T) once and the N step indices floor(U n_steps) -- the arrival
 // times of a Poisson process given their number are iid uniform, so the per-step counts
 // have exactly the law of the reference's independent Poisson(lambda dt) draws
@@ -108,7 +107,8 @@ __device__ __forceinline__ double2 jumps_slow(uint32_t w, double mu, double p0, 
 // Philox layout applies, one-factor path kernels use both normals of a pair) and the
 // divergent jump branch costs one integer compare per step.  Up to eight indices are
 // kept sorted in four registers; a path with more jumps (P = 2e-4 at lambda T = 2)
-// recomputes its indices at every step.  The host selects SCHED while lambda T <= 2.
+// recomputes its indices at every step.  The terminal-only SABR-jump kernel uses the
+// schedule group-wise instead (GROUPJ below).  The host selects SCHED while lambda T <= 2.
 template <int KIND, bool ANTI, int NIMPL, bool PER_STEP, bool SCHED, bool BGEN = false, class Sink>
 __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, State &sa, State &sb,
                                               RngView tab, Sink &&sink) {
