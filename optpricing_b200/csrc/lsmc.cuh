@@ -34,7 +34,7 @@ struct StoreSink {
     }
 };
 
-template <int KIND, bool ANTI, int NIMPL, bool SCHED = false>
+template <int KIND, bool ANTI, int NIMPL, bool SCHED = false, bool BGEN = false>
 __global__ void __launch_bounds__(EURO_THREADS) k_lsmc_paths(const EuroArgs A, double *store,
                                                              int64_t ld) {
     __shared__ RngShared<kind_two_factor(KIND)> tab;
@@ -46,8 +46,8 @@ __global__ void __launch_bounds__(EURO_THREADS) k_lsmc_paths(const EuroArgs A, d
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < A.n_local; g += stride) {
         State sa, sb;
         StoreSink sink{store, ld, g, A.n_local, KIND, ANTI, tv};
-        simulate_draw<KIND, ANTI, NIMPL, true, SCHED>(A, (uint64_t)(A.draw_offset + g), sa, sb, tv,
-                                                      sink);
+        simulate_draw<KIND, ANTI, NIMPL, true, SCHED, BGEN>(A, (uint64_t)(A.draw_offset + g), sa, sb,
+                                                            tv, sink);
     }
 }
 

@@ -793,9 +793,9 @@ extern "C" int optmc_fed_async(optmc_ctx *ctx, const optmc_model *model, double 
 // ---------------------------------------------------------------------------
 // Longstaff-Schwartz
 // ---------------------------------------------------------------------------
-template <int KIND, bool ANTI, int NIMPL, bool SCHED = false>
+template <int KIND, bool ANTI, int NIMPL, bool SCHED = false, bool BGEN = false>
 static int launch_paths_t(optmc_ctx *ctx, EuroArgs &A, double *store, int64_t ld, cudaStream_t st) {
-    auto kern = k_lsmc_paths<KIND, ANTI, NIMPL, SCHED>;
+    auto kern = k_lsmc_paths<KIND, ANTI, NIMPL, SCHED, BGEN>;
     int per_sm = 1;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, EURO_THREADS, 0) != cudaSuccess ||
         per_sm < 1)
@@ -811,11 +811,20 @@ static int launch_paths_t(optmc_ctx *ctx, EuroArgs &A, double *store, int64_t ld
 template <int KIND>
 static int launch_paths_k(optmc_ctx *ctx, EuroArgs &A, bool anti, double *store, int64_t ld,
                           cudaStream_t st) {
+    // SABR kinds on the hand-written maths, beta neither 0 nor 1: the step without the switch
+    bool bgen = false;
+    if constexpr (kind_sabr(KIND))
+        bgen = ctx->normals_impl == 1 && A.c.beta_mode != 1 && A.c.beta_mode != 2;
     if constexpr (kind_jumps(KIND)) {
         if (use_jump_schedule(A) && ctx->jump_schedule) {
             if (ctx->normals_impl == 0)
                 return anti ? launch_paths_t<KIND, true, 0, true>(ctx, A, store, ld, st)
                             : launch_paths_t<KIND, false, 0, true>(ctx, A, store, ld, st);
+            if constexpr (kind_sabr(KIND)) {
+                if (bgen)
+                    return anti ? launch_paths_t<KIND, true, 1, true, true>(ctx, A, store, ld, st)
+                                : launch_paths_t<KIND, false, 1, true, true>(ctx, A, store, ld, st);
+            }
             return anti ? launch_paths_t<KIND, true, 1, true>(ctx, A, store, ld, st)
                         : launch_paths_t<KIND, false, 1, true>(ctx, A, store, ld, st);
         }
@@ -823,6 +832,11 @@ static int launch_paths_k(optmc_ctx *ctx, EuroArgs &A, bool anti, double *store,
     if (ctx->normals_impl == 0)
         return anti ? launch_paths_t<KIND, true, 0>(ctx, A, store, ld, st)
                     : launch_paths_t<KIND, false, 0>(ctx, A, store, ld, st);
+    if constexpr (kind_sabr(KIND)) {
+        if (bgen)
+            return anti ? launch_paths_t<KIND, true, 1, false, true>(ctx, A, store, ld, st)
+                        : launch_paths_t<KIND, false, 1, false, true>(ctx, A, store, ld, st);
+    }
     return anti ? launch_paths_t<KIND, true, 1>(ctx, A, store, ld, st)
                 : launch_paths_t<KIND, false, 1>(ctx, A, store, ld, st);
 }
