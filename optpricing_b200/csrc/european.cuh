@@ -46,6 +46,24 @@ struct EuroArgs {
     double *aux;        // optional, one-factor log models: [W | J | J partner], n_local each
 };
 
+// N(0,1) draws from one Philox call for the jump sizes: x always; y is independent of x
+// only for the one-factor kinds (the two-factor kinds' second output is the mixed one).
+// NIMPL 1: the block's tables -- the first output of the step loop's own normal generator
+// is sqrt(dt) N(0,1) for every kind (the two-factor mixing row (m11, m12) has norm sqrt(dt)
+// in both correlation modes).
+template <int KIND, int NIMPL>
+__device__ __forceinline__ double2 unit_normals(uint4 w, const Consts &c, RngView tab) {
+    double z1, z2;
+    if constexpr (NIMPL == 0) {
+        normal_pair_lib(w.x, w.y, w.z, z1, z2);
+    } else {
+        normal_pair_fast<kind_two_factor(KIND)>(w.x, w.y, w.z, z1, z2, tab);
+        z1 *= c.inv_sqrt_dt;
+        z2 *= c.inv_sqrt_dt;
+    }
+    return make_double2(z1, z2);
+}
+
 // One jump size.  NIMPL 0: CUDA math library.  NIMPL 1: the block's tables -- the first
 // output of the step loop's own normal generator is sqrt(dt) N(0,1) for every kind (the
 // two-factor mixing row (m11, m12) has norm sqrt(dt) in both correlation modes), and
@@ -60,14 +78,7 @@ __device__ __forceinline__ double jump_size(uint4 w, const Consts &c, RngView ta
         else e = 0.5 * neg2_log_u(w.x, w.y, tab);
         return w.w < c.p_up_bits ? e * c.inv_eta1 : -e * c.inv_eta2;
     } else {
-        double z1, z2;
-        if constexpr (NIMPL == 0) {
-            normal_pair_lib(w.x, w.y, w.z, z1, z2);
-        } else {
-            normal_pair_fast<kind_two_factor(KIND)>(w.x, w.y, w.z, z1, z2, tab);
-            z1 *= c.inv_sqrt_dt;
-        }
-        return fma(c.sigma_j, z1, c.mu_j);           // N(mu_j, sigma_j)  (mc_kernels.py:111)
+        return fma(c.sigma_j, unit_normals<KIND, NIMPL>(w, c, tab).x, c.mu_j);   // N(mu_j, sigma_j)  (mc_kernels.py:111)
     }
 }
 
@@ -85,6 +96,26 @@ __device__ __forceinline__ double2 jumps_slow(uint32_t w, double mu, double p0, 
     uint4 e = philox4x32_10(make_uint4(id_lo, id_hi, step, 0xFFu), key);
     int n = poisson_slow(w, e.x, mu, p0);
     double2 acc = make_double2(0.0, 0.0);
+    if constexpr (KIND != OPTMC_KOU) {
+        // n iid N(mu_J, sigma_J^2) sizes sum to N(n mu_J, n sigma_J^2): ONE normal per path and
+        // draw whatever n is -- the same law as the reference's n draws (mc_kernels.py:111-115);
+        // the partner's is independent of it (the second output of the pair for the one-factor
+        // kinds, a second Philox call for the two-factor ones)
+        if (n > 0) {
+            const double nd = (double)n, sd = c.sigma_j * sqrt(nd);
+            const double2 z = unit_normals<KIND, NIMPL>(
+                philox4x32_10(make_uint4(id_lo, id_hi, step, 1u), key), c, tab);
+            acc.x = fma(sd, z.x, nd * c.mu_j);
+            if constexpr (ANTI) {
+                double zb = z.y;
+                if constexpr (kind_two_factor(KIND) || NIMPL == 0)
+                    zb = unit_normals<KIND, NIMPL>(
+                             philox4x32_10(make_uint4(id_lo, id_hi, step, 2u), key), c, tab).x;
+                acc.y = fma(sd, zb, nd * c.mu_j);
+            }
+        }
+        return acc;
+    }
     for (int j = 0; j < n; ++j) {
         acc.x += jump_size<KIND, NIMPL>(
             philox4x32_10(make_uint4(id_lo, id_hi, step, 1u | ((uint32_t)j << 8)), key), c, tab);
