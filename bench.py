@@ -43,7 +43,7 @@ sys.path.insert(0, ROOT)
 # fp64-pipe thread-instructions per path-step of the dominant kernel, counted
 # from the SASS of its step loop (tools/sass_stats.py; see profiles/ and
 # DESIGN.md "Roofline").  Pair-step count / 2 for the antithetic kernels.
-I64_PER_PATH_STEP = {"heston": 16.5, "bsm": 6.0}
+I64_PER_PATH_STEP = {"heston": 16.5, "bsm": 5.5}
 # Algorithmic flops per path-step (antithetic pairs share the draws)
 FLOPS_PER_PATH_STEP = {"heston": 28.0, "bsm": 6.0}
 

@@ -163,6 +163,9 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
     static_assert(!GROUPJ || TWO, "group-wise jumps: one step per Box-Muller pair");
     // terminal-only kernels of the log models defer the deterministic drift
     constexpr bool DEFER = !PER_STEP && !kind_sabr(KIND) && KIND != OPTMC_DUPIRE;
+    // one-factor log models with deferred drift: the partner's Brownian sum is minus the
+    // path's, so the step loop carries one accumulator for both
+    constexpr bool MIRROR = DEFER && !TWO;
     // SABR kinds with the hand-written maths: log-vol form, one exponential per step
     // (BGEN: the host has seen that beta is neither 0 nor 1 -- no switch in the step)
     constexpr int LOGV = (kind_sabr(KIND) && NIMPL == 1) ? (BGEN ? 2 : 1) : 0;
@@ -319,12 +322,13 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
             if constexpr (!LEGACY) after_step(i, slot);
         } else {
             step_diffusion<KIND, DEFER>(sa, z1, 0.0, c, tab, i);
-            if constexpr (ANTI) step_diffusion<KIND, DEFER>(sb, -z1, 0.0, c, tab, i);
+            if constexpr (ANTI && !MIRROR) step_diffusion<KIND, DEFER>(sb, -z1, 0.0, c, tab, i);
             if constexpr (!LEGACY) after_step(i, slot);
             if constexpr (SPC == 2) {
                 if (decltype(whole)::value || i + 1 < A.n_steps) {
                     step_diffusion<KIND, DEFER>(sa, z2, 0.0, c, tab, i + 1);
-                    if constexpr (ANTI) step_diffusion<KIND, DEFER>(sb, -z2, 0.0, c, tab, i + 1);
+                    if constexpr (ANTI && !MIRROR)
+                        step_diffusion<KIND, DEFER>(sb, -z2, 0.0, c, tab, i + 1);
                     after_step(i + 1, slot);
                 }
             }
@@ -484,7 +488,10 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
         }
     }
     finish_deferred<KIND, DEFER>(sa, c);
-    if constexpr (ANTI) finish_deferred<KIND, DEFER>(sb, c);
+    if constexpr (ANTI) {
+        if constexpr (MIRROR) sb.x = -sa.v;       // sa.v: the Brownian sum W kept by finish_deferred(sa)
+        finish_deferred<KIND, DEFER>(sb, c);
+    }
 }
 
 struct NoSink {
