@@ -319,3 +319,34 @@ def test_price_frame_validates_without_a_gpu():
         t.price_frame(bad, stock, ob.BSMModel(), rate)
     empty = pd.DataFrame({"strike": [], "maturity": [], "optionType": []})
     assert t.price_frame(empty, stock, ob.BSMModel(), rate).shape == (0,)
+
+
+def test_box_muller_log_table_needs_its_floor_at_zero():
+    """Why normal_parts_fast floors -2 ln u at 0 (csrc/philox.cuh): an exact emulation of the
+    512-entry table + degree-4 polynomial (neg2_log_poly, same constants, fused multiply-adds
+    in exact rational arithmetic) returns about -2e-16 instead of +2e-16 for the two largest
+    uniforms of the top binade -- and a negative radicand would turn the one-correction square
+    root into -inf.  Everywhere else in that bucket the value is positive."""
+    from fractions import Fraction as F
+
+    def fma(a, b, c):
+        return float(F(a) * F(b) + F(c))
+
+    log_n, c_1_12, c_n2ln2 = 512, 1.0 / 12.0, -1.3862943611198906188
+
+    def neg2_log(m, kfac):
+        i = int((m - 1.0) * log_n)
+        c = 1.0 + (i + 0.5) / log_n
+        tx, ty = -2.0 / c, -2.0 * math.log(c) + 24.0 * math.log(2.0)       # optmc.cu: RngBase.logt
+        r = fma(m, tx, 2.0)
+        p = fma(r, 0.03125, c_1_12)
+        p = fma(p, r, 0.25)
+        p = fma(p, r, 1.0)
+        return fma(p, r, fma(kfac, c_n2ln2, ty))
+
+    top = [neg2_log(2.0 - k * 2.0 ** -52, 11.0) for k in (1, 2)]           # u = 1 - k 2^-53
+    assert all(-1e-15 < v < 0.0 for v in top), top
+    rest = [neg2_log(2.0 - k * 2.0 ** -52, 11.0) for k in list(range(3, 400)) + [2 ** j for j in range(9, 43)]]
+    assert min(rest) > 0.0
+    for v, k in zip(rest, list(range(3, 400)) + [2 ** j for j in range(9, 43)]):
+        assert v == pytest.approx(-2.0 * math.log1p(-k * 2.0 ** -53), abs=1e-15)
