@@ -126,7 +126,7 @@ extern "C" int optmc_ctx_create(int device, optmc_ctx **out) {
             double c = 1.0 + (i + 0.5) / LOG_N;
             h->logt[i] = make_double2(-2.0 / c, -2.0 * std::log(c) + 24.0 * std::log(2.0));
         }
-        for (int j = 0; j < 32; ++j) h->exp2t[j] = std::exp2(j / 32.0);
+        for (int j = 0; j < EXP_N; ++j) h->exp2t[j] = std::exp2(j / (double)EXP_N);
         for (int i = 0; i < TRIG_N; ++i) {
             double a = (i + 0.5) * (2.0 * pi / TRIG_N);
             h->trig[i] = make_double2(std::cos(a), std::sin(a));

@@ -153,14 +153,15 @@ __device__ __forceinline__ uint32_t keep_u32(uint32_t x) {
 // ---------------------------------------------------------------------------
 constexpr int LOG_N = 512;     // buckets of [1,2) for ln
 constexpr int TRIG_N = 1024;   // angle buckets over the full circle
+constexpr int EXP_N = 512;     // 2^(j/512) for exp
 
 // Host-filled base tables (one copy per context, in global memory).
 struct RngBase {
     // bucket i has midpoint c_i = 1 + (i + .5)/512;
     //   x = -2 / c_i,  y = -2 ln c_i + 24 ln 2   (the 24 ln 2 pre-pays the exponent offset)
     double2 logt[LOG_N];
-    // 2^(j/32), j = 0..31
-    double exp2t[32];
+    // 2^(j/512), j = 0..511
+    double exp2t[EXP_N];
     // angle bucket i of [0, 2 pi): a_i = (i + .5) 2 pi / 1024;  x = cos a_i, y = sin a_i
     double2 trig[TRIG_N];
 };
@@ -170,10 +171,10 @@ __device__ RngBase g_rng_base;
 // (fast_log / fast_exp) -- the RNG tables extend it.
 struct MathShared {
     double2 logt[LOG_N];
-    double exp2t[32];
+    double exp2t[EXP_N];
 };
 constexpr uint32_t EXP_OFF = (uint32_t)sizeof(double2) * LOG_N;
-constexpr uint32_t TRIG_OFF = EXP_OFF + 32u * (uint32_t)sizeof(double);
+constexpr uint32_t TRIG_OFF = EXP_OFF + (uint32_t)EXP_N * (uint32_t)sizeof(double);
 
 // Per-block shared-memory tables.  The trig rows are specialised per launch:
 //   MIXED = false: (s cos a_i, s sin a_i) with a scale s (sqrt(dt) for the
@@ -196,7 +197,7 @@ struct RngView {
 
 __device__ __forceinline__ RngView fill_math_shared(MathShared *t) {
     for (int i = threadIdx.x; i < LOG_N; i += blockDim.x) t->logt[i] = g_rng_base.logt[i];
-    for (int i = threadIdx.x; i < 32; i += blockDim.x) t->exp2t[i] = g_rng_base.exp2t[i];
+    for (int i = threadIdx.x; i < EXP_N; i += blockDim.x) t->exp2t[i] = g_rng_base.exp2t[i];
     RngView v;
     v.base = keep_u32((uint32_t)__cvta_generic_to_shared(t));
     return v;
@@ -295,30 +296,27 @@ __device__ __forceinline__ double fast_log(double s, RngView t) {
     return fma((double)((hi >> 20) - 1023 + 12), C_LN2, -0.5 * q);
 }
 
-// e^x for |x| < 700: x = (32 k + j) ln2/32 + r, |r| <= ln2/64;
-// e^x = 2^k * 2^(j/32) * e^r with a degree-6 polynomial.  11 fp64-pipe
-// instructions (CUDA's exp: ~18 plus range branches); rel. error <= 5e-16 for |x| <= 10.
-__constant__ double C_EXP[6] = {46.166241308446828384,          // 32 / ln 2
-                                -0.021660849392498290395,        // -(ln2/32) high part (27 bits)
-                                0.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0};
-#define OPTMC_LN2_32_HI 0x1.62e42fcp-6     /* ln2/32 with the low 26 mantissa bits cleared */
-#define OPTMC_LN2_32_LO (0.021660849392498290395 - OPTMC_LN2_32_HI)
-#define OPTMC_SHORT_1_720 0x1.6c16cp-10    /* 1/720 to 20 bits: multiplies r^6 <= 1.6e-12 */
+// e^x for |x| < 700: x = (512 k + j) ln2/512 + r, |r| <= ln2/1024 = 6.8e-4;
+// e^x = 2^k * 2^(j/512) * e^r with a degree-4 polynomial (r^5/120 < 1.2e-18).  9 fp64-pipe
+// instructions (CUDA's exp: ~18 plus range branches; a 32-entry table needs degree 6 and
+// 11); rel. error <= 3.2e-16 (exact emulation over |x| <= 700).
+__constant__ double C_EXP[3] = {738.65986093514929,              // 512 / ln 2
+                                1.0 / 24.0, 1.0 / 6.0};
+#define OPTMC_LN2_N_HI 0x1.62e42fcp-10     /* ln2/512 with the low 26 mantissa bits cleared */
+#define OPTMC_LN2_N_LO 1.0831887298761837e-11
 __device__ __forceinline__ double fast_exp(double x, RngView t) {
     const double MAGIC = 6755399441055744.0;          // 1.5 * 2^52: low word = rint(value)
     double tt = fma(x, C_EXP[0], MAGIC);
     int n = __double2loint(tt);
     double nd = tt - MAGIC;
-    double r = fma(nd, -OPTMC_LN2_32_HI, x);
-    r = fma(nd, -OPTMC_LN2_32_LO, r);
-    double p = fma(r, OPTMC_SHORT_1_720, C_EXP[3]);
-    p = fma(p, r, C_EXP[4]);
-    p = fma(p, r, C_EXP[5]);
+    double r = fma(nd, -OPTMC_LN2_N_HI, x);
+    r = fma(nd, -OPTMC_LN2_N_LO, r);
+    double p = fma(r, C_EXP[1], C_EXP[2]);
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    double y = p * lds_f64(t.base + EXP_OFF + ((uint32_t)(n & 31) << 3));
-    return __hiloint2double(__double2hiint(y) + ((n >> 5) << 20), __double2loint(y));
+    double y = p * lds_f64(t.base + EXP_OFF + ((uint32_t)(n & (EXP_N - 1)) << 3));
+    return __hiloint2double(__double2hiint(y) + ((n >> 9) << 20), __double2loint(y));
 }
 
 // Baseline pair by the CUDA math library (also the jump-size path).
