@@ -51,13 +51,13 @@ struct EuroArgs {
 // NIMPL 1: the block's tables -- the first output of the step loop's own normal generator
 // is sqrt(dt) N(0,1) for every kind (the two-factor mixing row (m11, m12) has norm sqrt(dt)
 // in both correlation modes).
-template <int KIND, int NIMPL>
-__device__ __forceinline__ double2 unit_normals(uint4 w, const Consts &c, RngView tab) {
+template <int KIND, int NIMPL, class V>
+__device__ __forceinline__ double2 unit_normals(uint4 w, const Consts &c, V tab) {
     double z1, z2;
     if constexpr (NIMPL == 0) {
-        normal_pair_lib(w.x, w.y, w.z, z1, z2);
+        normal_pair_lib2(w.x, w.y, z1, z2);
     } else {
-        normal_pair_fast<kind_two_factor(KIND)>(w.x, w.y, w.z, z1, z2, tab);
+        normal_pair_fast<kind_two_factor(KIND)>(w.x, w.y, z1, z2, tab);
         z1 *= c.inv_sqrt_dt;
         z2 *= c.inv_sqrt_dt;
     }
@@ -69,8 +69,8 @@ __device__ __forceinline__ double2 unit_normals(uint4 w, const Consts &c, RngVie
 // two-factor mixing row (m11, m12) has norm sqrt(dt) in both correlation modes), and
 // -ln u comes from the log table.  With lambda T of order one most warps reach this
 // epilogue, so it is not as rare as a single step's jump.
-template <int KIND, int NIMPL>
-__device__ __forceinline__ double jump_size(uint4 w, const Consts &c, RngView tab) {
+template <int KIND, int NIMPL, class V>
+__device__ __forceinline__ double jump_size(uint4 w, const Consts &c, V tab) {
     if constexpr (KIND == OPTMC_KOU) {
         // up w.p. p_up: +Exp(eta1), else -Exp(eta2)   (mc_kernels.py:314-317)
         double e;
@@ -89,10 +89,10 @@ __device__ __forceinline__ double jump_size(uint4 w, const Consts &c, RngView ta
 // passed by reference.  Inlined on purpose: an out-of-line call would force the
 // kernel parameters (constants, Philox key) to be copied to local memory so that
 // their address can be taken.
-template <int KIND, bool ANTI, int NIMPL = 0>
+template <int KIND, bool ANTI, int NIMPL = 0, class V = RngView>
 __device__ __forceinline__ double2 jumps_slow(uint32_t w, double mu, double p0, const PhiloxKey &key,
                                            uint32_t id_lo, uint32_t id_hi, uint32_t step,
-                                           const Consts &c, RngView tab = RngView{0u}) {
+                                           const Consts &c, V tab = V{0u}) {
     uint4 e = philox4x32_10(make_uint4(id_lo, id_hi, step, 0xFFu), key);
     int n = poisson_slow(w, e.x, mu, p0);
     double2 acc = make_double2(0.0, 0.0);
@@ -140,9 +140,10 @@ __device__ __forceinline__ double2 jumps_slow(uint32_t w, double mu, double p0, 
 // kept sorted in four registers; a path with more jumps (P = 2e-4 at lambda T = 2)
 // recomputes its indices at every step.  The terminal-only SABR-jump kernel uses the
 // schedule group-wise instead (GROUPJ below).  The host selects SCHED while lambda T <= 2.
-template <int KIND, bool ANTI, int NIMPL, bool PER_STEP, bool SCHED, bool BGEN = false, class Sink>
+template <int KIND, bool ANTI, int NIMPL, bool PER_STEP, bool SCHED, bool BGEN = false, class V,
+          class Sink>
 __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, State &sa, State &sb,
-                                              RngView tab, Sink &&sink) {
+                                              V tab, Sink &&sink) {
     const Consts &c = A.c;
     constexpr bool TWO = kind_two_factor(KIND);
     constexpr bool JUMPS = kind_jumps(KIND);
@@ -287,16 +288,16 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
         if constexpr (PER_STEP) sink(i, sa, sb);
     };
 
-    // One Box-Muller pair (three Philox words: 64 bits of radius, 32 of angle) and the
-    // SPC steps it feeds, starting at step i.
+    // One Box-Muller pair (two Philox words, philox.cuh) and the SPC steps it feeds,
+    // starting at step i.
     // `whole` (a std::bool_constant): the caller knows that step i + 1 exists too
-    auto advance = [&](uint32_t w0, uint32_t w1, uint32_t w2, int i, auto whole, auto slot) {
+    auto advance = [&](uint32_t wa, uint32_t wb, int i, auto whole, auto slot) {
         // (z1, z2): two-factor models -- the mixed, scaled increments (dW_S, xi-weighted
         // dW_v); one-factor models -- sqrt(dt) N(0,1) for this step and the next.
         // Heston / Bates on the hand-written maths: the parts of the pair, one root per path
         if constexpr (NIMPL == 1 && (KIND == OPTMC_HESTON || KIND == OPTMC_BATES)) {
             double L, t1, t2;
-            normal_parts_fast<true>(w0, w1, w2, L, t1, t2, tab);
+            normal_parts_fast<true>(wa, wb, L, t1, t2, tab);
             step_heston_parts<DEFER>(sa, L, t1, t2, c);
             if constexpr (ANTI) step_heston_parts<DEFER>(sb, L, -t1, -t2, c);
             if constexpr (!LEGACY) after_step(i, slot);
@@ -305,7 +306,7 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
         double z1, z2;
         if constexpr (NIMPL == 0) {
             double a, b;
-            normal_pair_lib(w0, w1, w2, a, b);
+            normal_pair_lib2(wa, wb, a, b);
             if constexpr (TWO) {
                 z1 = fma(c.m12, b, c.m11 * a);
                 z2 = fma(c.m22, b, c.m21 * a);
@@ -314,7 +315,7 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
                 z2 = c.sqrt_dt * b;
             }
         } else {
-            normal_pair_fast<TWO>(w0, w1, w2, z1, z2, tab);
+            normal_pair_fast<TWO>(wa, wb, z1, z2, tab);
         }
         if constexpr (TWO) {
             step_diffusion<KIND, DEFER, LOGV>(sa, z1, z2, c, tab, i);
@@ -337,8 +338,8 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
     constexpr std::true_type WHOLE{};
     constexpr std::false_type RAGGED{};
     constexpr std::integral_constant<int, -1> NOSLOT{};
-    // Without a Poisson word per step all 128 bits of a Philox call are used:
-    // three calls (c2 = 3g, 3g+1, 3g+2) feed four pairs, see philox_pair_words.
+    // Without a Poisson word per step all 128 bits of a Philox call are used: call g feeds
+    // pairs 2g = (x, y) and 2g + 1 = (z, w), see philox_pair_words.
     if constexpr (GROUPJ) {
         // The warp finds the first group of four steps in which one of its paths jumps (one
         // min-reduction), runs the groups before it through the jump-free body -- a loop with a
@@ -351,16 +352,15 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
         while (i < A.n_steps) {
             const uint32_t hit_group = __reduce_min_sync(lanes, nxt >> 2);
             const int stop = (int)min((uint64_t)A.n_steps, (uint64_t)hit_group * 4u);
-            for (; i < stop; i += 4, call += 3) {
+            for (; i < stop; i += 4, call += 2) {
                 const uint4 a = philox4x32_10(make_uint4(id_lo, id_hi, call, 0u), A.key);
-                advance(a.x, a.y, a.z, i, RAGGED, NOSLOT);
+                advance(a.x, a.y, i, RAGGED, NOSLOT);
                 if (i + 1 < A.n_steps) {
-                    const uint4 b = philox4x32_10(make_uint4(id_lo, id_hi, call + 1u, 0u), A.key);
-                    advance(a.w, b.x, b.y, i + 1, RAGGED, NOSLOT);
+                    advance(a.z, a.w, i + 1, RAGGED, NOSLOT);
                     if (i + 2 < A.n_steps) {
-                        const uint4 d = philox4x32_10(make_uint4(id_lo, id_hi, call + 2u, 0u), A.key);
-                        advance(b.z, b.w, d.x, i + 2, RAGGED, NOSLOT);
-                        if (i + 3 < A.n_steps) advance(d.y, d.z, d.w, i + 3, RAGGED, NOSLOT);
+                        const uint4 b = philox4x32_10(make_uint4(id_lo, id_hi, call + 1u, 0u), A.key);
+                        advance(b.x, b.y, i + 2, RAGGED, NOSLOT);
+                        if (i + 3 < A.n_steps) advance(b.z, b.w, i + 3, RAGGED, NOSLOT);
                     }
                 }
             }
@@ -368,105 +368,69 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
             group_jumps(i);
             {
                 const uint4 a = philox4x32_10(make_uint4(id_lo, id_hi, call, 0u), A.key);
-                advance(a.x, a.y, a.z, i, RAGGED, std::integral_constant<int, 0>{});
+                advance(a.x, a.y, i, RAGGED, std::integral_constant<int, 0>{});
                 if (i + 1 < A.n_steps) {
-                    const uint4 b = philox4x32_10(make_uint4(id_lo, id_hi, call + 1u, 0u), A.key);
-                    advance(a.w, b.x, b.y, i + 1, RAGGED, std::integral_constant<int, 1>{});
+                    advance(a.z, a.w, i + 1, RAGGED, std::integral_constant<int, 1>{});
                     if (i + 2 < A.n_steps) {
-                        const uint4 d = philox4x32_10(make_uint4(id_lo, id_hi, call + 2u, 0u), A.key);
-                        advance(b.z, b.w, d.x, i + 2, RAGGED, std::integral_constant<int, 2>{});
+                        const uint4 b = philox4x32_10(make_uint4(id_lo, id_hi, call + 1u, 0u), A.key);
+                        advance(b.x, b.y, i + 2, RAGGED, std::integral_constant<int, 2>{});
                         if (i + 3 < A.n_steps)
-                            advance(d.y, d.z, d.w, i + 3, RAGGED, std::integral_constant<int, 3>{});
+                            advance(b.z, b.w, i + 3, RAGGED, std::integral_constant<int, 3>{});
                     }
                 }
             }
             i += 4;
-            call += 3;
+            call += 2;
         }
     } else if constexpr (SCHEDULED) {
-        // one copy of the step body (it carries the inlined jump code): the twelve words of
-        // three calls are handed out pair by pair
+        // one copy of the step body (it carries the inlined jump code): the four words of a
+        // call are handed out pair by pair
         uint32_t call = 0;
-        uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a, d = a;
-        int slot = 0;
+        uint4 a = make_uint4(0u, 0u, 0u, 0u);
+        bool second = false;
 #pragma unroll 1
-        for (int i = 0; i < A.n_steps; i += SPC, slot = (slot + 1) & 3) {
-            uint32_t w0, w1, w2;
-            if (slot == 0) {
-                a = philox4x32_10(make_uint4(id_lo, id_hi, call, 0u), A.key);
-                w0 = a.x; w1 = a.y; w2 = a.z;
-            } else if (slot == 1) {
-                b = philox4x32_10(make_uint4(id_lo, id_hi, call + 1u, 0u), A.key);
-                w0 = a.w; w1 = b.x; w2 = b.y;
-            } else if (slot == 2) {
-                d = philox4x32_10(make_uint4(id_lo, id_hi, call + 2u, 0u), A.key);
-                w0 = b.z; w1 = b.w; w2 = d.x;
+        for (int i = 0; i < A.n_steps; i += SPC, second = !second) {
+            uint32_t wa, wb;
+            if (!second) {
+                a = philox4x32_10(make_uint4(id_lo, id_hi, call++, 0u), A.key);
+                wa = a.x; wb = a.y;
             } else {
-                w0 = d.y; w1 = d.z; w2 = d.w;
-                call += 3;
+                wa = a.z; wb = a.w;
             }
-            advance(w0, w1, w2, i, RAGGED, NOSLOT);
+            advance(wa, wb, i, RAGGED, NOSLOT);
         }
     } else if constexpr (!LEGACY && TWO) {
-        // (the bounds tests between the pairs also keep the compiler from hoisting all three
-        // Philox calls to the top of the group: without them the two-factor loops measured
-        // 1.5 - 2.5 % slower, the one-factor loops below 1 - 7 % faster)
+        // (the bounds test between the pairs also keeps the compiler from hoisting the next
+        // Philox call to the top of the group)
         uint32_t call = 0;
         OPTMC_UNROLL_STEPS
-        for (int i = 0; i < A.n_steps; i += 4 * SPC, call += 3) {
+        for (int i = 0; i < A.n_steps; i += 2, ++call) {
             const uint4 a = philox4x32_10(make_uint4(id_lo, id_hi, call, 0u), A.key);
-            advance(a.x, a.y, a.z, i, RAGGED, NOSLOT);
-            if (i + SPC < A.n_steps) {
-                const uint4 b = philox4x32_10(make_uint4(id_lo, id_hi, call + 1u, 0u), A.key);
-                advance(a.w, b.x, b.y, i + SPC, RAGGED, NOSLOT);
-                if (i + 2 * SPC < A.n_steps) {
-                    const uint4 d = philox4x32_10(make_uint4(id_lo, id_hi, call + 2u, 0u), A.key);
-                    advance(b.z, b.w, d.x, i + 2 * SPC, RAGGED, NOSLOT);
-                    if (i + 3 * SPC < A.n_steps) advance(d.y, d.z, d.w, i + 3 * SPC, RAGGED, NOSLOT);
-                }
-            }
+            advance(a.x, a.y, i, RAGGED, NOSLOT);
+            if (i + 1 < A.n_steps) advance(a.z, a.w, i + 1, RAGGED, NOSLOT);
         }
     } else if constexpr (!LEGACY) {
-        // one-factor models: whole groups of eight steps without a single bounds test, then
-        // the ragged rest (n_steps % 8 steps) one pair at a time through one more copy of the step
-        constexpr int GS = 4 * SPC;
+        // one-factor models: whole groups of four steps without a single bounds test, then
+        // the ragged rest (n_steps % 4 steps) through one more call
+        constexpr int GS = 2 * SPC;
         uint32_t call = 0;
         int i = 0;
         OPTMC_UNROLL_STEPS
-        for (; i + GS <= A.n_steps; i += GS, call += 3) {
+        for (; i + GS <= A.n_steps; i += GS, ++call) {
             const uint4 a = philox4x32_10(make_uint4(id_lo, id_hi, call, 0u), A.key);
-            advance(a.x, a.y, a.z, i, WHOLE, NOSLOT);
-            const uint4 b = philox4x32_10(make_uint4(id_lo, id_hi, call + 1u, 0u), A.key);
-            advance(a.w, b.x, b.y, i + SPC, WHOLE, NOSLOT);
-            const uint4 d = philox4x32_10(make_uint4(id_lo, id_hi, call + 2u, 0u), A.key);
-            advance(b.z, b.w, d.x, i + 2 * SPC, WHOLE, NOSLOT);
-            advance(d.y, d.z, d.w, i + 3 * SPC, WHOLE, NOSLOT);
+            advance(a.x, a.y, i, WHOLE, NOSLOT);
+            advance(a.z, a.w, i + SPC, WHOLE, NOSLOT);
         }
         if (i < A.n_steps) {
-            uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a, d = a;
-#pragma unroll 1
-            for (int slot = 0; i < A.n_steps; ++slot, i += SPC) {     // at most four pairs
-                uint32_t w0, w1, w2;
-                if (slot == 0) {
-                    a = philox4x32_10(make_uint4(id_lo, id_hi, call, 0u), A.key);
-                    w0 = a.x; w1 = a.y; w2 = a.z;
-                } else if (slot == 1) {
-                    b = philox4x32_10(make_uint4(id_lo, id_hi, call + 1u, 0u), A.key);
-                    w0 = a.w; w1 = b.x; w2 = b.y;
-                } else if (slot == 2) {
-                    d = philox4x32_10(make_uint4(id_lo, id_hi, call + 2u, 0u), A.key);
-                    w0 = b.z; w1 = b.w; w2 = d.x;
-                } else {
-                    w0 = d.y; w1 = d.z; w2 = d.w;
-                }
-                advance(w0, w1, w2, i, RAGGED, NOSLOT);
-            }
+            const uint4 a = philox4x32_10(make_uint4(id_lo, id_hi, call, 0u), A.key);
+            advance(a.x, a.y, i, RAGGED, NOSLOT);
+            if (i + SPC < A.n_steps) advance(a.z, a.w, i + SPC, RAGGED, NOSLOT);
         }
     } else {
         OPTMC_UNROLL_STEPS
         for (int i = 0; i < A.n_steps; ++i) {
             const uint4 w = philox4x32_10(make_uint4(id_lo, id_hi, (uint32_t)i, 0u), A.key);
-            advance(w.x, w.y, w.z, i, RAGGED, NOSLOT);
+            advance(w.x, w.y, i, RAGGED, NOSLOT);
             if (__builtin_expect(poisson_maybe(w.w, A.pois_p0_bits[0]), 0)) {
                 double2 J = jumps_slow<KIND, ANTI, NIMPL>(w.w, A.pois_mu[0], A.pois_p0[0], A.key,
                                                           id_lo, id_hi, (uint32_t)i, c, tab);
@@ -514,6 +478,39 @@ __host__ __device__ constexpr int euro_min_blocks(int kind, int nimpl, bool sche
 #endif
 }
 
+// What one simulated draw adds to the block's five running sums (and to the optional
+// terminal / aux arrays): payoff of the draw and its partner, the control (mean terminal spot).
+template <int KIND, bool ANTI>
+__device__ __forceinline__ void accumulate_draw(const EuroArgs &A, int64_t g, const State &sa,
+                                                const State &sb, double (&acc)[5]) {
+    if constexpr (!kind_two_factor(KIND) && KIND != OPTMC_DUPIRE) {
+        // log S_T = log S_0 + n drift(sigma) + sigma W + J: W and J do not depend on sigma,
+        // so sigma-bumped prices (vega) can be read off this one simulation
+        if (A.aux) {
+            A.aux[g] = sa.v;
+            A.aux[A.n_local + g] = sa.w;
+            if constexpr (ANTI) A.aux[2 * A.n_local + g] = sb.w;
+        }
+    }
+    double ST = terminal_spot(KIND, sa);
+    double pay = A.is_call ? ST - A.strike : A.strike - ST;   // monte_carlo.py:110-114
+    pay = fmax(pay, 0.0);
+    double ctl = ST;
+    if (A.terminal) A.terminal[g] = ST;
+    if constexpr (ANTI) {
+        double STb = terminal_spot(KIND, sb);
+        double payb = A.is_call ? STb - A.strike : A.strike - STb;
+        pay = 0.5 * (pay + fmax(payb, 0.0));
+        ctl = 0.5 * (ST + STb);
+        if (A.terminal) A.terminal[A.n_local + g] = STb;
+    }
+    acc[0] += pay;
+    acc[1] = fma(pay, pay, acc[1]);
+    acc[2] += ctl;
+    acc[3] = fma(ctl, ctl, acc[3]);
+    acc[4] = fma(pay, ctl, acc[4]);
+}
+
 template <int KIND, bool ANTI, int NIMPL, bool SCHED = false, bool BGEN = false>
 __global__ void __launch_bounds__(EURO_THREADS, euro_min_blocks(KIND, NIMPL, SCHED))
 k_european(const EuroArgs A) {
@@ -529,32 +526,47 @@ k_european(const EuroArgs A) {
         State sa, sb;
         simulate_draw<KIND, ANTI, NIMPL, false, SCHED, BGEN>(A, (uint64_t)(A.draw_offset + g), sa, sb, tv,
                                                        NoSink{});
-        if constexpr (!kind_two_factor(KIND) && KIND != OPTMC_DUPIRE) {
-            // log S_T = log S_0 + n drift(sigma) + sigma W + J: W and J do not depend on sigma,
-            // so sigma-bumped prices (vega) can be read off this one simulation
-            if (A.aux) {
-                A.aux[g] = sa.v;
-                A.aux[A.n_local + g] = sa.w;
-                if constexpr (ANTI) A.aux[2 * A.n_local + g] = sb.w;
-            }
-        }
-        double ST = terminal_spot(KIND, sa);
-        double pay = A.is_call ? ST - A.strike : A.strike - ST;   // monte_carlo.py:110-114
-        pay = fmax(pay, 0.0);
-        double ctl = ST;
-        if (A.terminal) A.terminal[g] = ST;
-        if constexpr (ANTI) {
-            double STb = terminal_spot(KIND, sb);
-            double payb = A.is_call ? STb - A.strike : A.strike - STb;
-            pay = 0.5 * (pay + fmax(payb, 0.0));
-            ctl = 0.5 * (ST + STb);
-            if (A.terminal) A.terminal[A.n_local + g] = STb;
-        }
-        acc[0] += pay;
-        acc[1] = fma(pay, pay, acc[1]);
-        acc[2] += ctl;
-        acc[3] = fma(ctl, ctl, acc[3]);
-        acc[4] = fma(pay, ctl, acc[4]);
+        accumulate_draw<KIND, ANTI>(A, g, sa, sb, acc);
+    }
+    block_sum<5>(acc, scratch);
+    if (threadIdx.x == 0) {
+        double *p = A.partials + (size_t)blockIdx.x * NPART;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) p[k] = acc[k];
+    }
+}
+
+// The same kernel on the lane-replicated tables (philox.cuh: RngViewT<8>): ONE block per SM --
+// 768 threads for Heston / Bates (85 registers), 1024 for the one-factor models (64) -- whose
+// warps share 128 / 192 KB of conflict-free tables in dynamic shared memory.  The models that
+// also need the exp table inside the step loop (the SABR kinds) stay on k_european.
+__host__ __device__ constexpr bool kind_wide(int kind) {
+    return kind == OPTMC_BSM || kind == OPTMC_MERTON || kind == OPTMC_KOU || kind == OPTMC_HESTON ||
+           kind == OPTMC_BATES;
+}
+__host__ __device__ constexpr int wide_threads(int kind) {
+#ifdef OPTMC_WIDE_THREADS
+    return OPTMC_WIDE_THREADS;
+#else
+    return kind_two_factor(kind) ? 768 : 1024;
+#endif
+}
+
+template <int KIND, bool ANTI>
+__global__ void __launch_bounds__(wide_threads(KIND), 1) k_european_wide(const EuroArgs A) {
+    static_assert(kind_wide(KIND), "no exp table in the lane-replicated layout");
+    extern __shared__ __align__(16) unsigned char wide_smem[];
+    __shared__ double scratch[5 * 32];
+    const RngViewW tv = fill_rng_wide<kind_two_factor(KIND)>(
+        wide_smem, kind_two_factor(KIND) ? A.c.m11 : A.c.sqrt_dt, A.c.m12, A.c.m21, A.c.m22);
+    __syncthreads();
+    double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < A.n_local; g += stride) {
+        State sa, sb;
+        simulate_draw<KIND, ANTI, 1, false, false, false>(A, (uint64_t)(A.draw_offset + g), sa, sb,
+                                                          tv, NoSink{});
+        accumulate_draw<KIND, ANTI>(A, g, sa, sb, acc);
     }
     block_sum<5>(acc, scratch);
     if (threadIdx.x == 0) {

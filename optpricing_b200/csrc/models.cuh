@@ -114,8 +114,11 @@ __device__ __forceinline__ void step_heston_parts(State &s, double L, double t1,
     double vp = relu64(s.v);
     // v_sqrt * radius, to the accuracy the Box-Muller radius always had here (one Newton
     // correction, rel. 1e-12: a perturbation of a N(0,1) draw no price can see); the
-    // fed-draw parity kernels take step_heston with its < 1 ulp root
-    double rq = sqrt_nonneg_fast(vp * L);
+    // fed-draw parity kernels take step_heston with its < 1 ulp root.
+    // The 1e-290 keeps the seed finite where v+ L is 0 (v+ = 0 is common when Feller's
+    // condition fails): the root comes out at 1e-145 instead of 0, for one FMA where a
+    // product plus an integer clamp stood.
+    double rq = sqrt_pos_fast(fma(vp, L, C_TINY));
     if constexpr (DEFER) {
         s.x = fma(rq, t1, s.x);
         s.w += vp;
@@ -152,7 +155,8 @@ __device__ __forceinline__ void step_dupire(State &s, double dw, int i, const Co
 
 // s_pos ** beta (mc_kernels.py:211): exp(beta ln s) on the table-driven helpers,
 // with the exact special cases beta in {1, 0, 1/2}.
-__device__ __forceinline__ double sabr_pow(double s_pos, const Consts &c, RngView t) {
+template <class V>
+__device__ __forceinline__ double sabr_pow(double s_pos, const Consts &c, V t) {
     switch (c.beta_mode) {
         case 1: return s_pos;
         case 2: return 1.0;
@@ -184,9 +188,8 @@ __device__ __forceinline__ double floor_neg650(double a) {
 // LOGV: 0 = literal form; 1 = log-vol form, beta_mode read at run time; 2 = log-vol form
 // for a beta that is neither 0 nor 1, chosen by the host -- the step loop then carries one
 // code path instead of three and no switch.
-template <int LOGV>
-__device__ __forceinline__ void step_sabr(State &s, double z1, double cz, const Consts &c,
-                                          RngView t) {
+template <int LOGV, class V>
+__device__ __forceinline__ void step_sabr(State &s, double z1, double cz, const Consts &c, V t) {
     if constexpr (LOGV != 0) {
         const double s_pos = floor_1e8(s.x);
         double coef;
@@ -217,9 +220,9 @@ __device__ __forceinline__ void mix_fed(int kind, double dw1, double dw2, const 
     if (kind == OPTMC_HESTON || kind == OPTMC_BATES) cz *= c.xi;
 }
 
-template <int KIND, bool DEFER = false, int LOGV = 0>
+template <int KIND, bool DEFER = false, int LOGV = 0, class V = RngView>
 __device__ __forceinline__ void step_diffusion(State &s, double z1, double cz, const Consts &c,
-                                               RngView t, int i) {
+                                               V t, int i) {
     if constexpr (KIND == OPTMC_DUPIRE)
         step_dupire(s, z1, i, c);
     else if constexpr (KIND == OPTMC_HESTON || KIND == OPTMC_BATES)
@@ -256,7 +259,8 @@ __device__ __forceinline__ double terminal_spot(int kind, const State &s) {
 }
 
 // Spot after a step, for the path kernels (path_kernels.py:34: paths[:, i+1] = exp(log_s))
-__device__ __forceinline__ double step_spot(int kind, const State &s, RngView t) {
+template <class V>
+__device__ __forceinline__ double step_spot(int kind, const State &s, V t) {
     return kind_sabr(kind) ? s.x : fast_exp(s.x, t);
 }
 

@@ -26,6 +26,7 @@ struct optmc_ctx {
     int normals_impl = 1;       // 0: CUDA math library, 1: hand-written (philox.cuh)
     int euro_blocks_per_sm = 0; // 0: occupancy API decides
     int euro_threads = EURO_THREADS;
+    int euro_wide = 1;          // 1: lane-replicated tables, one block per SM (k_european_wide)
     int lsmc_mode = 1;          // 1: one persistent launch for all dates, 0: one launch per date
     int jump_schedule = 1;      // 1: pre-drawn jump schedule where it applies, 0: Poisson word per step
     int fed_stream = 1;         // 1: k_fed_stream for the models without jumps, 0: tiled k_fed for all
@@ -124,12 +125,14 @@ extern "C" int optmc_ctx_create(int device, optmc_ctx **out) {
         const double pi = 3.14159265358979323846;
         for (int i = 0; i < LOG_N; ++i) {
             double c = 1.0 + (i + 0.5) / LOG_N;
-            h->logt[i] = make_double2(-2.0 / c, -2.0 * std::log(c) + 24.0 * std::log(2.0));
+            h->logt[i] = make_double2(-2.0 / c, -2.0 * std::log(c) + 64.0 * std::log(2.0));
         }
         for (int j = 0; j < EXP_N; ++j) h->exp2t[j] = std::exp2(j / (double)EXP_N);
-        for (int i = 0; i < TRIG_N; ++i) {
-            double a = (i + 0.5) * (2.0 * pi / TRIG_N);
-            h->trig[i] = make_double2(std::cos(a), std::sin(a));
+        for (int i = 0; i < ANG_N; ++i) {
+            const double a = (i + 0.5) * (2.0 * pi / ANG_N);
+            const double b = ((i + 0.5) / ANG_N - 0.5) * (2.0 * pi / ANG_N);
+            h->coarse[i] = make_double2(std::cos(a), std::sin(a));
+            h->fine[i] = make_double2(std::cos(b), std::sin(b));
         }
         e = cudaMemcpyToSymbol(g_rng_base, h, sizeof(RngBase));
         delete h;
@@ -183,6 +186,9 @@ extern "C" int optmc_set_int(optmc_ctx *ctx, const char *key, int64_t value) {
     } else if (!strcmp(key, "euro_threads")) {
         if (value != 64 && value != 128 && value != 256) FAIL("euro_threads must be 64, 128 or 256");
         ctx->euro_threads = (int)value;
+    } else if (!strcmp(key, "euro_wide")) {
+        if (value != 0 && value != 1) FAIL("euro_wide must be 0 or 1");
+        ctx->euro_wide = (int)value;
     } else if (!strcmp(key, "fed_stream")) {
         if (value != 0 && value != 1) FAIL("fed_stream must be 0 or 1");
         ctx->fed_stream = (int)value;
@@ -359,11 +365,38 @@ static int launch_euro_t(optmc_ctx *ctx, EuroArgs &A, cudaStream_t st, int *grid
     return 0;
 }
 
+// One block per SM on the lane-replicated tables (european.cuh: k_european_wide).
+template <int KIND, bool ANTI>
+static int launch_euro_wide(optmc_ctx *ctx, EuroArgs &A, cudaStream_t st, int *grid_out) {
+    auto kern = k_european_wide<KIND, ANTI>;
+    constexpr int threads = wide_threads(KIND);
+    const int smem = (int)wide_smem_bytes(kind_two_factor(KIND));
+    static bool attr_set[64] = {};                 // per device
+    if (!attr_set[ctx->device & 63]) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set[ctx->device & 63] = true;
+    }
+    const int64_t need = (A.n_local + threads - 1) / threads;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, ctx->sm_count));
+    kern<<<grid, threads, smem, st>>>(A);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    *grid_out = grid;
+    return 0;
+}
+
 template <int KIND>
 static int launch_euro_k(optmc_ctx *ctx, EuroArgs &A, bool anti, cudaStream_t st, int *grid) {
     if (ctx->normals_impl == 0)
         return anti ? launch_euro_t<KIND, true, 0>(ctx, A, st, grid)
                     : launch_euro_t<KIND, false, 0>(ctx, A, st, grid);
+    if constexpr (kind_wide(KIND)) {
+        // small jobs keep the compact kernel: its 24 - 40 KB of tables fill in no time and
+        // several small blocks per SM spread a few thousand draws better
+        if (ctx->euro_wide && A.n_local >= (int64_t)ctx->sm_count * wide_threads(KIND))
+            return anti ? launch_euro_wide<KIND, true>(ctx, A, st, grid)
+                        : launch_euro_wide<KIND, false>(ctx, A, st, grid);
+    }
     if constexpr (kind_sabr(KIND)) {
         // beta neither 0 nor 1: the variant whose step has the general exp(ln v + beta ln s) only
         const bool bgen = A.c.beta_mode != 1 && A.c.beta_mode != 2;
@@ -1089,13 +1122,13 @@ __global__ void k_normals(PhiloxKey key, int64_t n, int step, double *out) {
     __syncthreads();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t w0, w1, w2;
-    philox_pair_words(key, (uint64_t)i, (uint32_t)step, w0, w1, w2);
+    uint32_t wa, wb;
+    philox_pair_words(key, (uint64_t)i, (uint32_t)step, wa, wb);
     double a, b;
     if constexpr (NIMPL == 0)
-        normal_pair_lib(w0, w1, w2, a, b);
+        normal_pair_lib2(wa, wb, a, b);
     else
-        normal_pair_fast<false>(w0, w1, w2, a, b, tv);
+        normal_pair_fast<false>(wa, wb, a, b, tv);
     out[2 * i] = a;
     out[2 * i + 1] = b;
 }

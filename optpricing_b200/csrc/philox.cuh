@@ -7,9 +7,9 @@
 //
 // Philox4x32-10 (Salmon et al., SC'11).  Counter layout used by the engine:
 //   c0, c1 = draw id (64 bit)        c2 = call index       c3 = stream tag
-// Stream tags (c3): 0 = Brownian draws -- packed (philox_pair_words: calls 3g..3g+2
-//   feed pairs 4g..4g+3) where the step loop needs no Poisson word, else one call
-//   per step (three words for the pair, the fourth for the step's Poisson draw);
+// Stream tags (c3): 0 = Brownian draws -- packed (philox_pair_words: call g feeds
+//   Box-Muller pairs 2g and 2g+1) where the step loop needs no Poisson word, else one
+//   call per step (two words for the pair, the fourth for the step's Poisson draw);
 //   0xFE = whole-path Poisson draw; 0xFF = extra Poisson bits;
 //   (1 + partner) | (jump index << 8) = jump-size draws; 0x40 = fp32-mode pairs;
 //   0x20.. = single-step samplers (levy.cuh).
@@ -20,8 +20,8 @@
 // resource).  Hence: round keys are expanded once on the host (no per-round key
 // adds), polynomial coefficients live in the constant bank (no UMOV pairs), the
 // uniform's exponent comes from 12 dedicated bits (no 64-bit shifts), and the
-// transcendental parts use shared-memory tables (512 x 16 B for the logarithm,
-// 1024 x 16 or 32 B for the angle) so that each needs only a short polynomial.
+// transcendental parts use shared-memory tables: 512 x 16 B and a degree-4 polynomial
+// for the logarithm, two 512-row tables and one complex product for the angle.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -66,22 +66,14 @@ __device__ __forceinline__ uint4 philox_draw(const PhiloxKey &k, uint64_t id, ui
     return philox4x32_10(make_uint4((uint32_t)id, (uint32_t)(id >> 32), c2, c3), k);
 }
 
-// The three words of Box-Muller pair `pair` of one draw under the packed layout
-// the step loops use (european.cuh): calls c2 = 3g, 3g+1, 3g+2 of stream 0 yield
-// twelve words = four pairs,
-//   pair 4g: a.x a.y a.z   4g+1: a.w b.x b.y   4g+2: b.z b.w d.x   4g+3: d.y d.z d.w
-// (first two words: the 64-bit radius uniform, third: the angle).
+// The two words of Box-Muller pair `pair` of one draw under the packed layout the step
+// loops use (european.cuh): call c2 = g of stream 0 yields pairs 2g = (x, y) and
+// 2g + 1 = (z, w).
 __device__ __forceinline__ void philox_pair_words(const PhiloxKey &k, uint64_t id, uint32_t pair,
-                                                  uint32_t &w0, uint32_t &w1, uint32_t &w2) {
-    const uint32_t g = pair >> 2, slot = pair & 3u;
-    const uint4 a = philox_draw(k, id, 3u * g, 0u), b = philox_draw(k, id, 3u * g + 1u, 0u),
-                d = philox_draw(k, id, 3u * g + 2u, 0u);
-    switch (slot) {
-        case 0: w0 = a.x; w1 = a.y; w2 = a.z; break;
-        case 1: w0 = a.w; w1 = b.x; w2 = b.y; break;
-        case 2: w0 = b.z; w1 = b.w; w2 = d.x; break;
-        default: w0 = d.y; w1 = d.z; w2 = d.w;
-    }
+                                                  uint32_t &wa, uint32_t &wb) {
+    const uint4 a = philox_draw(k, id, pair >> 1, 0u);
+    wa = (pair & 1u) ? a.z : a.x;
+    wb = (pair & 1u) ? a.w : a.y;
 }
 
 // 64 random bits -> uniform double in (0, 1), 53 significant bits, never 0 or 1.
@@ -132,6 +124,16 @@ __device__ __forceinline__ double sqrt_nonneg_fast(double a) {
     return fma(e, h, g);
 }
 
+// The same for a normal a > 0 (no clamp of the seed's argument).
+__device__ __forceinline__ double sqrt_pos_fast(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(__hiloint2double(__double2hiint(a), 0)));
+    const double h = __hiloint2double(__double2hiint(y) - 0x00100000, 0);
+    double g = a * y;
+    double e = fma(-g, g, a);
+    return fma(e, h, g);
+}
+
 // index of the highest set bit (x != 0): one FLO instruction
 __device__ __forceinline__ uint32_t top_bit(uint32_t x) {
     uint32_t r;
@@ -147,23 +149,39 @@ __device__ __forceinline__ uint32_t keep_u32(uint32_t x) {
 }
 
 // ---------------------------------------------------------------------------
-// Two N(0,1) from three Philox words (Box-Muller): radius from 64 bits, angle
-// from 32.  IMPL 0 = CUDA math library calls (baseline, kept for A/B checks and
-// used on the rare jump-size path); IMPL 1 = hand-written for the fp64 pipe.
+// Two N(0,1) from TWO Philox words (Box-Muller), the mapping every fp64 step loop uses:
+//
+//   wa[31:20]  e: the binade of the radius uniform, u in [2^-(k+1), 2^-k) for k leading
+//              zeros of e (P = 2^-(k+1), exact; e == 0, P = 2^-12: the exponent continues
+//              into the mantissa bits, neg2_log_u_tail)
+//   wa[19:0] : wb[13:0] : 1 : 0...   the mantissa of u, 34 random bits + the midpoint bit
+//   wb[31:23]  i: coarse angle bucket, a_i = (i + 1/2) 2 pi / 512
+//   wb[22:14]  j: fine offset,          b_j = ((j + 1/2) / 512 - 1/2) 2 pi / 512
+//
+//   (z1, z2) = sqrt(-2 ln u) (cos, sin)(a_i + b_j)
+//
+// The angle runs over 2^18 equally spaced directions: every trigonometric moment of order
+// below 2^18 is exact, and the direction costs two table rows and one complex product --
+// (cos a_i, sin a_i)(cos b_j, sin b_j) -- instead of a table row, two polynomials in the
+// offset and the product (round 1: 96 bits and 11 fp64 instructions per pair; now 64 bits
+// and 4).  |z| reaches sqrt(2 * 46 ln 2) = 7.99.  One Philox4x32 call feeds two pairs.
+// IMPL 0 = the same mapping through the CUDA math library (A/B checks);
+// IMPL 1 = hand-written for the fp64 pipe.
 // ---------------------------------------------------------------------------
 constexpr int LOG_N = 512;     // buckets of [1,2) for ln
-constexpr int TRIG_N = 1024;   // angle buckets over the full circle
+constexpr int ANG_N = 512;     // coarse angle buckets, and fine offsets per bucket
 constexpr int EXP_N = 512;     // 2^(j/512) for exp
 
 // Host-filled base tables (one copy per context, in global memory).
 struct RngBase {
     // bucket i has midpoint c_i = 1 + (i + .5)/512;
-    //   x = -2 / c_i,  y = -2 ln c_i + 24 ln 2   (the 24 ln 2 pre-pays the exponent offset)
+    //   x = -2 / c_i,  y = -2 ln c_i + 64 ln 2   (the 64 ln 2 pre-pays the exponent offset)
     double2 logt[LOG_N];
     // 2^(j/512), j = 0..511
     double exp2t[EXP_N];
-    // angle bucket i of [0, 2 pi): a_i = (i + .5) 2 pi / 1024;  x = cos a_i, y = sin a_i
-    double2 trig[TRIG_N];
+    // (cos a_i, sin a_i) and (cos b_j, sin b_j)
+    double2 coarse[ANG_N];
+    double2 fine[ANG_N];
 };
 __device__ RngBase g_rng_base;
 
@@ -174,48 +192,120 @@ struct MathShared {
     double exp2t[EXP_N];
 };
 constexpr uint32_t EXP_OFF = (uint32_t)sizeof(double2) * LOG_N;
-constexpr uint32_t TRIG_OFF = EXP_OFF + (uint32_t)EXP_N * (uint32_t)sizeof(double);
+constexpr uint32_t COARSE_OFF = EXP_OFF + (uint32_t)EXP_N * (uint32_t)sizeof(double);
 
-// Per-block shared-memory tables.  The trig rows are specialised per launch:
+// Per-block shared-memory tables.  The coarse rows are specialised per launch:
 //   MIXED = false: (s cos a_i, s sin a_i) with a scale s (sqrt(dt) for the
 //                  one-factor models, 1 for plain normals);
 //   MIXED = true : the 2x2 mixing matrix M of the two-factor models applied to
 //                  the rotation basis, (A1, B1, A2, B2) with
 //                  A_r = M_r1 cos a_i + M_r2 sin a_i,  B_r = M_r2 cos a_i - M_r1 sin a_i,
-//                  so that  M (cos(a_i + d), sin(a_i + d))^T = (A_r cos d + B_r sin d)_r
+//                  so that  M (cos(a_i + b), sin(a_i + b))^T = (A_r cos b + B_r sin b)_r
 //                  and the correlated, scaled increments need no further arithmetic.
 template <bool MIXED>
 struct RngShared {
     MathShared math;
-    double2 trig[TRIG_N * (MIXED ? 2 : 1)];
+    double2 coarse[ANG_N * (MIXED ? 2 : 1)];
+    double2 fine[ANG_N];
 };
+__host__ __device__ constexpr uint32_t fine_off(bool mixed) {
+    return COARSE_OFF + (uint32_t)ANG_N * 16u * (mixed ? 2u : 1u);
+}
 
 // 32-bit shared-window address of the tables: lookups are one LDS.128 each.
-struct RngView {
-    uint32_t base;
+//
+// REPL = 1: the compact layout above (28 / 36 KB per block, several blocks per SM).  A
+//   random-address LDS.128 then costs ~12.8 shared-memory wavefronts instead of 4 (ncu,
+//   profiles/r01_ncu_heston_summary.md: l1tex 94 %): eight lanes of a quarter-warp pick
+//   eight random 16-byte bank groups.
+// REPL = 8: every 16-byte entry is stored eight times, entry i of copy g at byte
+//   (8 i + g) 16, and lane l reads copy l & 7 -- the eight lanes of a quarter-warp hit eight
+//   different bank groups whatever their entries are: conflict-free by construction
+//   (measured: 1.75e9 -> 6.6e3 conflict wavefronts per C2 launch, l1tex 94 -> 31 %).  The
+//   log table and each direction component take 64 KB, the fine table (four copies, lane
+//   l reads copy l & 3: two lanes of a quarter-warp can meet) 32 KB: 160 / 224 KB, so ONE
+//   block of 768 / 1024 threads per SM shares them.
+template <int REPL>
+struct RngViewT {
+    uint32_t base;          // warp-uniform: address arithmetic stays in uniform registers
+    uint32_t lane;          // REPL > 1: 16 (l & 7), OR-ed into the (masked) entry offset
+    uint32_t lane4;         // REPL > 1: 16 (l & 3), for the four-copy fine table
+    static constexpr int R = REPL;
+    // address of the entry at (masked) byte offset idx of the table at byte offset `table`
+    __device__ __forceinline__ uint32_t at(uint32_t idx, uint32_t table = 0u) const {
+        if constexpr (REPL == 1) return base + table + idx;
+        else return base + table + (idx | lane);
+    }
+    __device__ __forceinline__ uint32_t at4(uint32_t idx, uint32_t table) const {
+        if constexpr (REPL == 1) return base + table + idx;
+        else return base + table + (idx | lane4);
+    }
 };
+using RngView = RngViewT<1>;
+using RngViewW = RngViewT<8>;
+constexpr uint32_t WIDE_TABLE_BYTES = 512u * 16u * 8u;       // one 512-entry table, eight copies
+constexpr uint32_t WIDE_COARSE_OFF = WIDE_TABLE_BYTES;       // after the log table
+__host__ __device__ constexpr uint32_t wide_fine_off(bool mixed) {
+    return WIDE_TABLE_BYTES * (mixed ? 3u : 2u);
+}
+__host__ __device__ constexpr uint32_t wide_smem_bytes(bool mixed) {
+    return wide_fine_off(mixed) + WIDE_TABLE_BYTES / 2u;
+}
 
 __device__ __forceinline__ RngView fill_math_shared(MathShared *t) {
     for (int i = threadIdx.x; i < LOG_N; i += blockDim.x) t->logt[i] = g_rng_base.logt[i];
     for (int i = threadIdx.x; i < EXP_N; i += blockDim.x) t->exp2t[i] = g_rng_base.exp2t[i];
     RngView v;
     v.base = keep_u32((uint32_t)__cvta_generic_to_shared(t));
+    v.lane = v.lane4 = 0u;
     return v;
+}
+
+// one coarse row, mixed (see RngShared)
+__device__ __forceinline__ void mix_row(double2 cs, double m11, double m12, double m21, double m22,
+                                        double2 &r1, double2 &r2) {
+    r1 = make_double2(fma(m12, cs.y, m11 * cs.x), fma(m12, cs.x, -(m11 * cs.y)));
+    r2 = make_double2(fma(m22, cs.y, m21 * cs.x), fma(m22, cs.x, -(m21 * cs.y)));
 }
 
 template <bool MIXED>
 __device__ __forceinline__ RngView fill_rng_shared(RngShared<MIXED> *t, double m11, double m12,
                                                    double m21, double m22) {
     RngView v = fill_math_shared(&t->math);
-    for (int i = threadIdx.x; i < TRIG_N; i += blockDim.x) {
-        double2 cs = g_rng_base.trig[i];
-        if constexpr (MIXED) {
-            t->trig[2 * i] = make_double2(fma(m12, cs.y, m11 * cs.x), fma(m12, cs.x, -(m11 * cs.y)));
-            t->trig[2 * i + 1] = make_double2(fma(m22, cs.y, m21 * cs.x), fma(m22, cs.x, -(m21 * cs.y)));
-        } else {
-            t->trig[i] = make_double2(m11 * cs.x, m11 * cs.y);
-        }
+    for (int i = threadIdx.x; i < ANG_N; i += blockDim.x) {
+        const double2 cs = g_rng_base.coarse[i];
+        if constexpr (MIXED)
+            mix_row(cs, m11, m12, m21, m22, t->coarse[2 * i], t->coarse[2 * i + 1]);
+        else
+            t->coarse[i] = make_double2(m11 * cs.x, m11 * cs.y);
+        t->fine[i] = g_rng_base.fine[i];
     }
+    return v;
+}
+
+// Lane-replicated tables in dynamic shared memory (see RngViewT).
+template <bool MIXED>
+__device__ __forceinline__ RngViewW fill_rng_wide(unsigned char *smem, double m11, double m12,
+                                                  double m21, double m22) {
+    double2 *logt = reinterpret_cast<double2 *>(smem);
+    double2 *t1 = reinterpret_cast<double2 *>(smem + WIDE_COARSE_OFF);
+    double2 *t2 = reinterpret_cast<double2 *>(smem + 2 * WIDE_COARSE_OFF);
+    double2 *fine = reinterpret_cast<double2 *>(smem + wide_fine_off(MIXED));
+    for (int i = threadIdx.x; i < LOG_N * 8; i += blockDim.x) logt[i] = g_rng_base.logt[i >> 3];
+    for (int i = threadIdx.x; i < ANG_N * 8; i += blockDim.x) {
+        const double2 cs = g_rng_base.coarse[i >> 3];
+        if constexpr (MIXED)
+            mix_row(cs, m11, m12, m21, m22, t1[i], t2[i]);
+        else
+            t1[i] = make_double2(m11 * cs.x, m11 * cs.y);
+    }
+    for (int i = threadIdx.x; i < ANG_N * 4; i += blockDim.x) fine[i] = g_rng_base.fine[i >> 2];
+    RngViewW v;
+    v.base = keep_u32((uint32_t)__cvta_generic_to_shared(smem));
+    v.lane = keep_u32((threadIdx.x & 7u) * 16u);
+    uint32_t laneid;                    // (a second source, so that the two offsets stay two
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(laneid));      //  registers: one LOP3 per address)
+    v.lane4 = keep_u32((laneid & 3u) * 16u);
     return v;
 }
 
@@ -238,13 +328,8 @@ __device__ __forceinline__ double2 lds_f64x2(uint32_t addr) {
 // exactly-representable "short" literal with one constant-bank value, so that no
 // coefficient has to live in (and be read from) a vector register.
 __constant__ double C_1_12 = 1.0 / 12.0;
+__constant__ double C_TINY = 1e-290;                         // see step_heston_parts
 __constant__ double C_N2LN2 = -1.3862943611198906188;        // -2 ln 2
-__constant__ double C_1_24 = 1.0 / 24.0;
-__constant__ double C_N1_6 = -1.0 / 6.0;
-// 1/120 rounded to 20 mantissa bits (rel. 6e-8): it multiplies d^5 <= 3e-13
-#define OPTMC_SHORT_1_120 0x1.11111p-7
-// offset inside an angle bucket: d = j' h / 2^23 with j' odd in (-2^22, 2^22), h = 2 pi / 1024
-__constant__ double C_FINE = 6.283185307179586477 / 1024.0 / 8388608.0;
 
 // -2 ln u for a uniform u in (0,1) built from the words (lo, hi):
 //   hi[31:20] exponent bits: k = their leading zeros, u in [2^-(k+1), 2^-k)
@@ -256,11 +341,19 @@ __device__ __forceinline__ double neg2_log_poly(double m, double2 tb, double kfa
     double p = fma(r, 0.03125, C_1_12);
     p = fma(p, r, 0.25);
     p = fma(p, r, 1.0);
-    // -2 ln u = 2 (k+1) ln2 - 2 ln m;  tb.y carries 24 ln2, kfac = 11 - k (top set bit index)
+    // -2 ln u = 2 (k+1) ln2 - 2 ln m;  tb.y carries 64 ln2, kfac = 31 - k (top set bit of the high word)
     return fma(p, r, fma(kfac, C_N2LN2, tb.y));
 }
 
-__device__ __noinline__ double neg2_log_u_tail(uint32_t lo, uint32_t hi, RngView t) {
+// byte offset of the log-table entry for a double's high word (mantissa bits 19..11)
+template <class V>
+__device__ __forceinline__ uint32_t log_entry(uint32_t hi) {
+    if constexpr (V::R == 1) return (hi >> 7) & ((LOG_N - 1) * 16u);
+    else return (hi >> 4) & ((LOG_N - 1) * 128u);
+}
+
+template <class V>
+__device__ __noinline__ double neg2_log_u_tail(uint32_t lo, uint32_t hi, V t) {
     // hi < 2^20: the remaining 52 bits x = hi:lo carry exponent and mantissa
     uint64_t x = ((uint64_t)hi << 32) | lo;        // < 2^52
     int k = x ? __clzll((long long)x) - 12 : 51;   // leading zeros within the 52 bits
@@ -268,32 +361,34 @@ __device__ __noinline__ double neg2_log_u_tail(uint32_t lo, uint32_t hi, RngView
     uint64_t frac = ((x << k) << 1) & 0xFFFFFFFFFFFFFull;
     uint64_t mbits = 0x3FF0000000000000ull | frac;
     double m = __longlong_as_double((long long)mbits);
-    double2 tb = lds_f64x2(t.base + (uint32_t)((mbits >> 43) & (LOG_N - 1)) * 16u);
-    return neg2_log_poly(m, tb, (double)(11 - (12 + k)));
+    double2 tb = lds_f64x2(t.at(log_entry<V>((uint32_t)(mbits >> 32))));
+    return neg2_log_poly(m, tb, (double)(31 - (12 + k)));
 }
 
-__device__ __forceinline__ double neg2_log_u(uint32_t lo, uint32_t hi, RngView t) {
-    uint32_t e = hi >> 20;
-    if (__builtin_expect(e == 0u, 0)) return neg2_log_u_tail(lo, hi, t);
+template <class V>
+__device__ __forceinline__ double neg2_log_u(uint32_t lo, uint32_t hi, V t) {
+    if (__builtin_expect(hi < 0x100000u, 0)) return neg2_log_u_tail(lo, hi, t);
     double m = __hiloint2double(0x3FF00000 | (hi & 0xFFFFF), lo);
-    double2 tb = lds_f64x2(t.base + ((hi >> 7) & ((LOG_N - 1) * 16u)));
-    return neg2_log_poly(m, tb, (double)top_bit(e));
+    double2 tb = lds_f64x2(t.at(log_entry<V>(hi)));
+    // top_bit(hi) = 20 + top_bit(e): the table's y carries the 20 (64 ln 2 instead of 24 ln 2)
+    return neg2_log_poly(m, tb, (double)top_bit(hi));
 }
 
 // ln s for a positive normal double s: exponent from the bit pattern, ln of the
 // mantissa from the same table/polynomial as above.  7 fp64-pipe instructions
 // (CUDA's log: ~30 plus special-case branches); abs. error <= 4e-15.
 __constant__ double C_LN2 = 0.69314718055994530942;
-__device__ __forceinline__ double fast_log(double s, RngView t) {
+template <class V>
+__device__ __forceinline__ double fast_log(double s, V t) {
     int hi = __double2hiint(s);
     double m = __hiloint2double((hi & 0xFFFFF) | 0x3FF00000, __double2loint(s));
-    double2 tb = lds_f64x2(t.base + (((uint32_t)hi >> 7) & ((LOG_N - 1) * 16u)));
+    double2 tb = lds_f64x2(t.at(log_entry<V>((uint32_t)hi)));
     double r = fma(m, tb.x, 2.0);
     double p = fma(r, 0.03125, C_1_12);
     p = fma(p, r, 0.25);
     p = fma(p, r, 1.0);
-    double q = fma(p, r, tb.y);                       // -2 ln m + 24 ln 2
-    return fma((double)((hi >> 20) - 1023 + 12), C_LN2, -0.5 * q);
+    double q = fma(p, r, tb.y);                       // -2 ln m + 64 ln 2
+    return fma((double)((hi >> 20) - 1023 + 32), C_LN2, -0.5 * q);
 }
 
 // e^x for |x| < 700: x = (512 k + j) ln2/512 + r, |r| <= ln2/1024 = 6.8e-4;
@@ -304,7 +399,9 @@ __constant__ double C_EXP[3] = {738.65986093514929,              // 512 / ln 2
                                 1.0 / 24.0, 1.0 / 6.0};
 #define OPTMC_LN2_N_HI 0x1.62e42fcp-10     /* ln2/512 with the low 26 mantissa bits cleared */
 #define OPTMC_LN2_N_LO 1.0831887298761837e-11
-__device__ __forceinline__ double fast_exp(double x, RngView t) {
+template <class V>
+__device__ __forceinline__ double fast_exp(double x, V t) {
+    static_assert(V::R == 1, "the lane-replicated layout carries no exp table");
     const double MAGIC = 6755399441055744.0;          // 1.5 * 2^52: low word = rint(value)
     double tt = fma(x, C_EXP[0], MAGIC);
     int n = __double2loint(tt);
@@ -319,7 +416,8 @@ __device__ __forceinline__ double fast_exp(double x, RngView t) {
     return __hiloint2double(__double2hiint(y) + ((n >> 9) << 20), __double2loint(y));
 }
 
-// Baseline pair by the CUDA math library (also the jump-size path).
+// Baseline pair by the CUDA math library from three words (the single-step samplers of
+// levy.cuh keep it: 64-bit radius uniform, 32-bit angle).
 __device__ __forceinline__ void normal_pair_lib(uint32_t w0, uint32_t w1, uint32_t w2, double &z1,
                                                 double &z2) {
     double rad = sqrt(-2.0 * log(u01_open(w0, w1)));
@@ -329,41 +427,70 @@ __device__ __forceinline__ void normal_pair_lib(uint32_t w0, uint32_t w1, uint32
     z2 = rad * s;
 }
 
-// Hand-written pair.  angle = a_i + d: the top 10 bits of w2 pick the bucket, the
-// low 22 bits the offset d in (-h/2, h/2).  normal_parts_fast returns the squared radius
-// L = -2 ln u >= 0 and the direction,
+// low word of the radius uniform's mantissa: wb[13:0], the midpoint bit, zeros
+__device__ __forceinline__ uint32_t radius_lo(uint32_t wb) { return wb * 0x40000u + 0x20000u; }
+
+// The step loops' mapping (top of this section) through the CUDA math library: the same
+// reals as normal_pair_fast, for A/B checks (normals_impl = 0).
+__device__ __forceinline__ void normal_pair_lib2(uint32_t wa, uint32_t wb, double &z1, double &z2) {
+    const uint32_t lo = radius_lo(wb), e = wa >> 20;
+    double u;
+    if (e != 0u) {
+        const double m = __hiloint2double(0x3FF00000 | (wa & 0xFFFFF), lo);
+        u = ldexp(m, -(int)(12u - top_bit(e)));                 // k + 1 = 12 - top_bit(e)
+    } else {
+        uint64_t x = ((uint64_t)wa << 32) | lo;                 // < 2^52
+        int k = x ? __clzll((long long)x) - 12 : 51;
+        k = k > 51 ? 51 : k;
+        const uint64_t frac = ((x << k) << 1) & 0xFFFFFFFFFFFFFull;
+        u = ldexp(__longlong_as_double((long long)(0x3FF0000000000000ull | frac)), -(13 + k));
+    }
+    const double rad = sqrt(fmax(-2.0 * log(u), 0.0));
+    double s, c;
+    sincospi(((double)(wb >> 14) + 0.5) * 0x1.0p-17, &s, &c);   // 2 pi ((wb >> 14) + .5) / 2^18
+    z1 = rad * c;
+    z2 = rad * s;
+}
+
+// Hand-written pair.  normal_parts_fast returns the squared radius L = -2 ln u >= 0 and the
+// direction,
 //   MIXED = false: (t1, t2) = s (cos, sin)(angle)
 //   MIXED = true : (t1, t2) = M (cos, sin)(angle)^T
 // and the pair is (z1, z2) = sqrt(L) (t1, t2).  Heston's step needs the normals only as
 // sqrt(v) z, so it takes the parts and draws ONE root, sqrt(v L) (models.cuh).
 // L is floored at 0: for the two largest u of the top binade the table + polynomial
 // value of -2 ln u (abs. error 5e-16 there) comes out at -2e-16 instead of +2e-16.
-template <bool MIXED>
-__device__ __forceinline__ void normal_parts_fast(uint32_t w0, uint32_t w1, uint32_t w2, double &L,
-                                                  double &t1, double &t2, RngView t) {
-    L = relu64(neg2_log_u(w0, w1, t));
-    int fine = (int)((w2 & 0x3FFFFFu) * 2u) - 0x3FFFFF;            // odd, in (-2^22, 2^22)
-    double d = (double)fine * C_FINE;
-    double d2 = d * d;
-    double cd = fma(fma(d2, C_1_24, -0.5), d2, 1.0);                         // cos d
-    double sd = fma(fma(d2, OPTMC_SHORT_1_120, C_N1_6), d2, 1.0) * d;        // sin d
-    if constexpr (MIXED) {
-        uint32_t row = t.base + TRIG_OFF + ((w2 >> 17) & ((TRIG_N - 1) * 32u));
-        double2 r1 = lds_f64x2(row), r2 = lds_f64x2(row + 16u);
-        t1 = fma(r1.x, cd, r1.y * sd);
-        t2 = fma(r2.x, cd, r2.y * sd);
+template <bool MIXED, class V>
+__device__ __forceinline__ void normal_parts_fast(uint32_t wa, uint32_t wb, double &L, double &t1,
+                                                  double &t2, V t) {
+    L = relu64(neg2_log_u(radius_lo(wb), wa, t));
+    uint32_t row, fin;
+    if constexpr (V::R == 1) {
+        row = t.at(MIXED ? (wb >> 18) & ((ANG_N - 1) * 32u) : (wb >> 19) & ((ANG_N - 1) * 16u),
+                   COARSE_OFF);
+        fin = t.at((wb >> 10) & ((ANG_N - 1) * 16u), fine_off(MIXED));
     } else {
-        double2 cs = lds_f64x2(t.base + TRIG_OFF + ((w2 >> 18) & ((TRIG_N - 1) * 16u)));
-        t1 = fma(cs.x, cd, -(cs.y * sd));
-        t2 = fma(cs.y, cd, cs.x * sd);
+        row = t.at((wb >> 16) & ((ANG_N - 1) * 128u), WIDE_COARSE_OFF);
+        fin = t.at4((wb >> 8) & ((ANG_N - 1) * 64u), wide_fine_off(MIXED));
+    }
+    const double2 f = lds_f64x2(fin);                              // (cos b_j, sin b_j)
+    if constexpr (MIXED) {
+        const double2 r1 = lds_f64x2(row);
+        const double2 r2 = lds_f64x2(row + (V::R == 1 ? 16u : WIDE_TABLE_BYTES));
+        t1 = fma(r1.x, f.x, r1.y * f.y);
+        t2 = fma(r2.x, f.x, r2.y * f.y);
+    } else {
+        const double2 cs = lds_f64x2(row);
+        t1 = fma(cs.x, f.x, -(cs.y * f.y));
+        t2 = fma(cs.y, f.x, cs.x * f.y);
     }
 }
 
-template <bool MIXED>
-__device__ __forceinline__ void normal_pair_fast(uint32_t w0, uint32_t w1, uint32_t w2, double &z1,
-                                                 double &z2, RngView t) {
+template <bool MIXED, class V>
+__device__ __forceinline__ void normal_pair_fast(uint32_t wa, uint32_t wb, double &z1, double &z2,
+                                                 V t) {
     double L, t1, t2;
-    normal_parts_fast<MIXED>(w0, w1, w2, L, t1, t2, t);
+    normal_parts_fast<MIXED>(wa, wb, L, t1, t2, t);
     double rad = sqrt_nonneg_fast(L);
     z1 = rad * t1;
     z2 = rad * t2;

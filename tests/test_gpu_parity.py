@@ -334,10 +334,17 @@ def test_philox_bsm_against_closed_form(price_goldens):
     t = ob.MonteCarloTechnique(n_paths=1 << 22, n_steps=10, seed=0)
     got = t.price(CALL, ST, ob.BSMModel({"sigma": 0.2}), RT).price
     assert abs(got - price_goldens["G1_closed_form"]) < 3.5 * t.last_stats["stderr"]
-    # the reference's own acceptance bar (tests/techniques/test_monte_carlo.py:111-126)
-    t = ob.MonteCarloTechnique(n_paths=20000, n_steps=10, seed=0)
+    # The reference's own acceptance test (tests/techniques/test_monte_carlo.py:111-126) asserts
+    # abs=1e-2 at 20 000 x 10, seed 0, where one standard error is 0.07: it holds for the draws
+    # seed 0 happens to give numpy's generator.  rng_mode="numpy" reproduces those draws (G1 to
+    # 1e-12), so it passes there by construction; on the device RNG the same contract is met
+    # statistically -- within 3.5 standard errors -- and no tighter.
+    t = ob.MonteCarloTechnique(n_paths=20000, n_steps=10, seed=0, rng_mode="numpy")
     assert t.price(CALL, ST, ob.BSMModel({"sigma": 0.2}), RT).price == pytest.approx(
-        price_goldens["G1_closed_form"], abs=1e-1)
+        price_goldens["G1_closed_form"], abs=1e-2)
+    t = ob.MonteCarloTechnique(n_paths=20000, n_steps=10, seed=0)
+    got = t.price(CALL, ST, ob.BSMModel({"sigma": 0.2}), RT).price
+    assert abs(got - price_goldens["G1_closed_form"]) < 3.5 * t.last_stats["stderr"]
 
 
 def test_philox_independent_correlation_matches_fft(price_goldens):
