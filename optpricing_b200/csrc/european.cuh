@@ -75,7 +75,7 @@ __device__ __forceinline__ double jump_size(uint4 w, const Consts &c, V tab) {
         // up w.p. p_up: +Exp(eta1), else -Exp(eta2)   (mc_kernels.py:314-317)
         double e;
         if constexpr (NIMPL == 0) e = -log(u01_open(w.x, w.y));
-        else e = 0.5 * neg2_log_u(w.x, w.y, tab);
+        else e = 0.5 * neg2_log_u(w.x | 1u, w.y, tab);
         return w.w < c.p_up_bits ? e * c.inv_eta1 : -e * c.inv_eta2;
     } else {
         return fma(c.sigma_j, unit_normals<KIND, NIMPL>(w, c, tab).x, c.mu_j);   // N(mu_j, sigma_j)  (mc_kernels.py:111)
@@ -400,14 +400,21 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
             advance(wa, wb, i, RAGGED, NOSLOT);
         }
     } else if constexpr (!LEGACY && TWO) {
-        // (the bounds test between the pairs also keeps the compiler from hoisting the next
-        // Philox call to the top of the group)
+        // Whole calls (two steps) without a bounds test: with the branch-free logarithm the
+        // body is one basic block.  (Issuing the next call's Philox rounds ahead of the
+        // current steps, whole or in two halves, measured 5 - 7 % slower: ptxas then keeps the
+        // round keys in vector registers and reloads constants -- profiles/r02_experiments.md.)
         uint32_t call = 0;
+        int i = 0;
         OPTMC_UNROLL_STEPS
-        for (int i = 0; i < A.n_steps; i += 2, ++call) {
+        for (; i + 2 <= A.n_steps; i += 2, ++call) {
             const uint4 a = philox4x32_10(make_uint4(id_lo, id_hi, call, 0u), A.key);
             advance(a.x, a.y, i, RAGGED, NOSLOT);
-            if (i + 1 < A.n_steps) advance(a.z, a.w, i + 1, RAGGED, NOSLOT);
+            advance(a.z, a.w, i + 1, RAGGED, NOSLOT);
+        }
+        if (i < A.n_steps) {
+            const uint4 a = philox4x32_10(make_uint4(id_lo, id_hi, call, 0u), A.key);
+            advance(a.x, a.y, i, RAGGED, NOSLOT);
         }
     } else if constexpr (!LEGACY) {
         // one-factor models: whole groups of four steps without a single bounds test, then

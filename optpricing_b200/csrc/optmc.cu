@@ -125,7 +125,7 @@ extern "C" int optmc_ctx_create(int device, optmc_ctx **out) {
         const double pi = 3.14159265358979323846;
         for (int i = 0; i < LOG_N; ++i) {
             double c = 1.0 + (i + 0.5) / LOG_N;
-            h->logt[i] = make_double2(-2.0 / c, -2.0 * std::log(c) + 64.0 * std::log(2.0));
+            h->logt[i] = make_double2(-2.0 / c, -2.0 * std::log(c));
         }
         for (int j = 0; j < EXP_N; ++j) h->exp2t[j] = std::exp2(j / (double)EXP_N);
         for (int i = 0; i < ANG_N; ++i) {

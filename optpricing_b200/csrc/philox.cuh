@@ -19,7 +19,7 @@
 // Heston kernel showed fp64 42 % / ALU 41 % busy with issue slots the binding
 // resource).  Hence: round keys are expanded once on the host (no per-round key
 // adds), polynomial coefficients live in the constant bank (no UMOV pairs), the
-// uniform's exponent comes from 12 dedicated bits (no 64-bit shifts), and the
+// uniform's exponent and mantissa come out of one integer-to-double conversion, and the
 // transcendental parts use shared-memory tables: 512 x 16 B and a degree-4 polynomial
 // for the logarithm, two 512-row tables and one complex product for the angle.
 #pragma once
@@ -54,6 +54,18 @@ inline void philox_expand_key(uint64_t seed, PhiloxKey *k) {
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKey &k) {
 #pragma unroll
     for (int i = 0; i < OPTMC_PHILOX_ROUNDS; ++i) {
+        uint32_t hi0 = __umulhi(PHILOX_M0, c.x), lo0 = PHILOX_M0 * c.x;
+        uint32_t hi1 = __umulhi(PHILOX_M1, c.z), lo1 = PHILOX_M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.k0[i], lo1, hi0 ^ c.w ^ k.k1[i], lo0);
+    }
+    return c;
+}
+
+// rounds [R0, R1) of the same function, for step loops that spread a call over their body
+template <int R0, int R1>
+__device__ __forceinline__ uint4 philox_rounds(uint4 c, const PhiloxKey &k) {
+#pragma unroll
+    for (int i = R0; i < R1; ++i) {
         uint32_t hi0 = __umulhi(PHILOX_M0, c.x), lo0 = PHILOX_M0 * c.x;
         uint32_t hi1 = __umulhi(PHILOX_M1, c.z), lo1 = PHILOX_M1 * c.z;
         c = make_uint4(hi1 ^ c.y ^ k.k0[i], lo1, hi0 ^ c.w ^ k.k1[i], lo0);
@@ -151,10 +163,7 @@ __device__ __forceinline__ uint32_t keep_u32(uint32_t x) {
 // ---------------------------------------------------------------------------
 // Two N(0,1) from TWO Philox words (Box-Muller), the mapping every fp64 step loop uses:
 //
-//   wa[31:20]  e: the binade of the radius uniform, u in [2^-(k+1), 2^-k) for k leading
-//              zeros of e (P = 2^-(k+1), exact; e == 0, P = 2^-12: the exponent continues
-//              into the mantissa bits, neg2_log_u_tail)
-//   wa[19:0] : wb[13:0] : 1 : 0...   the mantissa of u, 34 random bits + the midpoint bit
+//   wa : wb[13:0]   x: 46 random bits; the radius uniform is u = (x + 1/2) 2^-46
 //   wb[31:23]  i: coarse angle bucket, a_i = (i + 1/2) 2 pi / 512
 //   wb[22:14]  j: fine offset,          b_j = ((j + 1/2) / 512 - 1/2) 2 pi / 512
 //
@@ -164,7 +173,7 @@ __device__ __forceinline__ uint32_t keep_u32(uint32_t x) {
 // below 2^18 is exact, and the direction costs two table rows and one complex product --
 // (cos a_i, sin a_i)(cos b_j, sin b_j) -- instead of a table row, two polynomials in the
 // offset and the product (round 1: 96 bits and 11 fp64 instructions per pair; now 64 bits
-// and 4).  |z| reaches sqrt(2 * 46 ln 2) = 7.99.  One Philox4x32 call feeds two pairs.
+// and 4).  |z| reaches sqrt(2 * 47 ln 2) = 8.07.  One Philox4x32 call feeds two pairs.
 // IMPL 0 = the same mapping through the CUDA math library (A/B checks);
 // IMPL 1 = hand-written for the fp64 pipe.
 // ---------------------------------------------------------------------------
@@ -175,7 +184,7 @@ constexpr int EXP_N = 512;     // 2^(j/512) for exp
 // Host-filled base tables (one copy per context, in global memory).
 struct RngBase {
     // bucket i has midpoint c_i = 1 + (i + .5)/512;
-    //   x = -2 / c_i,  y = -2 ln c_i + 64 ln 2   (the 64 ln 2 pre-pays the exponent offset)
+    //   x = -2 / c_i,  y = -2 ln c_i
     double2 logt[LOG_N];
     // 2^(j/512), j = 0..511
     double exp2t[EXP_N];
@@ -230,6 +239,7 @@ struct RngViewT {
     uint32_t base;          // warp-uniform: address arithmetic stays in uniform registers
     uint32_t lane;          // REPL > 1: 16 (l & 7), OR-ed into the (masked) entry offset
     uint32_t lane4;         // REPL > 1: 16 (l & 3), for the four-copy fine table
+    uint32_t k3ff;          // 0x3FF00000 held in a register (mantissa_hi)
     static constexpr int R = REPL;
     // address of the entry at (masked) byte offset idx of the table at byte offset `table`
     __device__ __forceinline__ uint32_t at(uint32_t idx, uint32_t table = 0u) const {
@@ -258,6 +268,7 @@ __device__ __forceinline__ RngView fill_math_shared(MathShared *t) {
     RngView v;
     v.base = keep_u32((uint32_t)__cvta_generic_to_shared(t));
     v.lane = v.lane4 = 0u;
+    v.k3ff = keep_u32(0x3FF00000u);
     return v;
 }
 
@@ -306,6 +317,7 @@ __device__ __forceinline__ RngViewW fill_rng_wide(unsigned char *smem, double m1
     uint32_t laneid;                    // (a second source, so that the two offsets stay two
     asm volatile("mov.u32 %0, %%laneid;" : "=r"(laneid));      //  registers: one LOP3 per address)
     v.lane4 = keep_u32((laneid & 3u) * 16u);
+    v.k3ff = keep_u32(0x3FF00000u);
     return v;
 }
 
@@ -331,17 +343,16 @@ __constant__ double C_1_12 = 1.0 / 12.0;
 __constant__ double C_TINY = 1e-290;                         // see step_heston_parts
 __constant__ double C_N2LN2 = -1.3862943611198906188;        // -2 ln 2
 
-// -2 ln u for a uniform u in (0,1) built from the words (lo, hi):
-//   hi[31:20] exponent bits: k = their leading zeros, u in [2^-(k+1), 2^-k)
-//   hi[19:0] : lo            the 52 mantissa bits of m in [1,2);  u = m 2^-(k+1)
-// If all 12 exponent bits are zero (p = 2^-12) the exponent continues into the
-// mantissa bits (slow path), so u stays exactly uniform on its 2^-64 grid.
+// -2 ln u for the uniform u = x 2^-64, x = hi:lo != 0 (callers set a low bit).  The
+// integer goes through ONE conversion to double -- exponent and mantissa of u in one
+// instruction, the deep tail (u down to 2^-64) included: no leading-zero count, no
+// rare branch to split the step loop's basic block.
 __device__ __forceinline__ double neg2_log_poly(double m, double2 tb, double kfac) {
     double r = fma(m, tb.x, 2.0);                  // r' = -2 (m / c - 1)
     double p = fma(r, 0.03125, C_1_12);
     p = fma(p, r, 0.25);
     p = fma(p, r, 1.0);
-    // -2 ln u = 2 (k+1) ln2 - 2 ln m;  tb.y carries 64 ln2, kfac = 31 - k (top set bit of the high word)
+    // u = m 2^kfac, -64 <= kfac <= 0:  -2 ln u = -2 ln m - 2 kfac ln 2;  tb.y = -2 ln c
     return fma(p, r, fma(kfac, C_N2LN2, tb.y));
 }
 
@@ -352,26 +363,21 @@ __device__ __forceinline__ uint32_t log_entry(uint32_t hi) {
     else return (hi >> 4) & ((LOG_N - 1) * 128u);
 }
 
-template <class V>
-__device__ __noinline__ double neg2_log_u_tail(uint32_t lo, uint32_t hi, V t) {
-    // hi < 2^20: the remaining 52 bits x = hi:lo carry exponent and mantissa
-    uint64_t x = ((uint64_t)hi << 32) | lo;        // < 2^52
-    int k = x ? __clzll((long long)x) - 12 : 51;   // leading zeros within the 52 bits
-    k = k > 51 ? 51 : k;
-    uint64_t frac = ((x << k) << 1) & 0xFFFFFFFFFFFFFull;
-    uint64_t mbits = 0x3FF0000000000000ull | frac;
-    double m = __longlong_as_double((long long)mbits);
-    double2 tb = lds_f64x2(t.at(log_entry<V>((uint32_t)(mbits >> 32))));
-    return neg2_log_poly(m, tb, (double)(31 - (12 + k)));
+// high word of the mantissa m in [1, 2) of a positive double with high word hi:
+// (hi & 0xFFFFF) | 0x3FF00000 as ONE three-input logic instruction
+__device__ __forceinline__ int mantissa_hi(int hi, uint32_t k3ff) {
+    int r;
+    asm("lop3.b32 %0, %1, 0xFFFFF, %2, 0xEA;" : "=r"(r) : "r"(hi), "r"(k3ff));
+    return r;
 }
 
 template <class V>
 __device__ __forceinline__ double neg2_log_u(uint32_t lo, uint32_t hi, V t) {
-    if (__builtin_expect(hi < 0x100000u, 0)) return neg2_log_u_tail(lo, hi, t);
-    double m = __hiloint2double(0x3FF00000 | (hi & 0xFFFFF), lo);
-    double2 tb = lds_f64x2(t.at(log_entry<V>(hi)));
-    // top_bit(hi) = 20 + top_bit(e): the table's y carries the 20 (64 ln 2 instead of 24 ln 2)
-    return neg2_log_poly(m, tb, (double)top_bit(hi));
+    const double d = __ull2double_rn(((unsigned long long)hi << 32) | lo);      // u 2^64
+    const int dh = __double2hiint(d);
+    const double m = __hiloint2double(mantissa_hi(dh, t.k3ff), __double2loint(d));
+    const double2 tb = lds_f64x2(t.at(log_entry<V>((uint32_t)dh)));
+    return neg2_log_poly(m, tb, (double)((dh - 0x43F00000) >> 20));       // exponent - 64
 }
 
 // ln s for a positive normal double s: exponent from the bit pattern, ln of the
@@ -387,8 +393,8 @@ __device__ __forceinline__ double fast_log(double s, V t) {
     double p = fma(r, 0.03125, C_1_12);
     p = fma(p, r, 0.25);
     p = fma(p, r, 1.0);
-    double q = fma(p, r, tb.y);                       // -2 ln m + 64 ln 2
-    return fma((double)((hi >> 20) - 1023 + 32), C_LN2, -0.5 * q);
+    double q = fma(p, r, tb.y);                       // -2 ln m
+    return fma((double)((hi >> 20) - 1023), C_LN2, -0.5 * q);
 }
 
 // e^x for |x| < 700: x = (512 k + j) ln2/512 + r, |r| <= ln2/1024 = 6.8e-4;
@@ -427,24 +433,13 @@ __device__ __forceinline__ void normal_pair_lib(uint32_t w0, uint32_t w1, uint32
     z2 = rad * s;
 }
 
-// low word of the radius uniform's mantissa: wb[13:0], the midpoint bit, zeros
+// low word of the radius uniform (x + 1/2) 2^18: wb[13:0], the midpoint bit, zeros
 __device__ __forceinline__ uint32_t radius_lo(uint32_t wb) { return wb * 0x40000u + 0x20000u; }
 
 // The step loops' mapping (top of this section) through the CUDA math library: the same
 // reals as normal_pair_fast, for A/B checks (normals_impl = 0).
 __device__ __forceinline__ void normal_pair_lib2(uint32_t wa, uint32_t wb, double &z1, double &z2) {
-    const uint32_t lo = radius_lo(wb), e = wa >> 20;
-    double u;
-    if (e != 0u) {
-        const double m = __hiloint2double(0x3FF00000 | (wa & 0xFFFFF), lo);
-        u = ldexp(m, -(int)(12u - top_bit(e)));                 // k + 1 = 12 - top_bit(e)
-    } else {
-        uint64_t x = ((uint64_t)wa << 32) | lo;                 // < 2^52
-        int k = x ? __clzll((long long)x) - 12 : 51;
-        k = k > 51 ? 51 : k;
-        const uint64_t frac = ((x << k) << 1) & 0xFFFFFFFFFFFFFull;
-        u = ldexp(__longlong_as_double((long long)(0x3FF0000000000000ull | frac)), -(13 + k));
-    }
+    const double u = ldexp(__ull2double_rn(((unsigned long long)wa << 32) | radius_lo(wb)), -64);
     const double rad = sqrt(fmax(-2.0 * log(u), 0.0));
     double s, c;
     sincospi(((double)(wb >> 14) + 0.5) * 0x1.0p-17, &s, &c);   // 2 pi ((wb >> 14) + .5) / 2^18
