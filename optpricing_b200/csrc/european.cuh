@@ -92,7 +92,7 @@ __device__ __forceinline__ double jump_size(uint4 w, const Consts &c, V tab) {
 template <int KIND, bool ANTI, int NIMPL = 0, class V = RngView>
 __device__ __forceinline__ double2 jumps_slow(uint32_t w, double mu, double p0, const PhiloxKey &key,
                                            uint32_t id_lo, uint32_t id_hi, uint32_t step,
-                                           const Consts &c, V tab = V{0u}) {
+                                           const Consts &c, V tab = V{}) {
     uint4 e = philox4x32_10(make_uint4(id_lo, id_hi, step, 0xFFu), key);
     int n = poisson_slow(w, e.x, mu, p0);
     double2 acc = make_double2(0.0, 0.0);
@@ -522,10 +522,9 @@ template <int KIND, bool ANTI, int NIMPL, bool SCHED = false, bool BGEN = false>
 __global__ void __launch_bounds__(EURO_THREADS, euro_min_blocks(KIND, NIMPL, SCHED))
 k_european(const EuroArgs A) {
     __shared__ RngShared<kind_two_factor(KIND)> tab;
-    RngView tv{0u};
     __shared__ double scratch[5 * 32];
-    tv = fill_rng_shared(&tab, kind_two_factor(KIND) ? A.c.m11 : A.c.sqrt_dt, A.c.m12, A.c.m21,
-                         A.c.m22);
+    const RngView tv = fill_rng_shared(&tab, kind_two_factor(KIND) ? A.c.m11 : A.c.sqrt_dt, A.c.m12,
+                                       A.c.m21, A.c.m22);
     __syncthreads();
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -543,36 +542,38 @@ k_european(const EuroArgs A) {
     }
 }
 
-// The same kernel on the lane-replicated tables (philox.cuh: RngViewT<8>): ONE block per SM --
-// 768 threads for Heston / Bates (85 registers), 1024 for the one-factor models (64) -- whose
-// warps share 128 / 192 KB of conflict-free tables in dynamic shared memory.  The models that
-// also need the exp table inside the step loop (the SABR kinds) stay on k_european.
-__host__ __device__ constexpr bool kind_wide(int kind) {
-    return kind == OPTMC_BSM || kind == OPTMC_MERTON || kind == OPTMC_KOU || kind == OPTMC_HESTON ||
-           kind == OPTMC_BATES;
-}
-__host__ __device__ constexpr int wide_threads(int kind) {
+// The same kernel on lane-replicated tables (philox.cuh: WideLayout / WideExpLayout): ONE
+// block per SM -- 768 threads for the two-factor kinds (85 registers), 1024 for the one-factor
+// models (64) -- whose warps share 160 - 224 KB of (nearly) conflict-free tables in dynamic
+// shared memory.
+__host__ __device__ constexpr int wide_threads(int kind, bool sched = false) {
 #ifdef OPTMC_WIDE_THREADS
     return OPTMC_WIDE_THREADS;
 #else
-    return kind_two_factor(kind) ? 768 : 1024;
+    // (SABR-jump on the jump schedule keeps eight jump factors in its jump groups: 640
+    // threads = 102 registers, no spills)
+    return kind == OPTMC_SABR_JUMP && sched ? 640 : kind_two_factor(kind) ? 768 : 1024;
 #endif
 }
+template <int KIND>
+using wide_layout_t = std::conditional_t<kind_sabr(KIND), WideExpLayout, WideLayout>;
+template <int KIND>
+constexpr uint32_t wide_smem_bytes() { return wide_layout_t<KIND>::bytes(kind_two_factor(KIND)); }
 
-template <int KIND, bool ANTI>
-__global__ void __launch_bounds__(wide_threads(KIND), 1) k_european_wide(const EuroArgs A) {
-    static_assert(kind_wide(KIND), "no exp table in the lane-replicated layout");
+template <int KIND, bool ANTI, bool SCHED = false, bool BGEN = false>
+__global__ void __launch_bounds__(wide_threads(KIND, SCHED), 1) k_european_wide(const EuroArgs A) {
+    static_assert(KIND != OPTMC_DUPIRE, "Dupire keeps the compact kernel");
     extern __shared__ __align__(16) unsigned char wide_smem[];
     __shared__ double scratch[5 * 32];
-    const RngViewW tv = fill_rng_wide<kind_two_factor(KIND)>(
+    const auto tv = fill_rng_tables<wide_layout_t<KIND>, kind_two_factor(KIND)>(
         wide_smem, kind_two_factor(KIND) ? A.c.m11 : A.c.sqrt_dt, A.c.m12, A.c.m21, A.c.m22);
     __syncthreads();
     double acc[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < A.n_local; g += stride) {
         State sa, sb;
-        simulate_draw<KIND, ANTI, 1, false, false, false>(A, (uint64_t)(A.draw_offset + g), sa, sb,
-                                                          tv, NoSink{});
+        simulate_draw<KIND, ANTI, 1, false, SCHED, BGEN>(A, (uint64_t)(A.draw_offset + g), sa, sb,
+                                                         tv, NoSink{});
         accumulate_draw<KIND, ANTI>(A, g, sa, sb, acc);
     }
     block_sum<5>(acc, scratch);

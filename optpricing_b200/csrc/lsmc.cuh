@@ -38,9 +38,8 @@ template <int KIND, bool ANTI, int NIMPL, bool SCHED = false, bool BGEN = false>
 __global__ void __launch_bounds__(EURO_THREADS) k_lsmc_paths(const EuroArgs A, double *store,
                                                              int64_t ld) {
     __shared__ RngShared<kind_two_factor(KIND)> tab;
-    RngView tv{0u};
-    tv = fill_rng_shared(&tab, kind_two_factor(KIND) ? A.c.m11 : A.c.sqrt_dt, A.c.m12, A.c.m21,
-                         A.c.m22);
+    const RngView tv = fill_rng_shared(&tab, kind_two_factor(KIND) ? A.c.m11 : A.c.sqrt_dt, A.c.m12,
+                                       A.c.m21, A.c.m22);
     __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < A.n_local; g += stride) {

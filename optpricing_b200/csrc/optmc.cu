@@ -366,11 +366,11 @@ static int launch_euro_t(optmc_ctx *ctx, EuroArgs &A, cudaStream_t st, int *grid
 }
 
 // One block per SM on the lane-replicated tables (european.cuh: k_european_wide).
-template <int KIND, bool ANTI>
+template <int KIND, bool ANTI, bool SCHED = false, bool BGEN = false>
 static int launch_euro_wide(optmc_ctx *ctx, EuroArgs &A, cudaStream_t st, int *grid_out) {
-    auto kern = k_european_wide<KIND, ANTI>;
-    constexpr int threads = wide_threads(KIND);
-    const int smem = (int)wide_smem_bytes(kind_two_factor(KIND));
+    auto kern = k_european_wide<KIND, ANTI, SCHED, BGEN>;
+    constexpr int threads = wide_threads(KIND, SCHED);
+    const int smem = (int)wide_smem_bytes<KIND>();
     static bool attr_set[64] = {};                 // per device
     if (!attr_set[ctx->device & 63]) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -385,37 +385,43 @@ static int launch_euro_wide(optmc_ctx *ctx, EuroArgs &A, cudaStream_t st, int *g
     return 0;
 }
 
+// Which kernel prices a job: a property of the whole job (n_draws), not of this rank's shard,
+// so that every rank of a partitioned pricing runs the same code.
+static bool use_wide(const optmc_ctx *ctx, int kind, int64_t n_draws) {
+    return ctx->euro_wide && ctx->normals_impl == 1 && kind != OPTMC_DUPIRE &&
+           n_draws >= (int64_t)ctx->sm_count * wide_threads(kind);
+}
+
 template <int KIND>
-static int launch_euro_k(optmc_ctx *ctx, EuroArgs &A, bool anti, cudaStream_t st, int *grid) {
+static int launch_euro_k(optmc_ctx *ctx, EuroArgs &A, bool anti, bool wide, cudaStream_t st,
+                         int *grid) {
     if (ctx->normals_impl == 0)
         return anti ? launch_euro_t<KIND, true, 0>(ctx, A, st, grid)
                     : launch_euro_t<KIND, false, 0>(ctx, A, st, grid);
-    if constexpr (kind_wide(KIND)) {
-        // small jobs keep the compact kernel: its 24 - 40 KB of tables fill in no time and
-        // several small blocks per SM spread a few thousand draws better
-        if (ctx->euro_wide && A.n_local >= (int64_t)ctx->sm_count * wide_threads(KIND))
-            return anti ? launch_euro_wide<KIND, true>(ctx, A, st, grid)
-                        : launch_euro_wide<KIND, false>(ctx, A, st, grid);
-    }
+#define EURO_GO(SCHED_, BGEN_)                                                               \
+    do {                                                                                     \
+        if constexpr (KIND != OPTMC_DUPIRE) {                                                \
+            if (wide)                                                                        \
+                return anti ? launch_euro_wide<KIND, true, SCHED_, BGEN_>(ctx, A, st, grid)  \
+                            : launch_euro_wide<KIND, false, SCHED_, BGEN_>(ctx, A, st, grid);\
+        }                                                                                    \
+        return anti ? launch_euro_t<KIND, true, 1, SCHED_, BGEN_>(ctx, A, st, grid)          \
+                    : launch_euro_t<KIND, false, 1, SCHED_, BGEN_>(ctx, A, st, grid);        \
+    } while (0)
     if constexpr (kind_sabr(KIND)) {
         // beta neither 0 nor 1: the variant whose step has the general exp(ln v + beta ln s) only
         const bool bgen = A.c.beta_mode != 1 && A.c.beta_mode != 2;
         // SABR-jump (jumps act on S inside the step loop): the jump schedule while lambda T is small
         if constexpr (KIND == OPTMC_SABR_JUMP) {
             if (ctx->jump_schedule && use_jump_schedule(A)) {
-                if (bgen)
-                    return anti ? launch_euro_t<KIND, true, 1, true, true>(ctx, A, st, grid)
-                                : launch_euro_t<KIND, false, 1, true, true>(ctx, A, st, grid);
-                return anti ? launch_euro_t<KIND, true, 1, true, false>(ctx, A, st, grid)
-                            : launch_euro_t<KIND, false, 1, true, false>(ctx, A, st, grid);
+                if (bgen) EURO_GO(true, true);
+                EURO_GO(true, false);
             }
         }
-        if (bgen)
-            return anti ? launch_euro_t<KIND, true, 1, false, true>(ctx, A, st, grid)
-                        : launch_euro_t<KIND, false, 1, false, true>(ctx, A, st, grid);
+        if (bgen) EURO_GO(false, true);
     }
-    return anti ? launch_euro_t<KIND, true, 1>(ctx, A, st, grid)
-                : launch_euro_t<KIND, false, 1>(ctx, A, st, grid);
+    EURO_GO(false, false);
+#undef EURO_GO
 }
 
 template <int KIND>
@@ -556,7 +562,8 @@ extern "C" int optmc_european_aux_async(optmc_ctx *ctx, const optmc_model *model
         }
         if (rc) return rc;
     } else if (sim->n_local > 0) {
-#define GO(K) rc = launch_euro_k<K>(ctx, A, anti, st, &grid)
+        const bool wide = use_wide(ctx, model->kind, sim->n_draws);
+#define GO(K) rc = launch_euro_k<K>(ctx, A, anti, wide, st, &grid)
         DISPATCH_KIND(model->kind, GO)
 #undef GO
         if (rc) return rc;
@@ -1117,8 +1124,7 @@ __global__ void k_philox_raw(PhiloxKey key, int64_t n, uint32_t c2, uint32_t c3,
 template <int NIMPL>
 __global__ void k_normals(PhiloxKey key, int64_t n, int step, double *out) {
     __shared__ RngShared<false> tab;
-    RngView tv{0u};
-    tv = fill_rng_shared(&tab, 1.0, 0.0, 0.0, 0.0);
+    const RngView tv = fill_rng_shared(&tab, 1.0, 0.0, 0.0, 0.0);
     __syncthreads();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;

@@ -194,131 +194,168 @@ struct RngBase {
 };
 __device__ RngBase g_rng_base;
 
-// Shared-memory layout common to every kernel that uses the math helpers
-// (fast_log / fast_exp) -- the RNG tables extend it.
-struct MathShared {
-    double2 logt[LOG_N];
-    double exp2t[EXP_N];
-};
-constexpr uint32_t EXP_OFF = (uint32_t)sizeof(double2) * LOG_N;
-constexpr uint32_t COARSE_OFF = EXP_OFF + (uint32_t)EXP_N * (uint32_t)sizeof(double);
+// ---------------------------------------------------------------------------
+// Shared-memory tables.  One layout template serves every kernel; what varies is how many
+// COPIES of each table a block keeps:
+//
+//   copies = 1: compact (28 / 36 KB per block, several blocks per SM).  A random-address
+//     LDS.128 then costs ~12.8 shared-memory wavefronts instead of 4 (ncu,
+//     profiles/r01_ncu_heston_summary.md: l1tex 94 %): the eight lanes of a quarter-warp pick
+//     eight random 16-byte bank groups.
+//   copies = C > 1: every entry is stored C times, entry i of copy g at (C i + g) entries,
+//     and lane l reads copy l mod C.  With 8 copies of a 16-byte table the eight lanes of a
+//     quarter-warp hit eight different bank groups whatever their entries are: conflict-free
+//     by construction (measured: 1.75e9 -> 6.6e3 conflict wavefronts per C2 launch).  The
+//     tables then fill the shared memory of an SM, so ONE block of 768 / 1024 threads per SM
+//     shares them (k_european_wide).
+//
+// Order in memory: log | exp | coarse T1 | coarse T2 (two-factor kinds) | fine.
+//   log    (x, y) = (-2 / c_i, -2 ln c_i)                       16 B entries
+//   exp    2^(j/512)                                             8 B entries
+//   T1/T2  coarse rows, specialised per launch:
+//            one-factor: T1 = (s cos a_i, s sin a_i), s = sqrt(dt) (1 for plain normals);
+//            two-factor: the 2x2 mixing matrix M applied to the rotation basis,
+//              T_r = (A_r, B_r),  A_r = M_r1 cos a_i + M_r2 sin a_i,  B_r = M_r2 cos a_i - M_r1 sin a_i,
+//            so that M (cos(a_i + b), sin(a_i + b))^T = (A_r cos b + B_r sin b)_r and the
+//            correlated, scaled increments need no further arithmetic.
+//   fine   (cos b_j, sin b_j)
+// ---------------------------------------------------------------------------
+__host__ __device__ constexpr int ilog2(uint32_t x) { return x <= 1u ? 0 : 1 + ilog2(x >> 1); }
 
-// Per-block shared-memory tables.  The coarse rows are specialised per launch:
-//   MIXED = false: (s cos a_i, s sin a_i) with a scale s (sqrt(dt) for the
-//                  one-factor models, 1 for plain normals);
-//   MIXED = true : the 2x2 mixing matrix M of the two-factor models applied to
-//                  the rotation basis, (A1, B1, A2, B2) with
-//                  A_r = M_r1 cos a_i + M_r2 sin a_i,  B_r = M_r2 cos a_i - M_r1 sin a_i,
-//                  so that  M (cos(a_i + b), sin(a_i + b))^T = (A_r cos b + B_r sin b)_r
-//                  and the correlated, scaled increments need no further arithmetic.
+template <int LOGC, int EXPC, int ANGC, int FINEC>
+struct TableLayout {
+    static constexpr int LOG_COPIES = LOGC, EXP_COPIES = EXPC, ANG_COPIES = ANGC, FINE_COPIES = FINEC;
+    static constexpr uint32_t LOG_STRIDE = 16u * LOGC, EXP_STRIDE = 8u * EXPC,
+                              ANG_STRIDE = 16u * ANGC, FINE_STRIDE = 16u * FINEC;
+    static constexpr uint32_t LOG_OFF = 0u;
+    static constexpr uint32_t EXP_OFF = LOG_OFF + (uint32_t)LOG_N * LOG_STRIDE;
+    static constexpr uint32_t T1_OFF = EXP_OFF + (uint32_t)EXP_N * EXP_STRIDE;
+    static constexpr uint32_t T2_OFF = T1_OFF + (uint32_t)ANG_N * ANG_STRIDE;
+    __host__ __device__ static constexpr uint32_t fine_off(bool mixed) {
+        return T2_OFF + (mixed ? (uint32_t)ANG_N * ANG_STRIDE : 0u);
+    }
+    __host__ __device__ static constexpr uint32_t bytes(bool mixed) {
+        return fine_off(mixed) + (uint32_t)ANG_N * FINE_STRIDE;
+    }
+};
+
+// 32-bit shared-window address of a block's tables + the lane's copy offsets.
+template <class LAYOUT>
+struct RngViewT {
+    using Lay = LAYOUT;
+    uint32_t base;          // warp-uniform: address arithmetic stays in uniform registers
+    uint32_t l8, l4, l2;    // 16 (l mod 8), 16 (l mod 4), 16 (l mod 2): OR-ed into entry offsets
+    uint32_t le;            // 8 (l mod EXP_COPIES)
+    uint32_t k3ff;          // 0x3FF00000 held in a register (mantissa_hi)
+    template <int COPIES>
+    __device__ __forceinline__ uint32_t lane16() const {
+        static_assert(COPIES == 1 || COPIES == 2 || COPIES == 4 || COPIES == 8, "copies");
+        return COPIES == 8 ? l8 : COPIES == 4 ? l4 : COPIES == 2 ? l2 : 0u;
+    }
+    // addresses of the entries selected by the bit fields the generators use
+    __device__ __forceinline__ uint32_t log_at(uint32_t hi) const {      // mantissa bits 19..11
+        constexpr int sh = 11 - ilog2(Lay::LOG_STRIDE);
+        return base + Lay::LOG_OFF + (((hi >> sh) & ((LOG_N - 1) * Lay::LOG_STRIDE)) |
+                                      lane16<Lay::LOG_COPIES>());
+    }
+    __device__ __forceinline__ uint32_t exp_at(uint32_t n) const {       // n mod 512
+        static_assert(Lay::EXP_COPIES >= 1, "this layout carries no exp table");
+        return base + Lay::EXP_OFF + (((n & (EXP_N - 1)) * Lay::EXP_STRIDE) |
+                                      (Lay::EXP_COPIES > 1 ? le : 0u));
+    }
+    __device__ __forceinline__ uint32_t coarse_at(uint32_t wb) const {   // wb[31:23]
+        constexpr int sh = 23 - ilog2(Lay::ANG_STRIDE);
+        return base + Lay::T1_OFF + (((wb >> sh) & ((ANG_N - 1) * Lay::ANG_STRIDE)) |
+                                     lane16<Lay::ANG_COPIES>());
+    }
+    template <bool MIXED>
+    __device__ __forceinline__ uint32_t fine_at(uint32_t wb) const {     // wb[22:14]
+        constexpr int sh = 14 - ilog2(Lay::FINE_STRIDE);
+        return base + Lay::fine_off(MIXED) + (((wb >> sh) & ((ANG_N - 1) * Lay::FINE_STRIDE)) |
+                                              lane16<Lay::FINE_COPIES>());
+    }
+};
+using CompactLayout = TableLayout<1, 1, 1, 1>;
+using WideLayout = TableLayout<8, 0, 8, 4>;      // Heston, Bates, one-factor models: 160 / 224 KB
+using WideExpLayout = TableLayout<8, 4, 8, 2>;   // SABR kinds (exp table in the step): 224 KB
+using RngView = RngViewT<CompactLayout>;
+using RngViewW = RngViewT<WideLayout>;
+using RngViewS = RngViewT<WideExpLayout>;
+
+// Static shared-memory block of the compact layout.
 template <bool MIXED>
 struct RngShared {
-    MathShared math;
-    double2 coarse[ANG_N * (MIXED ? 2 : 1)];
-    double2 fine[ANG_N];
+    alignas(16) unsigned char bytes[CompactLayout::bytes(MIXED)];
 };
-__host__ __device__ constexpr uint32_t fine_off(bool mixed) {
-    return COARSE_OFF + (uint32_t)ANG_N * 16u * (mixed ? 2u : 1u);
-}
-
-// 32-bit shared-window address of the tables: lookups are one LDS.128 each.
-//
-// REPL = 1: the compact layout above (28 / 36 KB per block, several blocks per SM).  A
-//   random-address LDS.128 then costs ~12.8 shared-memory wavefronts instead of 4 (ncu,
-//   profiles/r01_ncu_heston_summary.md: l1tex 94 %): eight lanes of a quarter-warp pick
-//   eight random 16-byte bank groups.
-// REPL = 8: every 16-byte entry is stored eight times, entry i of copy g at byte
-//   (8 i + g) 16, and lane l reads copy l & 7 -- the eight lanes of a quarter-warp hit eight
-//   different bank groups whatever their entries are: conflict-free by construction
-//   (measured: 1.75e9 -> 6.6e3 conflict wavefronts per C2 launch, l1tex 94 -> 31 %).  The
-//   log table and each direction component take 64 KB, the fine table (four copies, lane
-//   l reads copy l & 3: two lanes of a quarter-warp can meet) 32 KB: 160 / 224 KB, so ONE
-//   block of 768 / 1024 threads per SM shares them.
-template <int REPL>
-struct RngViewT {
-    uint32_t base;          // warp-uniform: address arithmetic stays in uniform registers
-    uint32_t lane;          // REPL > 1: 16 (l & 7), OR-ed into the (masked) entry offset
-    uint32_t lane4;         // REPL > 1: 16 (l & 3), for the four-copy fine table
-    uint32_t k3ff;          // 0x3FF00000 held in a register (mantissa_hi)
-    static constexpr int R = REPL;
-    // address of the entry at (masked) byte offset idx of the table at byte offset `table`
-    __device__ __forceinline__ uint32_t at(uint32_t idx, uint32_t table = 0u) const {
-        if constexpr (REPL == 1) return base + table + idx;
-        else return base + table + (idx | lane);
-    }
-    __device__ __forceinline__ uint32_t at4(uint32_t idx, uint32_t table) const {
-        if constexpr (REPL == 1) return base + table + idx;
-        else return base + table + (idx | lane4);
-    }
+struct MathShared {      // log + exp only (fast_log / fast_exp in kernels without normals)
+    alignas(16) unsigned char bytes[CompactLayout::T1_OFF];
 };
-using RngView = RngViewT<1>;
-using RngViewW = RngViewT<8>;
-constexpr uint32_t WIDE_TABLE_BYTES = 512u * 16u * 8u;       // one 512-entry table, eight copies
-constexpr uint32_t WIDE_COARSE_OFF = WIDE_TABLE_BYTES;       // after the log table
-__host__ __device__ constexpr uint32_t wide_fine_off(bool mixed) {
-    return WIDE_TABLE_BYTES * (mixed ? 3u : 2u);
-}
-__host__ __device__ constexpr uint32_t wide_smem_bytes(bool mixed) {
-    return wide_fine_off(mixed) + WIDE_TABLE_BYTES / 2u;
-}
 
-__device__ __forceinline__ RngView fill_math_shared(MathShared *t) {
-    for (int i = threadIdx.x; i < LOG_N; i += blockDim.x) t->logt[i] = g_rng_base.logt[i];
-    for (int i = threadIdx.x; i < EXP_N; i += blockDim.x) t->exp2t[i] = g_rng_base.exp2t[i];
-    RngView v;
-    v.base = keep_u32((uint32_t)__cvta_generic_to_shared(t));
-    v.lane = v.lane4 = 0u;
-    v.k3ff = keep_u32(0x3FF00000u);
-    return v;
-}
-
-// one coarse row, mixed (see RngShared)
+// one coarse row, mixed (see above)
 __device__ __forceinline__ void mix_row(double2 cs, double m11, double m12, double m21, double m22,
                                         double2 &r1, double2 &r2) {
     r1 = make_double2(fma(m12, cs.y, m11 * cs.x), fma(m12, cs.x, -(m11 * cs.y)));
     r2 = make_double2(fma(m22, cs.y, m21 * cs.x), fma(m22, cs.x, -(m21 * cs.y)));
 }
 
-template <bool MIXED>
-__device__ __forceinline__ RngView fill_rng_shared(RngShared<MIXED> *t, double m11, double m12,
-                                                   double m21, double m22) {
-    RngView v = fill_math_shared(&t->math);
-    for (int i = threadIdx.x; i < ANG_N; i += blockDim.x) {
-        const double2 cs = g_rng_base.coarse[i];
-        if constexpr (MIXED)
-            mix_row(cs, m11, m12, m21, m22, t->coarse[2 * i], t->coarse[2 * i + 1]);
-        else
-            t->coarse[i] = make_double2(m11 * cs.x, m11 * cs.y);
-        t->fine[i] = g_rng_base.fine[i];
-    }
+template <class LAYOUT>
+__device__ __forceinline__ RngViewT<LAYOUT> make_view(const void *smem) {
+    RngViewT<LAYOUT> v;
+    uint32_t laneid;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(laneid));
+    v.base = keep_u32((uint32_t)__cvta_generic_to_shared(smem));
+    // (separately laundered, so that each stays its own register and an entry address is
+    //  ONE three-input logic instruction: (bits & mask) | lane offset)
+    v.l8 = keep_u32((laneid & 7u) * 16u);
+    v.l4 = keep_u32((laneid & 3u) * 16u);
+    v.l2 = keep_u32((laneid & 1u) * 16u);
+    v.le = keep_u32((laneid & (uint32_t)(LAYOUT::EXP_COPIES > 1 ? LAYOUT::EXP_COPIES - 1 : 0)) * 8u);
+    v.k3ff = keep_u32(0x3FF00000u);
     return v;
 }
 
-// Lane-replicated tables in dynamic shared memory (see RngViewT).
-template <bool MIXED>
-__device__ __forceinline__ RngViewW fill_rng_wide(unsigned char *smem, double m11, double m12,
-                                                  double m21, double m22) {
-    double2 *logt = reinterpret_cast<double2 *>(smem);
-    double2 *t1 = reinterpret_cast<double2 *>(smem + WIDE_COARSE_OFF);
-    double2 *t2 = reinterpret_cast<double2 *>(smem + 2 * WIDE_COARSE_OFF);
-    double2 *fine = reinterpret_cast<double2 *>(smem + wide_fine_off(MIXED));
-    for (int i = threadIdx.x; i < LOG_N * 8; i += blockDim.x) logt[i] = g_rng_base.logt[i >> 3];
-    for (int i = threadIdx.x; i < ANG_N * 8; i += blockDim.x) {
-        const double2 cs = g_rng_base.coarse[i >> 3];
+// log (+ exp) tables
+template <class LAYOUT>
+__device__ __forceinline__ void fill_math_tables(unsigned char *smem) {
+    double2 *logt = reinterpret_cast<double2 *>(smem + LAYOUT::LOG_OFF);
+    for (int i = threadIdx.x; i < LOG_N * LAYOUT::LOG_COPIES; i += blockDim.x)
+        logt[i] = g_rng_base.logt[i / LAYOUT::LOG_COPIES];
+    if constexpr (LAYOUT::EXP_COPIES >= 1) {
+        double *expt = reinterpret_cast<double *>(smem + LAYOUT::EXP_OFF);
+        for (int i = threadIdx.x; i < EXP_N * LAYOUT::EXP_COPIES; i += blockDim.x)
+            expt[i] = g_rng_base.exp2t[i / LAYOUT::EXP_COPIES];
+    }
+}
+
+// all tables of a kernel that draws normals
+template <class LAYOUT, bool MIXED>
+__device__ __forceinline__ RngViewT<LAYOUT> fill_rng_tables(unsigned char *smem, double m11,
+                                                            double m12, double m21, double m22) {
+    fill_math_tables<LAYOUT>(smem);
+    double2 *t1 = reinterpret_cast<double2 *>(smem + LAYOUT::T1_OFF);
+    double2 *t2 = reinterpret_cast<double2 *>(smem + LAYOUT::T2_OFF);
+    double2 *fine = reinterpret_cast<double2 *>(smem + LAYOUT::fine_off(MIXED));
+    for (int i = threadIdx.x; i < ANG_N * LAYOUT::ANG_COPIES; i += blockDim.x) {
+        const double2 cs = g_rng_base.coarse[i / LAYOUT::ANG_COPIES];
         if constexpr (MIXED)
             mix_row(cs, m11, m12, m21, m22, t1[i], t2[i]);
         else
             t1[i] = make_double2(m11 * cs.x, m11 * cs.y);
     }
-    for (int i = threadIdx.x; i < ANG_N * 4; i += blockDim.x) fine[i] = g_rng_base.fine[i >> 2];
-    RngViewW v;
-    v.base = keep_u32((uint32_t)__cvta_generic_to_shared(smem));
-    v.lane = keep_u32((threadIdx.x & 7u) * 16u);
-    uint32_t laneid;                    // (a second source, so that the two offsets stay two
-    asm volatile("mov.u32 %0, %%laneid;" : "=r"(laneid));      //  registers: one LOP3 per address)
-    v.lane4 = keep_u32((laneid & 3u) * 16u);
-    v.k3ff = keep_u32(0x3FF00000u);
-    return v;
+    for (int i = threadIdx.x; i < ANG_N * LAYOUT::FINE_COPIES; i += blockDim.x)
+        fine[i] = g_rng_base.fine[i / LAYOUT::FINE_COPIES];
+    return make_view<LAYOUT>(smem);
+}
+
+__device__ __forceinline__ RngView fill_math_shared(MathShared *t) {
+    fill_math_tables<CompactLayout>(t->bytes);
+    return make_view<CompactLayout>(t->bytes);
+}
+
+template <bool MIXED>
+__device__ __forceinline__ RngView fill_rng_shared(RngShared<MIXED> *t, double m11, double m12,
+                                                   double m21, double m22) {
+    return fill_rng_tables<CompactLayout, MIXED>(t->bytes, m11, m12, m21, m22);
 }
 
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
@@ -356,13 +393,6 @@ __device__ __forceinline__ double neg2_log_poly(double m, double2 tb, double kfa
     return fma(p, r, fma(kfac, C_N2LN2, tb.y));
 }
 
-// byte offset of the log-table entry for a double's high word (mantissa bits 19..11)
-template <class V>
-__device__ __forceinline__ uint32_t log_entry(uint32_t hi) {
-    if constexpr (V::R == 1) return (hi >> 7) & ((LOG_N - 1) * 16u);
-    else return (hi >> 4) & ((LOG_N - 1) * 128u);
-}
-
 // high word of the mantissa m in [1, 2) of a positive double with high word hi:
 // (hi & 0xFFFFF) | 0x3FF00000 as ONE three-input logic instruction
 __device__ __forceinline__ int mantissa_hi(int hi, uint32_t k3ff) {
@@ -376,7 +406,7 @@ __device__ __forceinline__ double neg2_log_u(uint32_t lo, uint32_t hi, V t) {
     const double d = __ull2double_rn(((unsigned long long)hi << 32) | lo);      // u 2^64
     const int dh = __double2hiint(d);
     const double m = __hiloint2double(mantissa_hi(dh, t.k3ff), __double2loint(d));
-    const double2 tb = lds_f64x2(t.at(log_entry<V>((uint32_t)dh)));
+    const double2 tb = lds_f64x2(t.log_at((uint32_t)dh));
     return neg2_log_poly(m, tb, (double)((dh - 0x43F00000) >> 20));       // exponent - 64
 }
 
@@ -388,7 +418,7 @@ template <class V>
 __device__ __forceinline__ double fast_log(double s, V t) {
     int hi = __double2hiint(s);
     double m = __hiloint2double((hi & 0xFFFFF) | 0x3FF00000, __double2loint(s));
-    double2 tb = lds_f64x2(t.at(log_entry<V>((uint32_t)hi)));
+    double2 tb = lds_f64x2(t.log_at((uint32_t)hi));
     double r = fma(m, tb.x, 2.0);
     double p = fma(r, 0.03125, C_1_12);
     p = fma(p, r, 0.25);
@@ -407,7 +437,6 @@ __constant__ double C_EXP[3] = {738.65986093514929,              // 512 / ln 2
 #define OPTMC_LN2_N_LO 1.0831887298761837e-11
 template <class V>
 __device__ __forceinline__ double fast_exp(double x, V t) {
-    static_assert(V::R == 1, "the lane-replicated layout carries no exp table");
     const double MAGIC = 6755399441055744.0;          // 1.5 * 2^52: low word = rint(value)
     double tt = fma(x, C_EXP[0], MAGIC);
     int n = __double2loint(tt);
@@ -418,7 +447,7 @@ __device__ __forceinline__ double fast_exp(double x, V t) {
     p = fma(p, r, 0.5);
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
-    double y = p * lds_f64(t.base + EXP_OFF + ((uint32_t)(n & (EXP_N - 1)) << 3));
+    double y = p * lds_f64(t.exp_at((uint32_t)n));
     return __hiloint2double(__double2hiint(y) + ((n >> 9) << 20), __double2loint(y));
 }
 
@@ -459,19 +488,11 @@ template <bool MIXED, class V>
 __device__ __forceinline__ void normal_parts_fast(uint32_t wa, uint32_t wb, double &L, double &t1,
                                                   double &t2, V t) {
     L = relu64(neg2_log_u(radius_lo(wb), wa, t));
-    uint32_t row, fin;
-    if constexpr (V::R == 1) {
-        row = t.at(MIXED ? (wb >> 18) & ((ANG_N - 1) * 32u) : (wb >> 19) & ((ANG_N - 1) * 16u),
-                   COARSE_OFF);
-        fin = t.at((wb >> 10) & ((ANG_N - 1) * 16u), fine_off(MIXED));
-    } else {
-        row = t.at((wb >> 16) & ((ANG_N - 1) * 128u), WIDE_COARSE_OFF);
-        fin = t.at4((wb >> 8) & ((ANG_N - 1) * 64u), wide_fine_off(MIXED));
-    }
+    const uint32_t row = t.coarse_at(wb), fin = t.template fine_at<MIXED>(wb);
     const double2 f = lds_f64x2(fin);                              // (cos b_j, sin b_j)
     if constexpr (MIXED) {
         const double2 r1 = lds_f64x2(row);
-        const double2 r2 = lds_f64x2(row + (V::R == 1 ? 16u : WIDE_TABLE_BYTES));
+        const double2 r2 = lds_f64x2(row + (V::Lay::T2_OFF - V::Lay::T1_OFF));
         t1 = fma(r1.x, f.x, r1.y * f.y);
         t2 = fma(r2.x, f.x, r2.y * f.y);
     } else {
