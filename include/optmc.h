@@ -179,6 +179,9 @@ int optmc_payoff_sweep_async(optmc_ctx *ctx, const double *terminal_dev, int64_t
  *   optmc_european_aux_async  = optmc_european_async that also stores, per draw,
  *                               aux_dev[g] = W, aux_dev[n_local + g] = J and (antithetic)
  *                               aux_dev[2 n_local + g] = J of the partner, whose W is -W
+ *                               (BSM, Merton, Kou; Bates: W slot 0, J = the path's summed
+ *                               log-jumps -- with the device normals of optmc_normals that is
+ *                               everything a path's terminal value is a function of)
  *   optmc_sigma_sweep_async   payoff moments of up to 16 scenarios (a0 = log S_0 + n drift,
  *                             sigma, strike, is_call) over the stored (W, J): what
  *                             GreekMixin.vega's two re-pricings on common random numbers
@@ -318,11 +321,15 @@ int optmc_lsmc_peer_attach(optmc_ctx *ctx, int32_t rank, int32_t world, const vo
  * Diagnostics used by the tests and by bench.py's roofline.
  *   optmc_philox_raw     out_dev[4*i..] = Philox4x32-10(counter = (lo(i), hi(i), c2, c3), key = seed)
  *   optmc_normals        out_dev[2*i], out_dev[2*i+1] = the two N(0,1) of Box-Muller pair
- *                        `step` of draw i: three Philox calls (c2 = 3g..3g+2) feed the four
- *                        pairs 4g..4g+3; a pair drives one step of a two-factor model or two
- *                        consecutive steps of a one-factor model (the per-step jump kernels
- *                        -- SABR-jump, jump path kernels -- use one call per step instead:
- *                        three words for the pair, the fourth for the Poisson draw)
+ *                        `step` of draw i: Philox call c2 = g of stream 0 feeds the pairs 2g
+ *                        (words x, y) and 2g + 1 (words z, w); from the two words (wa, wb) of a
+ *                        pair, u = ((wa : wb[13:0]) + 1/2) 2^-46, angle = 2 pi ((wb >> 14) + 1/2)
+ *                        / 2^18, (z1, z2) = sqrt(-2 ln u) (cos, sin)(angle).  A pair drives one
+ *                        step of a two-factor model or two consecutive steps of a one-factor
+ *                        model (the per-step jump kernels -- jump path kernels with lambda T >
+ *                        2 -- use one call per step instead: words x, y for the pair, w for the
+ *                        Poisson draw).  These are the normals the step loops of
+ *                        optmc_european / optmc_lsmc_paths consume (tests/test_gpu_replay.py).
  *   optmc_fp64_peak      runs a register-resident DFMA loop on every SM for
  *                        ~`iters` iterations and returns fp64 FMA instructions
  *                        per second (thread-level): the measured denominator of

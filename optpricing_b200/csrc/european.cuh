@@ -114,14 +114,15 @@ __device__ __forceinline__ double2 jumps_slow(uint32_t w, double mu, double p0, 
                 acc.y = fma(sd, zb, nd * c.mu_j);
             }
         }
-        return acc;
-    }
-    for (int j = 0; j < n; ++j) {
-        acc.x += jump_size<KIND, NIMPL>(
-            philox4x32_10(make_uint4(id_lo, id_hi, step, 1u | ((uint32_t)j << 8)), key), c, tab);
-        if constexpr (ANTI)
-            acc.y += jump_size<KIND, NIMPL>(
-                philox4x32_10(make_uint4(id_lo, id_hi, step, 2u | ((uint32_t)j << 8)), key), c, tab);
+    } else {
+        for (int j = 0; j < n; ++j) {
+            acc.x += jump_size<KIND, NIMPL>(
+                philox4x32_10(make_uint4(id_lo, id_hi, step, 1u | ((uint32_t)j << 8)), key), c, tab);
+            if constexpr (ANTI)
+                acc.y += jump_size<KIND, NIMPL>(
+                    philox4x32_10(make_uint4(id_lo, id_hi, step, 2u | ((uint32_t)j << 8)), key), c,
+                    tab);
+        }
     }
     return acc;
 }
@@ -172,6 +173,7 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
     constexpr int LOGV = (kind_sabr(KIND) && NIMPL == 1) ? (BGEN ? 2 : 1) : 0;
     init_state<KIND, DEFER, LOGV>(sa, c);
     init_state<KIND, DEFER, LOGV>(sb, c);
+    sa.j = sb.j = 0.0;
     // A Box-Muller pair feeds one step of a two-factor model, or two consecutive
     // steps of a one-factor model (one step when every step needs its own Poisson word).
     constexpr int SPC = (TWO || LEGACY) ? 1 : 2;
@@ -456,6 +458,10 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
                                                       id_lo, id_hi, 0xFFFFFFFFu, c, tab);
             apply_jump<KIND, DEFER>(sa, J.x);
             if constexpr (ANTI) apply_jump<KIND, DEFER>(sb, J.y);
+            if constexpr (KIND == OPTMC_BATES) {
+                sa.j = J.x;
+                sb.j = J.y;
+            }
         }
     }
     finish_deferred<KIND, DEFER>(sa, c);
@@ -497,6 +503,15 @@ __device__ __forceinline__ void accumulate_draw(const EuroArgs &A, int64_t g, co
             A.aux[g] = sa.v;
             A.aux[A.n_local + g] = sa.w;
             if constexpr (ANTI) A.aux[2 * A.n_local + g] = sb.w;
+        }
+    }
+    if constexpr (KIND == OPTMC_BATES) {
+        // the summed log-jumps of the draw and its partner (replay tests: the diffusion part of
+        // a path is a function of the device normals, the jump part is this one number)
+        if (A.aux) {
+            A.aux[g] = 0.0;
+            A.aux[A.n_local + g] = sa.j;
+            if constexpr (ANTI) A.aux[2 * A.n_local + g] = sb.j;
         }
     }
     double ST = terminal_spot(KIND, sa);
@@ -546,13 +561,16 @@ k_european(const EuroArgs A) {
 // block per SM -- 768 threads for the two-factor kinds (85 registers), 1024 for the one-factor
 // models (64) -- whose warps share 160 - 224 KB of (nearly) conflict-free tables in dynamic
 // shared memory.
+#ifndef OPTMC_SJ_THREADS
+#define OPTMC_SJ_THREADS 512
+#endif
 __host__ __device__ constexpr int wide_threads(int kind, bool sched = false) {
 #ifdef OPTMC_WIDE_THREADS
     return OPTMC_WIDE_THREADS;
 #else
-    // (SABR-jump on the jump schedule keeps eight jump factors in its jump groups: 640
-    // threads = 102 registers, no spills)
-    return kind == OPTMC_SABR_JUMP && sched ? 640 : kind_two_factor(kind) ? 768 : 1024;
+    // (SABR-jump on the jump schedule keeps eight jump factors in its jump groups: 512
+    // threads = 128 registers; 15.3 ms at 2^24 x 252 against 15.8 with 640, 16.0 with 768)
+    return kind == OPTMC_SABR_JUMP && sched ? OPTMC_SJ_THREADS : kind_two_factor(kind) ? 768 : 1024;
 #endif
 }
 template <int KIND>

@@ -68,7 +68,8 @@ __host__ __device__ constexpr bool kind_sabr(int k) {
 struct State {
     double x;  // log S (S for SABR kinds); with DEFER: the stochastic part only
     double v;  // variance (Heston/Bates, stored before the floor) or vol (SABR)
-    double w;  // DEFER only: running sum of v_pos (Heston/Bates)
+    double w;  // DEFER only: running sum of v_pos (Heston/Bates); sum of log-jumps (Merton/Kou)
+    double j;  // Bates terminal kernels: the path's summed log-jumps (written once, after the loop)
 };
 
 // DEFER (terminal-value kernels of the log models): the deterministic drift is

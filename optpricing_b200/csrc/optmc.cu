@@ -529,8 +529,8 @@ extern "C" int optmc_european_aux_async(optmc_ctx *ctx, const optmc_model *model
     if (!ctx) return -2;
     CK(cudaSetDevice(ctx->device));
     if (aux_dev && model && !(model->kind == OPTMC_BSM || model->kind == OPTMC_MERTON ||
-                              model->kind == OPTMC_KOU))
-        FAIL("aux_dev (W, J) exists for the one-factor log-Euler models only (BSM, Merton, Kou)");
+                              model->kind == OPTMC_KOU || model->kind == OPTMC_BATES))
+        FAIL("aux_dev exists for BSM, Merton, Kou (W, J) and Bates (J) only");
     if (aux_dev && sim && sim->precision != OPTMC_FP64) FAIL("aux_dev needs the fp64 mode");
     if (n_contracts < 1 || !strikes || !is_call || !moments_dev) FAIL("bad contract arguments");
     if (n_contracts > 1 && !terminal_dev)

@@ -26,3 +26,27 @@ KAT = [
     ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0),
      (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)),
 ]
+
+
+def pair_words(seed, ids, pair):
+    """The two Philox words (wa, wb) of Box-Muller pair `pair` of draws `ids`
+    (csrc/philox.cuh: philox_pair_words -- call c2 = pair // 2 of stream 0, words
+    (x, y) for even pairs, (z, w) for odd ones)."""
+    ids = np.asarray(ids, dtype=np.uint64)
+    n = ids.size
+    w = philox4x32_10(ids.astype(np.uint32), (ids >> np.uint64(32)).astype(np.uint32),
+                      np.full(n, pair // 2, np.uint32), np.zeros(n, np.uint32),
+                      int(seed) & 0xFFFFFFFF, int(seed) >> 32)
+    return (w[:, 2], w[:, 3]) if pair & 1 else (w[:, 0], w[:, 1])
+
+
+def normals_from_words(wa, wb):
+    """numpy restatement of the device's word -> N(0,1) pair mapping (csrc/philox.cuh):
+    u = ((wa : wb[13:0]) + 1/2) 2^-46, angle = 2 pi ((wb >> 14) + 1/2) / 2^18."""
+    wa = wa.astype(np.uint64)
+    wb = wb.astype(np.uint64)
+    x = (wa << np.uint64(14)) | (wb & np.uint64(0x3FFF))          # 46 random bits
+    u = (x.astype(np.float64) + 0.5) * 2.0 ** -46
+    rad = np.sqrt(-2.0 * np.log(u))
+    ang = 2.0 * np.pi * ((wb >> np.uint64(14)).astype(np.float64) + 0.5) / 2.0 ** 18
+    return rad * np.cos(ang), rad * np.sin(ang)
