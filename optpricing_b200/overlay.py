@@ -43,8 +43,16 @@ _ALIASES = {
 _CLASSES = ("MonteCarloTechnique", "AmericanMonteCarloTechnique")
 
 
-def install(reference_src: str | None = None) -> None:
+def install(reference_src: str | None = None, rng_mode: str | None = None) -> None:
+    """``rng_mode`` ("philox" | "numpy" | None): the draw source of techniques constructed
+    without an explicit ``rng_mode=`` from now on (None: leave it -- "philox" unless
+    OPTPRICING_B200_RNG_MODE is set).  "numpy" replays the reference's own host draws, so seeded
+    prices equal the reference's to 1e-12; "philox" is the throughput mode and meets the same
+    contracts statistically."""
     reference_src = reference_src or os.environ.get("OPTPRICING_REFERENCE_SRC")
+    if rng_mode is not None:
+        from optpricing_b200.techniques.monte_carlo import set_default_rng_mode
+        set_default_rng_mode(rng_mode)
     if "optpricing" not in sys.modules and reference_src:
         pkg_dir = os.path.join(reference_src, "optpricing")
         if not os.path.isdir(pkg_dir):

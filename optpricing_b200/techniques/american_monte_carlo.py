@@ -28,7 +28,7 @@ from optpricing_b200.models import model_kind
 from .base import BaseTechnique, GreekMixin, IVMixin, PricingResult
 from .kernels import path_kernels
 from .kernels.american_mc_kernels import DevicePathStore, longstaff_schwartz_pricer
-from .monte_carlo import shard_draws
+from .monte_carlo import default_rng_mode, shard_draws
 
 _PATH_KERNELS = {
     "bsm": path_kernels.bsm_path_kernel, "heston": path_kernels.heston_path_kernel,
@@ -40,10 +40,11 @@ _PATH_KERNELS = {
 
 class AmericanMonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
     def __init__(self, *, n_paths: int = 20_000, n_steps: int = 100, antithetic: bool = True,
-                 seed: int | None = None, lsm_degree: int = 2, rng_mode: str = "philox",
+                 seed: int | None = None, lsm_degree: int = 2, rng_mode: str | None = None,
                  distributed: bool | None = None, exchange: str = "nvlink"):
         if antithetic and n_paths % 2 != 0:
             n_paths += 1                       # american_monte_carlo.py:44-45
+        rng_mode = rng_mode or default_rng_mode()
         if rng_mode not in ("philox", "numpy"):
             raise ValueError("rng_mode must be 'philox' or 'numpy'")
         if exchange not in ("nvlink", "nccl"):

@@ -32,6 +32,7 @@ from __future__ import annotations
 
 import contextlib
 import math
+import os
 from typing import Any
 
 import numpy as np
@@ -153,14 +154,32 @@ class DeviceTerminal:
         self.moments, self.kind, self.seed = moments, kind, seed
 
 
+def default_rng_mode() -> str:
+    """Draw source of a technique constructed without ``rng_mode=``: "philox" (device RNG)
+    unless ``overlay.install(rng_mode=...)`` or OPTPRICING_B200_RNG_MODE says "numpy" -- the
+    mode in which a seeded technique reproduces the reference's own numbers (and its
+    lucky-seed acceptance test, tests/techniques/test_monte_carlo.py:111-126) to 1e-12."""
+    return _DEFAULT_RNG_MODE[0] or os.environ.get("OPTPRICING_B200_RNG_MODE", "philox")
+
+
+_DEFAULT_RNG_MODE = [None]
+
+
+def set_default_rng_mode(mode: str | None) -> None:
+    if mode not in (None, "philox", "numpy"):
+        raise ValueError("rng_mode must be 'philox' or 'numpy'")
+    _DEFAULT_RNG_MODE[0] = mode
+
+
 class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
     def __init__(self, *, n_paths: int = 20_000, n_steps: int = 100, antithetic: bool = True,
-                 seed: int | None = None, rng_mode: str = "philox",
+                 seed: int | None = None, rng_mode: str | None = None,
                  correlation: str = "reference", control_variate: bool = False,
                  distributed: bool | None = None, precision: str = "fp64",
                  steps_per_year: int | None = None, report_stats: bool = False):
         if antithetic and n_paths % 2 != 0:
             n_paths += 1                       # monte_carlo.py:58-59
+        rng_mode = rng_mode or default_rng_mode()
         if rng_mode not in ("philox", "numpy"):
             raise ValueError("rng_mode must be 'philox' or 'numpy'")
         if correlation not in ("reference", "independent"):
