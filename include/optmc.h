@@ -143,7 +143,8 @@ int optmc_european(optmc_ctx *ctx, const optmc_model *model, const optmc_sim *si
  *   jumps_dev      double[n_jumps]  jump sizes in the order the reference pulls
  *                  them from its RNG: by step, then path, then jump
  *                  (Merton/Bates/Kou: additive log-jumps; SABR-jump: the
- *                  N(mu_j, sigma_j) draws, exponentiated here)
+ *                  N(mu_j, sigma_j) draws, exponentiated here).  A path whose counts ask
+ *                  for sizes beyond n_jumps comes out NaN; nothing is read out of bounds
  *   x0             log_s0, or s0 for the SABR kinds (monte_carlo.py:217-220)
  *   sign           +1.0, or -1.0 for the antithetic second pass
  *                  (monte_carlo.py:247-254) without touching the buffers

@@ -558,6 +558,25 @@ class Engine:
 _engines = {}
 _lock = threading.Lock()
 
+# One pricing at a time per process.  The C ABI is not re-entrant per context (optmc.h) and
+# Engine.buffer() hands every caller the same cached device buffers, so two techniques priced
+# from two Python threads would overwrite each other's terminals / moments.  Every public
+# entry point of the techniques and of the fed-kernel wrappers runs under this re-entrant
+# lock (greeks call price(); price() may call price_many()).  One process drives one GPU, so
+# a process-wide lock serialises exactly the calls that share a context.
+PRICING_LOCK = threading.RLock()
+
+
+def serialized(fn):
+    """Decorator: run ``fn`` under PRICING_LOCK."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        with PRICING_LOCK:
+            return fn(*args, **kwargs)
+    return wrapper
+
 
 def get_engine(device: int | None = None) -> Engine:
     """The process-wide engine for ``device`` (default: torch's current device)."""

@@ -39,8 +39,9 @@ struct EuroArgs {
     // Poisson constants for a draw covering 1 step ([0]) or 2 steps ([1])
     double pois_mu[2], pois_p0[2];
     uint32_t pois_p0_bits[2];
-    double pois_mu_path, pois_p0_path;   // lambda T and exp(-lambda T): whole-path jump count
-    uint32_t pois_p0_path_bits;          // floor(exp(-lambda T) 2^32)
+    double pois_mu_path, pois_p0_path;   // lambda T / pois_chunks and exp(-that): whole-path count
+    uint32_t pois_p0_path_bits;          // floor(exp(-lambda T / pois_chunks) 2^32)
+    int pois_chunks;                     // 1 unless lambda T > 16 (terminal kernels only)
     double *partials;   // [gridDim.x][NPART]
     double *terminal;   // optional [n_local * (anti ? 2 : 1)]
     double *aux;        // optional, one-factor log models: [W | J | J partner], n_local each
@@ -90,11 +91,9 @@ __device__ __forceinline__ double jump_size(uint4 w, const Consts &c, V tab) {
 // kernel parameters (constants, Philox key) to be copied to local memory so that
 // their address can be taken.
 template <int KIND, bool ANTI, int NIMPL = 0, class V = RngView>
-__device__ __forceinline__ double2 jumps_slow(uint32_t w, double mu, double p0, const PhiloxKey &key,
-                                           uint32_t id_lo, uint32_t id_hi, uint32_t step,
-                                           const Consts &c, V tab = V{}) {
-    uint4 e = philox4x32_10(make_uint4(id_lo, id_hi, step, 0xFFu), key);
-    int n = poisson_slow(w, e.x, mu, p0);
+__device__ __forceinline__ double2 jump_sum(int n, const PhiloxKey &key, uint32_t id_lo,
+                                            uint32_t id_hi, uint32_t step, const Consts &c,
+                                            V tab = V{}) {
     double2 acc = make_double2(0.0, 0.0);
     if constexpr (KIND != OPTMC_KOU) {
         // n iid N(mu_J, sigma_J^2) sizes sum to N(n mu_J, n sigma_J^2): ONE normal per path and
@@ -125,6 +124,14 @@ __device__ __forceinline__ double2 jumps_slow(uint32_t w, double mu, double p0, 
         }
     }
     return acc;
+}
+
+template <int KIND, bool ANTI, int NIMPL = 0, class V = RngView>
+__device__ __forceinline__ double2 jumps_slow(uint32_t w, double mu, double p0, const PhiloxKey &key,
+                                           uint32_t id_lo, uint32_t id_hi, uint32_t step,
+                                           const Consts &c, V tab = V{}) {
+    uint4 e = philox4x32_10(make_uint4(id_lo, id_hi, step, 0xFFu), key);
+    return jump_sum<KIND, ANTI, NIMPL>(poisson_slow(w, e.x, mu, p0), key, id_lo, id_hi, step, c, tab);
 }
 
 // Simulate one draw over all steps.  SINK(step_index, sa, sb) is called after
@@ -452,10 +459,17 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
         }
     }
     if constexpr (JUMPS_AT_END) {
-        uint4 e = philox4x32_10(make_uint4(id_lo, id_hi, 0xFFFFFFFFu, 0xFEu), A.key);
-        if (poisson_maybe(e.x, A.pois_p0_path_bits)) {
-            double2 J = jumps_slow<KIND, ANTI, NIMPL>(e.x, A.pois_mu_path, A.pois_p0_path, A.key,
-                                                      id_lo, id_hi, 0xFFFFFFFFu, c, tab);
+        // N ~ Poisson(lambda T) as the sum of pois_chunks independent Poisson(lambda T / chunks)
+        // draws (one chunk unless lambda T > 16: the CDF walk of poisson_slow stays short and
+        // exp(-mu) far from underflow whatever the intensity), then the summed sizes of N jumps
+        int n = 0;
+        for (int ch = 0; ch < A.pois_chunks; ++ch) {
+            const uint4 e = philox4x32_10(make_uint4(id_lo, id_hi, 0xFFFFFFFFu - (uint32_t)ch, 0xFEu), A.key);
+            if (poisson_maybe(e.x, A.pois_p0_path_bits))
+                n += poisson_slow(e.x, e.y, A.pois_mu_path, A.pois_p0_path);
+        }
+        if (n > 0) {
+            double2 J = jump_sum<KIND, ANTI, NIMPL>(n, A.key, id_lo, id_hi, 0xFFFFFFFFu, c, tab);
             apply_jump<KIND, DEFER>(sa, J.x);
             if constexpr (ANTI) apply_jump<KIND, DEFER>(sb, J.y);
             if constexpr (KIND == OPTMC_BATES) {

@@ -133,10 +133,15 @@ __global__ void __launch_bounds__(EURO_THREADS, 4) k_european_f32(const EuroArgs
         } else {
             double ja = 0.0, jb = 0.0;
             if constexpr (JUMPS) {                               // whole-path jump draw (european.cuh)
-                uint4 e = philox4x32_10(make_uint4(id_lo, id_hi, 0xFFFFFFFFu, 0xFEu), A.key);
-                if (poisson_maybe(e.x, A.pois_p0_path_bits)) {
-                    double2 J = jumps_slow<KIND, ANTI>(e.x, A.pois_mu_path, A.pois_p0_path, A.key,
-                                                       id_lo, id_hi, 0xFFFFFFFFu, c);
+                int n = 0;
+                for (int ch = 0; ch < A.pois_chunks; ++ch) {
+                    const uint4 e = philox4x32_10(
+                        make_uint4(id_lo, id_hi, 0xFFFFFFFFu - (uint32_t)ch, 0xFEu), A.key);
+                    if (poisson_maybe(e.x, A.pois_p0_path_bits))
+                        n += poisson_slow(e.x, e.y, A.pois_mu_path, A.pois_p0_path);
+                }
+                if (n > 0) {
+                    double2 J = jump_sum<KIND, ANTI>(n, A.key, id_lo, id_hi, 0xFFFFFFFFu, c);
                     ja = J.x;
                     jb = J.y;
                 }

@@ -153,8 +153,11 @@ __global__ void __launch_bounds__(FED_P) k_fed(const FedArgs A) {
             if constexpr (JUMPS) {
                 int n = cnt[tid][j];
                 if (n > 0) {
-                    const double *jb =
-                        A.jumps + A.base[(size_t)(t0 + j) * A.n_blocks + blockIdx.x] + pre[tid][j];
+                    const int64_t j0 = A.base[(size_t)(t0 + j) * A.n_blocks + blockIdx.x] + pre[tid][j];
+                    // counts that ask for more sizes than the caller's buffer holds read none
+                    // beyond it (a NaN marks the path instead of an out-of-bounds access)
+                    if (j0 + n > A.n_jumps) { s.x = __longlong_as_double(0x7ff8000000000000LL); n = 0; }
+                    const double *jb = A.jumps + j0;
                     if (KIND != OPTMC_SABR_JUMP && A.sum_mode) {
                         double acc = 0.0;                       // np.sum(slice), path_kernels.py:116
                         for (int k = 0; k < n; ++k) acc += jb[k];
@@ -294,13 +297,17 @@ k_fed_stream(const FedArgs A) {
                         if (lane >= o) incl += t;
                     }
                     if (cnt > 0) {
-                        const double *jb = A.jumps + A.base[(size_t)i * A.n_blocks + wblk] + (incl - cnt);
+                        const int64_t j0 = A.base[(size_t)i * A.n_blocks + wblk] + (incl - cnt);
+                        int nj = cnt;
+                        // (see k_fed: no read beyond the caller's n_jumps; the path becomes NaN)
+                        if (j0 + nj > A.n_jumps) { s.x = __longlong_as_double(0x7ff8000000000000LL); nj = 0; }
+                        const double *jb = A.jumps + j0;
                         if (KIND != OPTMC_SABR_JUMP && A.sum_mode) {
                             double acc = 0.0;                     // np.sum(slice), path_kernels.py:116
-                            for (int k = 0; k < cnt; ++k) acc += jb[k];
+                            for (int k = 0; k < nj; ++k) acc += jb[k];
                             s.x += acc;
                         } else {
-                            for (int k = 0; k < cnt; ++k) apply_jump<KIND>(s, jb[k]);
+                            for (int k = 0; k < nj; ++k) apply_jump<KIND>(s, jb[k]);
                         }
                     }
                 }

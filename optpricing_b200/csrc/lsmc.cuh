@@ -373,16 +373,45 @@ __device__ __forceinline__ uint4 ll_peek(const uint4 *slot) {
     return w;
 }
 
-// `w` is a first look at the slot; spin until both halves carry `tag`.  False on timeout
-// (a lost block or rank, never the normal path: ~ seconds, and only the first wait of a
-// thread pays it -- callers stop waiting once they have seen one).
+// Wall clock (ns).  %globaltimer ticks every ~0.26 us: fine for a time-out, too coarse for the
+// phase stamps above.
+__device__ __forceinline__ unsigned long long wall_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// How long a block waits for another block -- or another PROCESS's kernel on a peer GPU --
+// before it gives up: wall-clock, generous (first-call module loads, a rank delayed by the
+// host), and independent of clocks and of how fast a poll is.
+#ifndef OPTMC_LL_TIMEOUT_NS
+#define OPTMC_LL_TIMEOUT_NS 20000000000ull
+#endif
+// A block that has given up keeps publishing -- correctly tagged, so nobody waits for it --
+// but publishes POISON instead of sums computed from garbage: whoever consumes it gives up
+// too, so every block of every rank ends with the error flag set instead of some of them
+// silently returning numbers built on a missing contribution.
+constexpr uint32_t LL_POISON_HI = 0x7FF8DEADu, LL_POISON_LO = 0xDEADDEADu;
+__device__ __forceinline__ double ll_poison() {
+    return __hiloint2double((int)LL_POISON_HI, (int)LL_POISON_LO);
+}
+
+// `w` is a first look at the slot; spin until both halves carry `tag`.  False on time-out or
+// poison (a lost block or rank, never the normal path); `dead`: this thread has already given
+// up once and does not wait again.
 __device__ __forceinline__ bool ll_wait(const uint4 *slot, uint32_t tag, uint4 w, double &v,
                                         bool dead = false) {
     unsigned int spins = 0;
+    unsigned long long t0 = 0;
     while (w.y != tag || w.w != tag) {
-        if (dead || ++spins > (1u << 22)) return false;
+        if (dead) return false;
+        if ((++spins & 0x3FFu) == 0u) {
+            const unsigned long long now = wall_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > OPTMC_LL_TIMEOUT_NS) return false;
+        }
         w = ll_peek(slot);
     }
+    if (w.z == LL_POISON_HI && w.x == LL_POISON_LO) return false;
     v = __hiloint2double((int)w.z, (int)w.x);
     return true;
 }
@@ -506,7 +535,7 @@ k_lsmc_persistent(const LsmcPersistArgs A) {
                     }
                 }
             }
-            __syncthreads();
+            timed_out = __syncthreads_or(timed_out);     // block-wide: one lost slot poisons the block
             if (stamp) A.timing[(size_t)(date + 1) * 4 + 1] = globaltimer_ns();
             for (int e = warp; e < NV; e += NW) {
                 double t = 0.0;
@@ -526,7 +555,7 @@ k_lsmc_persistent(const LsmcPersistArgs A) {
                 if (blockIdx.x == 0 && threadIdx.x < OPTMC_LSMC_GRAM * A.world) {
                     const int r = threadIdx.x / OPTMC_LSMC_GRAM, e = threadIdx.x % OPTMC_LSMC_GRAM;
                     ll_store_sys(A.peer_rank_slots[r] + base + (size_t)A.rank * LSMC_P_STRIDE + e,
-                                 tot[e], ptag);
+                                 timed_out ? ll_poison() : tot[e], ptag);
                 }
                 __syncthreads();         // everyone has read its own tot[] before it is overwritten
                 double v = 0.0;
@@ -540,7 +569,7 @@ k_lsmc_persistent(const LsmcPersistArgs A) {
                     }
                     tot[threadIdx.x] = v;
                 }
-                __syncthreads();
+                timed_out = __syncthreads_or(timed_out);
             }
             if (warp == 0) {
                 if (blockIdx.x == 0 && lane < OPTMC_LSMC_GRAM)
@@ -597,13 +626,13 @@ k_lsmc_persistent(const LsmcPersistArgs A) {
             const int e = P == 32 ? lane : lane >> 1;
             if (e < NV && (P == 32 || (lane & 1) == 0)) scratch[e * 32 + warp] = v[0];
         }
-        __syncthreads();
+        timed_out = __syncthreads_or(timed_out);
         for (int e = warp; e < NV; e += NW) {
             double t = lane < NW ? scratch[e * 32 + lane] : 0.0;
             t = warp_sum(t);
             if (lane == 0)
-                ll_store(A.slots + ((size_t)(epoch & 1u) * G + blockIdx.x) * LSMC_P_STRIDE + e, t,
-                         (A.nonce << 12) | (epoch & 0xFFFu));
+                ll_store(A.slots + ((size_t)(epoch & 1u) * G + blockIdx.x) * LSMC_P_STRIDE + e,
+                         timed_out ? ll_poison() : t, (A.nonce << 12) | (epoch & 0xFFFu));
         }
         ++epoch;
     }

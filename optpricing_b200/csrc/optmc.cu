@@ -295,7 +295,9 @@ static int make_consts(optmc_ctx *ctx, const optmc_model *m, double x0, double d
 }
 
 static void poisson_consts(EuroArgs &A) {
-    A.pois_mu_path = A.c.lam_dt * A.n_steps;
+    const double mu_T = A.c.lam_dt * A.n_steps;
+    A.pois_chunks = mu_T > 16.0 ? (int)std::min(std::ceil(mu_T / 16.0), 65536.0) : 1;
+    A.pois_mu_path = mu_T / A.pois_chunks;
     A.pois_p0_path = std::exp(-A.pois_mu_path);
     A.pois_p0_path_bits =
         (uint32_t)std::min(std::floor(A.pois_p0_path * 4294967296.0), 4294967295.0);
@@ -351,7 +353,7 @@ static int euro_grid(optmc_ctx *ctx, K kernel, int64_t n_local) {
 // is small enough for eight register slots to hold nearly every path's jumps, else a Poisson
 // word per step.
 static bool use_jump_schedule(const EuroArgs &A) {
-    return A.pois_mu_path <= 2.0 && A.n_steps < 65535;
+    return A.pois_chunks == 1 && A.pois_mu_path <= 2.0 && A.n_steps < 65535;
 }
 
 template <int KIND, bool ANTI, int NIMPL, bool SCHED = false, bool BGEN = false>

@@ -171,7 +171,7 @@ class CGMYModel(_LevyModel):
 
     def raw_cf(self, *, t: float):                      # models/cgmy.py:103-132
         import numpy as np
-        from math import gamma as gamma_func
+        from scipy.special import gamma as gamma_func     # the reference's: inf at Y = 1 -> nan
         C, G, M, Y = (self.params[k] for k in ("C", "G", "M", "Y"))
         return lambda u: np.exp(C * t * gamma_func(-Y) * ((M - 1j * u) ** Y - M ** Y
                                                           + (G + 1j * u) ** Y - G ** Y))

@@ -58,6 +58,7 @@ class AmericanMonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
         self.rng_mode = rng_mode
         self.distributed = distributed
 
+    @_engine.serialized
     def price(self, option, stock, model, rate, **kwargs: Any) -> PricingResult:
         if not model.supports_sde:
             raise TypeError("American MC pricing requires an SDE model.")
@@ -68,10 +69,23 @@ class AmericanMonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
         # Several ranks: the per-date Gram exchange runs inside the persistent kernel
         # over NVLink peer memory (default), or as one NCCL all-reduce per date.
         peers = sharded and self.exchange == "nvlink" and self._nvlink_ready(spot_paths.engine)
-        value = longstaff_schwartz_pricer(
-            stock_paths=spot_paths, K=option.strike, dt=option.maturity / self.n_steps,
-            r=rate.get_rate(option.maturity), is_call=_is_call(option), degree=self.lsm_degree,
-            all_reduce=all_reduce if sharded and not peers else None, peers=peers)
+        args = dict(stock_paths=spot_paths, K=option.strike, dt=option.maturity / self.n_steps,
+                    r=rate.get_rate(option.maturity), is_call=_is_call(option),
+                    degree=self.lsm_degree)
+        if not sharded:
+            return PricingResult(price=longstaff_schwartz_pricer(**args))
+        # A joint launch waits, on the device, for the kernels of the other PROCESSES: every
+        # rank must actually enter it.  Shard sizes are a function of (n_paths, world) alone, so
+        # every rank checks ALL shards locally and all raise together, before anything is
+        # launched, when one of them would be empty.  Should a rank still fail to arrive (host
+        # error, lost process), the others give up after a wall-clock time-out and poison what
+        # they publish (csrc/lsmc.cuh), so every rank that did launch raises EngineError.
+        num_draws = self.n_paths // 2 if self.antithetic else self.n_paths
+        if min(shard_draws(num_draws, rk, world)[1] for rk in range(world)) < 1:
+            raise ValueError(f"n_paths = {self.n_paths} leaves a rank without paths when sharded "
+                             f"over {world} ranks; use distributed=False for a job this small")
+        value = longstaff_schwartz_pricer(**args, peers=peers,
+                                          all_reduce=None if peers else all_reduce)
         return PricingResult(price=value)
 
     @staticmethod

@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from optpricing_b200._engine import get_engine, make_model
+from optpricing_b200._engine import get_engine, make_model, serialized
 
 
 def jump_draws_normal(jump_counts, mu_j, sigma_j):
@@ -32,6 +32,7 @@ def jump_draws_kou(jump_counts, p_up, eta1, eta2):
     return np.concatenate(chunks) if chunks else np.zeros(0)
 
 
+@serialized
 def run(kind, params, r, q, dt, x0, v0, dw1, dw2=None, jump_counts=None, jumps=None, *,
         paths=False, sum_mode=0, local_vol=None):
     eng = get_engine()

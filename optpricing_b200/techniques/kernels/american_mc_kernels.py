@@ -11,7 +11,7 @@ from __future__ import annotations
 
 import numpy as np
 
-from optpricing_b200._engine import get_engine
+from optpricing_b200._engine import get_engine, serialized
 
 
 class DevicePathStore:
@@ -31,6 +31,7 @@ class DevicePathStore:
         return out if dtype is None else out.astype(dtype)
 
 
+@serialized
 def longstaff_schwartz_pricer(stock_paths, K, dt, r, is_call, degree, all_reduce=None,
                               peers=False):
     """

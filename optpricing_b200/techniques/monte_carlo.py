@@ -219,6 +219,7 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
             self.n_steps = saved
 
     # ------------------------------------------------------------------ price
+    @_engine.serialized
     def price(self, option, stock, model, rate, **kwargs: Any):
         """``technique.price(option, stock, model, rate) -> PricingResult`` (monte_carlo.py:65-116)."""
         if self.steps_per_year is not None and not isinstance(option, (list, tuple, np.ndarray)):
@@ -298,11 +299,8 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
             kp.update(sigma=p["sigma"])
         elif kind == "bsm":
             kp["sigma"] = p.get("sigma")
-        elif kind == "dupire":
-            # the reference returns dupire_kernel without its vol_surface_func argument
-            # (monte_carlo.py:146-147), so its Dupire branch cannot run; the callable is
-            # what the kernel needs
-            kp["vol_surface_func"] = p["vol_surface"]
+        # (dupire: the kernel's vol_surface_func is added by the simulator, as in the
+        #  reference -- monte_carlo.py:146-147 returns the kernel, :243-244 adds the callable)
         if kind in ("sabr_jump", "bates", "merton"):
             kp.update(lambda_=p["lambda"], mu_j=p["mu_j"], sigma_j=p["sigma_j"])
         return _KERNELS[kind], kp
@@ -383,8 +381,13 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
             args["dw"] = self.rng.standard_normal(size=shape) * sd
         if model.has_jumps:
             args["jump_counts"] = self.rng.poisson(lam=model.params["lambda"] * dt, size=shape)
+        local_vol = getattr(model, "is_local_vol", False)
+        if local_vol:
+            args["vol_surface_func"] = model.params["vol_surface"]             # :243-244
         ST = kernel(**args)
-        if self.antithetic:
+        # the reference skips the antithetic pass for local-vol models (:247): n_paths / 2
+        # plain samples -- reproduced here so that same-seed prices and sample counts agree
+        if self.antithetic and not local_vol:
             for key in ("dw", "dw1", "dw2"):
                 if key in args:
                     args[key] = -args[key]
@@ -441,6 +444,7 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
             all_reduce(dev[: n * _engine.NMOM])
         return dev[: n * _engine.NMOM].cpu().numpy().reshape(n, _engine.NMOM), kind, seed
 
+    @_engine.serialized
     def price_many(self, options, stock, model, rate, **kwargs: Any) -> np.ndarray:
         """
         Prices of many European contracts on one underlying.  Contracts sharing a
@@ -485,6 +489,7 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
                 self.last_stats_many._set(i, row, r, T, c_mean, seed)
         return prices
 
+    @_engine.serialized
     def price_frame(self, options_df, stock, model, rate, **kwargs: Any) -> np.ndarray:
         """
         Prices of the contracts of a DataFrame with ``strike``, ``maturity`` and
@@ -547,12 +552,14 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
             out.append(f * st.get("cv_price", st["price"]))
         return out
 
+    @_engine.serialized
     def delta(self, option, stock, model, rate, h_frac: float = 1e-3, **kwargs: Any) -> float:
         if not self._scaling_greeks_ok(model):
             return super().delta(option, stock, model, rate, h_frac, **kwargs)
         up, dn = self._bumped_prices(option, stock, model, rate, (1 + h_frac, 1 - h_frac), **kwargs)
         return (up - dn) / (2 * stock.spot * h_frac)
 
+    @_engine.serialized
     def gamma(self, option, stock, model, rate, h_frac: float = 1e-3, **kw: Any) -> float:
         if not self._scaling_greeks_ok(model):
             return super().gamma(option, stock, model, rate, h_frac, **kw)
@@ -561,6 +568,7 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
         h = stock.spot * h_frac
         return (up - 2 * mid + dn) / (h * h)
 
+    @_engine.serialized
     def rho(self, option, stock, model, rate, h: float = 1e-4, **kw: Any) -> float:
         if not self._scaling_greeks_ok(model):
             return super().rho(option, stock, model, rate, h, **kw)
@@ -603,6 +611,7 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
 
     _ONE_FACTOR_KINDS = ("bsm", "merton", "kou")
 
+    @_engine.serialized
     def vega(self, option, stock, model, rate, h: float = 1e-4, **kw: Any) -> float:
         """
         GreekMixin.vega (greek_mixin.py:125-175): central difference in ``sigma`` on common
@@ -652,6 +661,7 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
             prices.append(st["cv_price"] if self.control_variate and "cv_price" in st else st["price"])
         return (prices[0] - prices[1]) / (2 * h)
 
+    @_engine.serialized
     def implied_volatility(self, option, stock, model, rate, target_price: float,
                            low: float = 1e-6, high: float = 5.0, tol: float = 1e-6,
                            **kwargs: Any) -> float:
@@ -716,6 +726,13 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
             if not hasattr(model, "raw_cf"):
                 raise NotImplementedError(f"Levy model '{model.name}' is missing required methods.")
             return self._device_terminal(model, S0, r, q, T, hint=self._hint)
+        if self.rng_mode == "numpy" and not hasattr(model, "sample_terminal_log_return") \
+                and levy_kind(model) is not None:
+            raise NotImplementedError(
+                f"rng_mode='numpy' prices '{model.name}' through the model's own host sampler "
+                "(sample_terminal_log_return, as the reference's model classes have); this "
+                "engine's model classes sample on the device only -- use rng_mode='philox' or "
+                "pass the reference's model object")
         if not hasattr(model, "sample_terminal_log_return") or not hasattr(model, "raw_cf"):
             raise NotImplementedError(f"Levy model '{model.name}' is missing required methods.")
         x = model.sample_terminal_log_return(T, self.n_paths, self.rng)

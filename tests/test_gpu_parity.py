@@ -966,3 +966,48 @@ def test_report_stats_travel_with_the_price(price_goldens):
     assert abs(res.price - price_goldens["G1_closed_form"]) < 4 * g["stderr"]
     assert ob.MonteCarloTechnique(n_paths=1 << 12, n_steps=4, seed=2).price(
         CALL, ST, ob.BSMModel(), RT).greeks == {}                     # default: the reference's result
+
+
+def test_pricings_from_two_threads_do_not_share_buffers():
+    """Engine.buffer() hands out cached device buffers; the techniques' entry points run under
+    one re-entrant process-wide lock, so concurrent callers get what serial callers get."""
+    from concurrent.futures import ThreadPoolExecutor
+    jobs = [("heston", 1 << 20, 40, 3), ("bsm", 1 << 21, 16, 4), ("kou", 1 << 19, 64, 5),
+            ("bates", 1 << 20, 24, 6)] * 3
+
+    def price(job):
+        kind, n, m, seed = job
+        t = ob.MonteCarloTechnique(n_paths=n, n_steps=m, seed=seed)
+        return (t.price(CALL, STQ, MODELS[kind](), RT).price,
+                t.delta(CALL, STQ, MODELS[kind](), RT))
+    serial = [price(j) for j in jobs]
+    with ThreadPoolExecutor(max_workers=6) as ex:
+        threaded = list(ex.map(price, jobs))
+    assert threaded == serial
+
+
+def test_large_jump_intensity_whole_path_draw(eng):
+    """lambda T far beyond where exp(-lambda T) is usable (the whole-path count is drawn in
+    chunks of intensity <= 16): the martingale control mean and the one-step exact law hold."""
+    p = {"sigma": 0.1, "lambda": 900.0, "mu_j": -0.001, "sigma_j": 0.004}
+    t = ob.MonteCarloTechnique(n_paths=1 << 22, n_steps=1, seed=3, control_variate=True)
+    t.price(CALL, STQ, ob.MertonJumpModel(p), RT)
+    s = t.last_stats
+    assert abs(s["control_mean"] - s["control_expected"]) < 4 * s["control_stderr"]
+    # one step: log S_T is N(m, s^2) mixed over N ~ Poisson(900); its variance is
+    # sigma^2 T + lambda T (mu_j^2 + sigma_j^2)
+    term = t._simulate_sde_path(ob.MertonJumpModel(p), 100.0, 0.05, 0.01, 1.0)
+    want_var = 0.1 ** 2 + 900.0 * (0.001 ** 2 + 0.004 ** 2)
+    assert np.log(term).var() == pytest.approx(want_var, rel=5 * math.sqrt(2 / term.size) * 2)
+
+
+def test_fed_jump_buffer_overrun_is_contained(eng):
+    """Counts asking for more jump sizes than the buffer holds: NaN paths, no out-of-bounds read."""
+    n, m = 64, 8
+    dw = np.zeros((n, m))
+    counts = np.ones((n, m), dtype=np.int64)
+    mdl = _engine.make_model("merton", ob.MertonJumpModel().params, 0.05, 0.0)
+    term, _ = eng.fed("merton", mdl, math.log(100.0), 1.0 / m, dw, None, counts,
+                      np.full(100, 0.01), sign=1.0, path_sum_mode=0, want_terminal=True,
+                      want_paths=False)
+    assert np.isnan(term).any() and np.isfinite(term).any()
