@@ -21,12 +21,13 @@ namespace optmc {
 constexpr int LSMC_THREADS = 256;
 
 // ---- path store fill (Philox) ---------------------------------------------
+template <class V>
 struct StoreSink {
     double *store;
     int64_t ld, g, n_local;
     int kind;
     bool anti;
-    RngView tab;
+    V tab;
     __device__ __forceinline__ void operator()(int i, const State &sa, const State &sb) const {
         double *row = store + (size_t)i * ld;
         row[g] = step_spot(kind, sa, tab);                      // path_kernels.py:34
@@ -44,9 +45,33 @@ __global__ void __launch_bounds__(EURO_THREADS) k_lsmc_paths(const EuroArgs A, d
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < A.n_local; g += stride) {
         State sa, sb;
-        StoreSink sink{store, ld, g, A.n_local, KIND, ANTI, tv};
+        StoreSink<RngView> sink{store, ld, g, A.n_local, KIND, ANTI, tv};
         simulate_draw<KIND, ANTI, NIMPL, true, SCHED, BGEN>(A, (uint64_t)(A.draw_offset + g), sa, sb,
                                                             tv, sink);
+    }
+}
+
+// The same fill on lane-replicated tables, one block per SM (european.cuh: k_european_wide).
+// Every kind takes the layout with the exp table: the log models exponentiate each stored spot.
+__host__ __device__ constexpr int paths_wide_threads(int kind, bool sched) {
+    return sched ? 512 : kind_two_factor(kind) ? 768 : 1024;
+}
+template <int KIND>
+constexpr uint32_t paths_wide_smem_bytes() { return WideExpLayout::bytes(kind_two_factor(KIND)); }
+
+template <int KIND, bool ANTI, bool SCHED = false, bool BGEN = false>
+__global__ void __launch_bounds__(paths_wide_threads(KIND, SCHED), 1)
+k_lsmc_paths_wide(const EuroArgs A, double *store, int64_t ld) {
+    extern __shared__ __align__(16) unsigned char wide_smem[];
+    const auto tv = fill_rng_tables<WideExpLayout, kind_two_factor(KIND)>(
+        wide_smem, kind_two_factor(KIND) ? A.c.m11 : A.c.sqrt_dt, A.c.m12, A.c.m21, A.c.m22);
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < A.n_local; g += stride) {
+        State sa, sb;
+        StoreSink<RngViewS> sink{store, ld, g, A.n_local, KIND, ANTI, tv};
+        simulate_draw<KIND, ANTI, 1, true, SCHED, BGEN>(A, (uint64_t)(A.draw_offset + g), sa, sb, tv,
+                                                        sink);
     }
 }
 

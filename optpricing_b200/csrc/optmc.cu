@@ -850,37 +850,62 @@ static int launch_paths_t(optmc_ctx *ctx, EuroArgs &A, double *store, int64_t ld
     return 0;
 }
 
+template <int KIND, bool ANTI, bool SCHED = false, bool BGEN = false>
+static int launch_paths_wide(optmc_ctx *ctx, EuroArgs &A, double *store, int64_t ld, cudaStream_t st) {
+    auto kern = k_lsmc_paths_wide<KIND, ANTI, SCHED, BGEN>;
+    constexpr int threads = paths_wide_threads(KIND, SCHED);
+    const int smem = (int)paths_wide_smem_bytes<KIND>();
+    static bool attr_set[64] = {};                 // per device
+    if (!attr_set[ctx->device & 63]) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set[ctx->device & 63] = true;
+    }
+    const int64_t need = (A.n_local + threads - 1) / threads;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, ctx->sm_count));
+    kern<<<grid, threads, smem, st>>>(A, store, ld);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 template <int KIND>
-static int launch_paths_k(optmc_ctx *ctx, EuroArgs &A, bool anti, double *store, int64_t ld,
-                          cudaStream_t st) {
-    // SABR kinds on the hand-written maths, beta neither 0 nor 1: the step without the switch
-    bool bgen = false;
-    if constexpr (kind_sabr(KIND))
-        bgen = ctx->normals_impl == 1 && A.c.beta_mode != 1 && A.c.beta_mode != 2;
-    if constexpr (kind_jumps(KIND)) {
-        if (use_jump_schedule(A) && ctx->jump_schedule) {
-            if (ctx->normals_impl == 0)
+static int launch_paths_k(optmc_ctx *ctx, EuroArgs &A, bool anti, bool wide, double *store,
+                          int64_t ld, cudaStream_t st) {
+    if (ctx->normals_impl == 0) {
+        if constexpr (kind_jumps(KIND)) {
+            if (use_jump_schedule(A) && ctx->jump_schedule)
                 return anti ? launch_paths_t<KIND, true, 0, true>(ctx, A, store, ld, st)
                             : launch_paths_t<KIND, false, 0, true>(ctx, A, store, ld, st);
-            if constexpr (kind_sabr(KIND)) {
-                if (bgen)
-                    return anti ? launch_paths_t<KIND, true, 1, true, true>(ctx, A, store, ld, st)
-                                : launch_paths_t<KIND, false, 1, true, true>(ctx, A, store, ld, st);
-            }
-            return anti ? launch_paths_t<KIND, true, 1, true>(ctx, A, store, ld, st)
-                        : launch_paths_t<KIND, false, 1, true>(ctx, A, store, ld, st);
         }
-    }
-    if (ctx->normals_impl == 0)
         return anti ? launch_paths_t<KIND, true, 0>(ctx, A, store, ld, st)
                     : launch_paths_t<KIND, false, 0>(ctx, A, store, ld, st);
-    if constexpr (kind_sabr(KIND)) {
-        if (bgen)
-            return anti ? launch_paths_t<KIND, true, 1, false, true>(ctx, A, store, ld, st)
-                        : launch_paths_t<KIND, false, 1, false, true>(ctx, A, store, ld, st);
     }
-    return anti ? launch_paths_t<KIND, true, 1>(ctx, A, store, ld, st)
-                : launch_paths_t<KIND, false, 1>(ctx, A, store, ld, st);
+#define PATHS_GO(SCHED_, BGEN_)                                                                   \
+    do {                                                                                          \
+        if constexpr (KIND != OPTMC_DUPIRE) {                                                     \
+            if (wide)                                                                             \
+                return anti ? launch_paths_wide<KIND, true, SCHED_, BGEN_>(ctx, A, store, ld, st) \
+                            : launch_paths_wide<KIND, false, SCHED_, BGEN_>(ctx, A, store, ld, st);\
+        }                                                                                         \
+        return anti ? launch_paths_t<KIND, true, 1, SCHED_, BGEN_>(ctx, A, store, ld, st)         \
+                    : launch_paths_t<KIND, false, 1, SCHED_, BGEN_>(ctx, A, store, ld, st);       \
+    } while (0)
+    // SABR kinds, beta neither 0 nor 1: the step without the switch
+    bool bgen = false;
+    if constexpr (kind_sabr(KIND)) bgen = A.c.beta_mode != 1 && A.c.beta_mode != 2;
+    if constexpr (kind_jumps(KIND)) {
+        if (use_jump_schedule(A) && ctx->jump_schedule) {
+            if constexpr (kind_sabr(KIND)) {
+                if (bgen) PATHS_GO(true, true);
+            }
+            PATHS_GO(true, false);
+        }
+    }
+    if constexpr (kind_sabr(KIND)) {
+        if (bgen) PATHS_GO(false, true);
+    }
+    PATHS_GO(false, false);
+#undef PATHS_GO
 }
 
 extern "C" int optmc_lsmc_paths_async(optmc_ctx *ctx, const optmc_model *model,
@@ -900,7 +925,8 @@ extern "C" int optmc_lsmc_paths_async(optmc_ctx *ctx, const optmc_model *model,
     if (ld < sim->n_local * (anti ? 2 : 1)) FAIL("ld smaller than the local path count");
     if (sim->n_local == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-#define GO(K) rc = launch_paths_k<K>(ctx, A, anti, store_dev, ld, st)
+    const bool wide = use_wide(ctx, model->kind, sim->n_draws);
+#define GO(K) rc = launch_paths_k<K>(ctx, A, anti, wide, store_dev, ld, st)
     DISPATCH_KIND(model->kind, GO)
 #undef GO
     return rc;
