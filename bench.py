@@ -453,16 +453,20 @@ def secondary(cx, name, steps, with_cpu=True):
         models = (ob.SABRJumpModel(), ob.KouModel())
         techs = [ob.MonteCarloTechnique(n_paths=1 << 24, n_steps=365, seed=11, control_variate=True)
                  for _ in models]
-        # per step: price + delta + vega of both models on common random numbers; the value
-        # counts the simulations actually run (engine counter), each 2^24 paths x 365 steps
+        # per step: price + delta + vega of both models on common random numbers, ONE
+        # price_with_greeks call per model = ONE simulation per model: SABR-jump carries the
+        # spot scenarios (up, base, down) side by side on shared draws (its vega is NaN as in
+        # the reference, greek_mixin.py:156-157); Kou's bumped prices are strike rescalings
+        # and a sigma sweep of the one simulation.  The value counts simulations actually run
+        # (engine counter), each 2^24 paths x 365 steps -- round 1 ran 6 per step.
         label = ("C5 SABR-with-jumps and Kou European call, 2^24 paths x 365 steps, control variate, "
-                 "price + delta + vega on common random numbers")
+                 "price + delta + vega on common random numbers (price_with_greeks)")
 
         def step():
             out = []
             for t, m in zip(techs, models):
-                out += [t.price(call, stock, m, rate).price, t.delta(call, stock, m, rate),
-                        t.vega(call, stock, m, rate)]
+                res = t.price_with_greeks(call, stock, m, rate, greeks=("delta", "vega"))
+                out += [res.price, res.greeks["delta"], res.greeks["vega"]]
             return out
     else:
         raise SystemExit(name)

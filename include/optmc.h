@@ -134,6 +134,19 @@ int optmc_european(optmc_ctx *ctx, const optmc_model *model, const optmc_sim *si
                    double *moments_host, double *terminal_dev, void *stream);
 
 /*
+ * Spot scenarios on common draws for the SABR kinds.  GreekMixin.delta / .gamma
+ * (techniques/base/greek_mixin.py:59-122) re-price 2 / 3 times with the spot bumped, on common
+ * random numbers.  For SABR and SABR-jump the vol path does not depend on the spot, so the
+ * bumped paths are carried side by side through ONE simulation: n_scen (2 or 3) spots
+ * s0 * spot_factors[k] share Philox, the normals, the vol path and the jump draws.  Writes
+ * OPTMC_NMOM doubles per scenario, equal (to rounding) to optmc_european_async called per
+ * scenario with s0 * spot_factors[k] and the same seed.
+ */
+int optmc_european_scen_async(optmc_ctx *ctx, const optmc_model *model, const optmc_sim *sim,
+                              int32_t n_scen, const double *spot_factors, double strike,
+                              int32_t is_call, double *moments_dev, void *stream);
+
+/*
  * Fed-draw kernels: the drop-in for the 7 terminal kernels of mc_kernels.py and
  * the 7 path kernels of path_kernels.py, same inputs in the same C-order
  * layouts, all in device memory:

@@ -80,6 +80,9 @@ SIGNATURES = [
     ("optmc_european_aux_async", c_int, [c_void_p, ctypes.POINTER(OptmcModel),
                                          ctypes.POINTER(OptmcSim), c_i32, _dp, _ip, c_void_p,
                                          c_void_p, c_void_p, c_void_p]),
+    ("optmc_european_scen_async", c_int, [c_void_p, ctypes.POINTER(OptmcModel),
+                                          ctypes.POINTER(OptmcSim), c_i32, _dp, c_double, c_i32,
+                                          c_void_p, c_void_p]),
     ("optmc_sigma_sweep_async", c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i32, _dp, _dp, _dp,
                                         _ip, c_void_p, c_void_p]),
     ("optmc_payoff_sweep_async", c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i32, _dp, _ip,
@@ -358,6 +361,16 @@ class Engine:
                                                   ctypes.byref(sim), k.size, kp, cp,
                                                   c_void_p(moments.data_ptr()), tptr,
                                                   self.stream()), "optmc_european_async")
+
+    def european_scen_async(self, model, sim, spot_factors, strike, is_call, moments):
+        """optmc_european_scen_async: 2 or 3 bumped-spot scenarios of a SABR kind on one set of
+        draws; 6 doubles per scenario into the torch tensor ``moments``."""
+        self.n_simulations += 1
+        f = np.ascontiguousarray(spot_factors, dtype=np.float64)
+        self._check(self.lib.optmc_european_scen_async(
+            self.ctx, ctypes.byref(model), ctypes.byref(sim), f.size, f.ctypes.data_as(_dp),
+            float(strike), 1 if is_call else 0, c_void_p(moments.data_ptr()), self.stream()),
+            "optmc_european_scen_async")
 
     def sigma_sweep(self, aux, n_local, antithetic, a0, sigma, strikes, is_call):
         """optmc_sigma_sweep_async -> device tensor of n_scenarios * 6 moments."""

@@ -148,9 +148,9 @@ __device__ __forceinline__ double2 jumps_slow(uint32_t w, double mu, double p0, 
 // kept sorted in four registers; a path with more jumps (P = 2e-4 at lambda T = 2)
 // recomputes its indices at every step.  The terminal-only SABR-jump kernel uses the
 // schedule group-wise instead (GROUPJ below).  The host selects SCHED while lambda T <= 2.
-template <int KIND, bool ANTI, int NIMPL, bool PER_STEP, bool SCHED, bool BGEN = false, class V,
-          class Sink>
-__device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, State &sa, State &sb,
+template <int KIND, bool ANTI, int NIMPL, bool PER_STEP, bool SCHED, bool BGEN = false, class S,
+          class V, class Sink>
+__device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, S &sa, S &sb,
                                               V tab, Sink &&sink) {
     const Consts &c = A.c;
     constexpr bool TWO = kind_two_factor(KIND);
@@ -486,7 +486,8 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, St
 }
 
 struct NoSink {
-    __device__ __forceinline__ void operator()(int, const State &, const State &) const {}
+    template <class S>
+    __device__ __forceinline__ void operator()(int, const S &, const S &) const {}
 };
 
 // Resident 256-thread blocks per SM the register budget is sized for.  Heston / Bates: three
@@ -613,6 +614,62 @@ __global__ void __launch_bounds__(wide_threads(KIND, SCHED), 1) k_european_wide(
         double *p = A.partials + (size_t)blockIdx.x * NPART;
 #pragma unroll
         for (int k = 0; k < 5; ++k) p[k] = acc[k];
+    }
+}
+
+// Spot scenarios of the SABR kinds on ONE set of draws: NS bumped spots -- the
+// re-pricings GreekMixin.delta / .gamma make on common random numbers (greek_mixin.py:59-122)
+// -- advance side by side; Philox, the Box-Muller pair, the vol path and the jump draws are
+// shared, only the spot recurrence (one logarithm and one exponential per scenario and step) is
+// repeated.  Same draws, same arithmetic per scenario as k_european_wide: the scenario prices
+// equal separate simulations with the bumped spot to rounding.
+// partials: [NS][gridDim.x][NPART], the layout k_finish_sweep adds up.
+// 512 threads = 128 registers (three spot states for path and partner); on the jump schedule,
+// whose jump groups keep eight jump factors more, 384 threads = 168 registers
+__host__ __device__ constexpr int scen_threads(bool sched) { return sched ? 384 : 512; }
+template <int KIND, bool ANTI, int NS, bool SCHED = false, bool BGEN = false>
+__global__ void __launch_bounds__(scen_threads(SCHED), 1) k_european_scen(const EuroArgs A) {
+    static_assert(kind_sabr(KIND), "spot scenarios share the vol path: SABR kinds");
+    extern __shared__ __align__(16) unsigned char wide_smem[];
+    __shared__ double scratch[5 * 32];     // (the tables take 224 of the 227 KB a block can have)
+    const auto tv = fill_rng_tables<WideExpLayout, true>(wide_smem, A.c.m11, A.c.m12, A.c.m21, A.c.m22);
+    __syncthreads();
+    double acc[5 * NS];
+#pragma unroll
+    for (int k = 0; k < 5 * NS; ++k) acc[k] = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < A.n_local; g += stride) {
+        StateT<Scen<NS>> sa, sb;
+        simulate_draw<KIND, ANTI, 1, false, SCHED, BGEN>(A, (uint64_t)(A.draw_offset + g), sa, sb,
+                                                         tv, NoSink{});
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            const double ST = sa.x.a[k];
+            double pay = fmax(A.is_call ? ST - A.strike : A.strike - ST, 0.0);
+            double ctl = ST;
+            if constexpr (ANTI) {
+                const double STb = sb.x.a[k];
+                pay = 0.5 * (pay + fmax(A.is_call ? STb - A.strike : A.strike - STb, 0.0));
+                ctl = 0.5 * (ST + STb);
+            }
+            acc[5 * k] += pay;
+            acc[5 * k + 1] = fma(pay, pay, acc[5 * k + 1]);
+            acc[5 * k + 2] += ctl;
+            acc[5 * k + 3] = fma(ctl, ctl, acc[5 * k + 3]);
+            acc[5 * k + 4] = fma(pay, ctl, acc[5 * k + 4]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        double a5[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) a5[j] = acc[5 * k + j];
+        block_sum<5>(a5, scratch);
+        if (threadIdx.x == 0) {
+            double *p = A.partials + ((size_t)k * gridDim.x + blockIdx.x) * NPART;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) p[j] = a5[j];
+        }
     }
 }
 

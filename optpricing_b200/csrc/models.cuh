@@ -53,6 +53,7 @@ struct Consts {
     int lv_n_s;
     double lv_lo, lv_inv_h, lv_max_u;
     double rq;                // r - q
+    double scen[3];           // spot factors of the scenario kernels (k_european_scen)
 };
 
 __host__ __device__ constexpr bool kind_two_factor(int k) {
@@ -65,12 +66,34 @@ __host__ __device__ constexpr bool kind_sabr(int k) {
     return k == OPTMC_SABR || k == OPTMC_SABR_JUMP;
 }
 
-struct State {
-    double x;  // log S (S for SABR kinds); with DEFER: the stochastic part only
+// N spot scenarios of one path on ONE set of draws (SABR kinds: the vol path does not depend
+// on S, so bumped-spot paths -- the up / base / down re-pricings of GreekMixin.delta and
+// .gamma, greek_mixin.py:59-122 -- share everything but the spot recurrence)
+template <int N>
+struct Scen {
+    double a[N];
+    __device__ __forceinline__ Scen &operator*=(double f) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) a[k] *= f;
+        return *this;
+    }
+    __device__ __forceinline__ Scen &operator+=(double f) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) a[k] += f;
+        return *this;
+    }
+};
+template <class X> struct scen_count { static constexpr int value = 1; };
+template <int N> struct scen_count<Scen<N>> { static constexpr int value = N; };
+
+template <class X>
+struct StateT {
+    X x;       // log S (S for SABR kinds); with DEFER: the stochastic part only
     double v;  // variance (Heston/Bates, stored before the floor) or vol (SABR)
     double w;  // DEFER only: running sum of v_pos (Heston/Bates); sum of log-jumps (Merton/Kou)
     double j;  // Bates terminal kernels: the path's summed log-jumps (written once, after the loop)
 };
+using State = StateT<double>;
 
 // DEFER (terminal-value kernels of the log models): the deterministic drift is
 // added once after the last step instead of every step,
@@ -129,8 +152,8 @@ __device__ __forceinline__ void step_heston_parts(State &s, double L, double t1,
     s.v = fma(rq, t2, fma(vp, c.one_minus_kappa_dt, c.kappa_theta_dt));
 }
 
-template <int KIND, bool DEFER>
-__device__ __forceinline__ void finish_deferred(State &s, const Consts &c) {
+template <int KIND, bool DEFER, class S>
+__device__ __forceinline__ void finish_deferred(S &s, const Consts &c) {
     if constexpr (DEFER) {
         if constexpr (KIND == OPTMC_HESTON || KIND == OPTMC_BATES)
             s.x = c.x0 + (c.n_rqc_dt + fma(s.w, c.neg_half_dt, s.x));
@@ -189,28 +212,43 @@ __device__ __forceinline__ double floor_neg650(double a) {
 // LOGV: 0 = literal form; 1 = log-vol form, beta_mode read at run time; 2 = log-vol form
 // for a beta that is neither 0 nor 1, chosen by the host -- the step loop then carries one
 // code path instead of three and no switch.
+// the spot recurrence of one SABR step, given the (log-)vol BEFORE its own update
 template <int LOGV, class V>
-__device__ __forceinline__ void step_sabr(State &s, double z1, double cz, const Consts &c, V t) {
+__device__ __forceinline__ void sabr_spot_update(double &x, double v, double z1, const Consts &c,
+                                                 V t) {
     if constexpr (LOGV != 0) {
-        const double s_pos = floor_1e8(s.x);
+        const double s_pos = floor_1e8(x);
         double coef;
         if constexpr (LOGV == 2) {
-            coef = fast_exp(floor_neg650(fma(c.beta, fast_log(s_pos, t), s.v)), t);
+            coef = fast_exp(floor_neg650(fma(c.beta, fast_log(s_pos, t), v)), t);
         } else {
             switch (c.beta_mode) {
-                case 1: coef = fast_exp(floor_neg650(s.v), t) * s_pos; break;
-                case 2: coef = fast_exp(floor_neg650(s.v), t); break;
-                default: coef = fast_exp(floor_neg650(fma(c.beta, fast_log(s_pos, t), s.v)), t);
+                case 1: coef = fast_exp(floor_neg650(v), t) * s_pos; break;
+                case 2: coef = fast_exp(floor_neg650(v), t); break;
+                default: coef = fast_exp(floor_neg650(fma(c.beta, fast_log(s_pos, t), v)), t);
             }
         }
-        s.x += fma(coef, z1, c.rqc_dt * s_pos);
-        s.v += fma(c.alpha, cz, c.neg_half_alpha2_dt);
+        x += fma(coef, z1, c.rqc_dt * s_pos);
     } else {
-        double s_pos = fmax(s.x, 1e-8);
-        double v_pos = relu64(s.v);
-        s.x += fma(v_pos * sabr_pow(s_pos, c, t), z1, c.rqc_dt * s_pos);
-        s.v = s.v * fast_exp(fma(c.alpha, cz, c.neg_half_alpha2_dt), t);
+        double s_pos = fmax(x, 1e-8);
+        double v_pos = relu64(v);
+        x += fma(v_pos * sabr_pow(s_pos, c, t), z1, c.rqc_dt * s_pos);
     }
+}
+
+template <int LOGV, class S, class V>
+__device__ __forceinline__ void step_sabr(S &s, double z1, double cz, const Consts &c, V t) {
+    constexpr int NS = scen_count<decltype(s.x)>::value;
+    if constexpr (NS == 1) {
+        sabr_spot_update<LOGV>(s.x, s.v, z1, c, t);
+    } else {
+#pragma unroll
+        for (int k = 0; k < NS; ++k) sabr_spot_update<LOGV>(s.x.a[k], s.v, z1, c, t);
+    }
+    if constexpr (LOGV != 0)
+        s.v += fma(c.alpha, cz, c.neg_half_alpha2_dt);
+    else
+        s.v = s.v * fast_exp(fma(c.alpha, cz, c.neg_half_alpha2_dt), t);
 }
 
 // Fed mode: the kernel's own correlation step applied to the given increments.
@@ -221,8 +259,8 @@ __device__ __forceinline__ void mix_fed(int kind, double dw1, double dw2, const 
     if (kind == OPTMC_HESTON || kind == OPTMC_BATES) cz *= c.xi;
 }
 
-template <int KIND, bool DEFER = false, int LOGV = 0, class V = RngView>
-__device__ __forceinline__ void step_diffusion(State &s, double z1, double cz, const Consts &c,
+template <int KIND, bool DEFER = false, int LOGV = 0, class S = State, class V = RngView>
+__device__ __forceinline__ void step_diffusion(S &s, double z1, double cz, const Consts &c,
                                                V t, int i) {
     if constexpr (KIND == OPTMC_DUPIRE)
         step_dupire(s, z1, i, c);
@@ -236,17 +274,24 @@ __device__ __forceinline__ void step_diffusion(State &s, double z1, double cz, c
 
 // Initial state.  With DEFER the log-spot accumulator starts at 0 and log S_0 is
 // added by finish_deferred; jumps (additive in log space) accumulate in x too.
-template <int KIND, bool DEFER, int LOGV = 0>
-__device__ __forceinline__ void init_state(State &s, const Consts &c) {
-    s.x = (DEFER && !kind_sabr(KIND)) ? 0.0 : c.x0;
+template <int KIND, bool DEFER, int LOGV = 0, class S = State>
+__device__ __forceinline__ void init_state(S &s, const Consts &c) {
+    constexpr int NS = scen_count<decltype(s.x)>::value;
+    if constexpr (NS == 1) {
+        s.x = (DEFER && !kind_sabr(KIND)) ? 0.0 : c.x0;
+    } else {
+        static_assert(kind_sabr(KIND), "spot scenarios: SABR kinds");
+#pragma unroll
+        for (int k = 0; k < NS; ++k) s.x.a[k] = c.x0 * c.scen[k];
+    }
     s.v = (LOGV != 0 && kind_sabr(KIND)) ? c.log_v0 : c.v0;
     s.w = 0.0;
 }
 
 // Apply one jump of size J (Merton/Bates/Kou: additive in log space,
 // mc_kernels.py:115,174,323; SABR-jump: multiplicative on S, :274).
-template <int KIND, bool DEFER = false>
-__device__ __forceinline__ void apply_jump(State &s, double J) {
+template <int KIND, bool DEFER = false, class S = State>
+__device__ __forceinline__ void apply_jump(S &s, double J) {
     if constexpr (KIND == OPTMC_SABR_JUMP)
         s.x *= exp(J);     // rare path: CUDA math library
     else if constexpr (DEFER && (KIND == OPTMC_MERTON || KIND == OPTMC_KOU))

@@ -580,6 +580,87 @@ extern "C" int optmc_european_aux_async(optmc_ctx *ctx, const optmc_model *model
                         is_call, moments_dev, st);
 }
 
+// ---------------------------------------------------------------------------
+// spot scenarios on common draws (SABR kinds)
+// ---------------------------------------------------------------------------
+template <int KIND, bool ANTI, int NS, bool SCHED, bool BGEN>
+static int launch_scen_t(optmc_ctx *ctx, EuroArgs &A, cudaStream_t st, int *grid_out) {
+    auto kern = k_european_scen<KIND, ANTI, NS, SCHED, BGEN>;
+    const int smem = (int)WideExpLayout::bytes(true);
+    static bool attr_set[64] = {};
+    if (!attr_set[ctx->device & 63]) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set[ctx->device & 63] = true;
+    }
+    constexpr int threads = scen_threads(SCHED);
+    const int64_t need = (A.n_local + threads - 1) / threads;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, ctx->sm_count));
+    kern<<<grid, threads, smem, st>>>(A);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    *grid_out = grid;
+    return 0;
+}
+
+template <int KIND, int NS>
+static int launch_scen_k(optmc_ctx *ctx, EuroArgs &A, bool anti, cudaStream_t st, int *grid) {
+    const bool bgen = A.c.beta_mode != 1 && A.c.beta_mode != 2;
+    bool sched = false;
+    if constexpr (KIND == OPTMC_SABR_JUMP) sched = ctx->jump_schedule && use_jump_schedule(A);
+#define SCEN_GO(SCHED_, BGEN_)                                                            \
+    return anti ? launch_scen_t<KIND, true, NS, SCHED_, BGEN_>(ctx, A, st, grid)         \
+                : launch_scen_t<KIND, false, NS, SCHED_, BGEN_>(ctx, A, st, grid)
+    if constexpr (KIND == OPTMC_SABR_JUMP) {
+        if (sched && bgen) SCEN_GO(true, true);
+        if (sched) SCEN_GO(true, false);
+    }
+    if (bgen) SCEN_GO(false, true);
+    SCEN_GO(false, false);
+#undef SCEN_GO
+}
+
+extern "C" int optmc_european_scen_async(optmc_ctx *ctx, const optmc_model *model,
+                                         const optmc_sim *sim, int32_t n_scen,
+                                         const double *spot_factors, double strike,
+                                         int32_t is_call, double *moments_dev, void *stream) {
+    if (!ctx) return -2;
+    CK(cudaSetDevice(ctx->device));
+    if (!model || !kind_sabr(model->kind))
+        FAIL("spot scenarios on common draws exist for the SABR kinds (the log-Euler models "
+             "get bumped prices by strike rescaling: optmc_payoff_sweep_async)");
+    if (n_scen < 2 || n_scen > 3 || !spot_factors || !moments_dev) FAIL("bad scenario arguments");
+    if (sim && sim->precision != OPTMC_FP64) FAIL("spot scenarios need the fp64 mode");
+    if (ctx->normals_impl != 1) FAIL("spot scenarios need normals_impl = 1");
+    EuroArgs A;
+    int rc = fill_euro_args(ctx, model, sim, &A);
+    if (rc) return rc;
+    for (int k = 0; k < n_scen; ++k) {
+        if (!(spot_factors[k] > 0.0)) FAIL("spot factors must be positive");
+        A.c.scen[k] = spot_factors[k];
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    A.strike = strike;
+    A.is_call = is_call ? 1 : 0;
+    A.partials = reinterpret_cast<double *>(ctx->scratch);
+    int grid = 1;
+    const bool anti = sim->antithetic != 0;
+    if (sim->n_local > 0) {
+        if (model->kind == OPTMC_SABR)
+            rc = n_scen == 2 ? launch_scen_k<OPTMC_SABR, 2>(ctx, A, anti, st, &grid)
+                             : launch_scen_k<OPTMC_SABR, 3>(ctx, A, anti, st, &grid);
+        else
+            rc = n_scen == 2 ? launch_scen_k<OPTMC_SABR_JUMP, 2>(ctx, A, anti, st, &grid)
+                             : launch_scen_k<OPTMC_SABR_JUMP, 3>(ctx, A, anti, st, &grid);
+        if (rc) return rc;
+    } else {
+        CK(cudaMemsetAsync(A.partials, 0, sizeof(double) * NPART * n_scen, st));
+    }
+    k_finish_sweep<<<n_scen, 256, 0, st>>>(A.partials, grid, (double)sim->n_local, moments_dev);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int optmc_european(optmc_ctx *ctx, const optmc_model *model, const optmc_sim *sim,
                               int32_t n_contracts, const double *strikes, const int32_t *is_call,
                               double *moments_host, double *terminal_dev, void *stream) {

@@ -400,7 +400,8 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
                 and not getattr(model, "has_exact_sampler", False)
                 and not getattr(model, "is_pure_levy", False))
 
-    def _sweep_async(self, model, S0, r, q, T, strikes, calls, out_dev, seed=None, **kwargs):
+    def _sweep_async(self, model, S0, r, q, T, strikes, calls, out_dev, seed=None, _aux=None,
+                     **kwargs):
         """
         Enqueue ONE simulation to maturity T and the payoff moments of every
         (strike, type) into ``out_dev`` (device, 6 doubles per contract): the
@@ -427,18 +428,19 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
             ks, cs = strikes[lo:lo + 64], calls[lo:lo + 64]
             dst = out_dev[lo * _engine.NMOM:(lo + ks.size) * _engine.NMOM]
             if lo == 0:
-                eng.european_async(mdl, sim, ks, cs, dst, terminal=term)
+                eng.european_async(mdl, sim, ks, cs, dst, terminal=term, aux=_aux)
             else:                                   # further chunks reuse the stored terminals
                 eng.payoff_sweep(term, cnt, self.antithetic, ks, cs, out=dst)
         return kind, seed, keep
 
-    def _sweep(self, model, S0, r, q, T, strikes, calls, seed=None, **kwargs):
+    def _sweep(self, model, S0, r, q, T, strikes, calls, seed=None, _aux=None, **kwargs):
         """One simulation, all contracts of one maturity -> (moments[n, 6], kind, seed)."""
         eng = _engine.get_engine()
         n = len(strikes)
         dev = eng.buffer("moments_many", n * _engine.NMOM)
         kind, seed, _keep = self._sweep_async(model, S0, r, q, T, strikes, calls,
-                                              dev[: n * _engine.NMOM], seed=seed, **kwargs)
+                                              dev[: n * _engine.NMOM], seed=seed, _aux=_aux,
+                                              **kwargs)
         _, _, all_reduce = self._group()
         if all_reduce is not None:
             all_reduce(dev[: n * _engine.NMOM])
@@ -552,8 +554,49 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
             out.append(f * st.get("cv_price", st["price"]))
         return out
 
+    def _scenario_greeks_ok(self, model) -> bool:
+        """SABR kinds: the vol path does not depend on the spot, so bumped-spot paths ride
+        through ONE simulation side by side (csrc/european.cuh: k_european_scen)."""
+        return (self._philox_sde(model) and model_kind(model) in ("sabr", "sabr_jump")
+                and self.precision == "fp64")
+
+    def _scenario_prices(self, option, stock, model, rate, spot_factors, **kw):
+        """Prices under S0 -> f S0 for 2 or 3 factors on common random numbers from one
+        simulation of a SABR kind: what GreekMixin's re-pricings compute (greek_mixin.py:59-122)."""
+        eng = _engine.get_engine()
+        S0, K, T = stock.spot, option.strike, option.maturity
+        r, q = rate.get_rate(T), stock.dividend
+        kind = model_kind(model)
+        num_draws = self.n_paths // 2 if self.antithetic else self.n_paths
+        with crn(self.rng), self._steps_for(T):           # greeks do not advance the stream
+            seed = int(self.rng.integers(0, 2**63 - 1, dtype=np.int64))
+            mdl = _engine.make_model(kind, model.params, r, q, v0=kw.get("v0"))
+            corr = (_engine.CORR_REFERENCE_EUROPEAN if self.correlation == "reference"
+                    else _engine.CORR_INDEPENDENT_DRAWS)
+            rank, world, all_reduce = self._group()
+            off, cnt = shard_draws(num_draws, rank, world)
+            sim = eng.make_sim(float(S0), T, num_draws, self.n_steps, self.antithetic, seed, corr,
+                               off, cnt)
+            n = len(spot_factors)
+            dev = eng.buffer("moments_scen", 3 * _engine.NMOM)
+            eng.european_scen_async(mdl, sim, spot_factors, K, _is_call(option), dev)
+            if all_reduce is not None:
+                all_reduce(dev[: n * _engine.NMOM])
+            mom = dev[: n * _engine.NMOM].cpu().numpy().reshape(n, _engine.NMOM)
+            out = []
+            for f, row in zip(spot_factors, mom):
+                c_mean = control_mean(kind, model.params, S0 * f, r, q, T, self.n_steps)
+                st = summarize(row, r, T, c_mean)
+                use_cv = self.control_variate and "cv_price" in st and math.isfinite(c_mean)
+                out.append(float(st["cv_price"] if use_cv else st["price"]))
+        return out
+
     @_engine.serialized
     def delta(self, option, stock, model, rate, h_frac: float = 1e-3, **kwargs: Any) -> float:
+        if self._scenario_greeks_ok(model):
+            up, dn = self._scenario_prices(option, stock, model, rate, (1 + h_frac, 1 - h_frac),
+                                           **kwargs)
+            return (up - dn) / (2 * stock.spot * h_frac)
         if not self._scaling_greeks_ok(model):
             return super().delta(option, stock, model, rate, h_frac, **kwargs)
         up, dn = self._bumped_prices(option, stock, model, rate, (1 + h_frac, 1 - h_frac), **kwargs)
@@ -561,6 +604,11 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
 
     @_engine.serialized
     def gamma(self, option, stock, model, rate, h_frac: float = 1e-3, **kw: Any) -> float:
+        if self._scenario_greeks_ok(model):
+            up, mid, dn = self._scenario_prices(option, stock, model, rate,
+                                                (1 + h_frac, 1.0, 1 - h_frac), **kw)
+            h = stock.spot * h_frac
+            return (up - 2 * mid + dn) / (h * h)
         if not self._scaling_greeks_ok(model):
             return super().gamma(option, stock, model, rate, h_frac, **kw)
         up, mid, dn = self._bumped_prices(option, stock, model, rate,
@@ -574,6 +622,129 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
             return super().rho(option, stock, model, rate, h, **kw)
         up, dn = self._bumped_prices(option, stock, model, rate, (), (h, -h), **kw)
         return (up - dn) / (2 * h)
+
+    @_engine.serialized
+    def price_with_greeks(self, option, stock, model, rate, greeks=("delta", "gamma", "vega"),
+                          h_frac: float = 1e-3, h_vega: float = 1e-4, h_rho: float = 1e-4,
+                          **kw: Any) -> PricingResult:
+        """
+        Price and greeks in ONE call -> ``PricingResult(price, greeks={...})`` (the ``greeks``
+        field the reference's dataclass carries, base/pricing_result.py:10-27, and never fills).
+        All numbers are on common random numbers -- the estimators of GreekMixin
+        (greek_mixin.py:29-265) -- from as few simulations as the model allows:
+
+        * log-Euler kinds (BSM, Heston, Merton, Bates, Kou): ONE simulation; price, delta, gamma
+          and rho are strike rescalings of its terminal values, vega (one-factor kinds) a sigma
+          sweep over the (W, J) stored by the same launch;
+        * SABR kinds: ONE simulation carrying the spot scenarios (up, base, down) side by side
+          for price, delta and gamma; vega is NaN as in the reference (no ``sigma``); rho re-prices;
+        * anything else (theta, numpy mode, fp32, single-step models): the mixin's re-pricings.
+        The generator advances once, as for one ``price`` call.
+        """
+        greeks = tuple(greeks)
+        unknown = set(greeks) - {"delta", "gamma", "vega", "rho", "theta"}
+        if unknown:
+            raise ValueError(f"unknown greeks {sorted(unknown)}")
+        S0, K, T = stock.spot, option.strike, option.maturity
+        r, q = rate.get_rate(T), stock.dividend
+        call = _is_call(option)
+        out: dict[str, float] = {}
+        state0 = self.rng.bit_generator.state
+
+        def via_mixin(names):
+            for g in names:
+                self.rng.bit_generator.state = state0
+                fn = getattr(self, g)
+                args = {"delta": (h_frac,), "gamma": (h_frac,), "vega": (h_vega,),
+                        "rho": (h_rho,), "theta": ()}[g]
+                out[g] = float(fn(option, stock, model, rate, *args, **kw))
+
+        if self._scenario_greeks_ok(model):
+            self.rng.bit_generator.state = state0
+            up, mid, dn = self._scenario_prices(option, stock, model, rate,
+                                                (1 + h_frac, 1.0, 1 - h_frac), **kw)
+            h = S0 * h_frac
+            price = mid
+            if "delta" in greeks:
+                out["delta"] = (up - dn) / (2 * h)
+            if "gamma" in greeks:
+                out["gamma"] = (up - 2 * mid + dn) / (h * h)
+            if "vega" in greeks and "sigma" not in model.params:
+                out["vega"] = float("nan")                    # greek_mixin.py:156-157
+            via_mixin([g for g in greeks if g not in out])
+        elif self._scaling_greeks_ok(model):
+            kind = model_kind(model)
+            scen = [(1.0, 0.0), (1 + h_frac, 0.0), (1 - h_frac, 0.0), (1.0, h_rho), (1.0, -h_rho)]
+            strikes = [K / (f * math.exp(hh * T)) for f, hh in scen]
+            eng = _engine.get_engine()
+            num_draws = self.n_paths // 2 if self.antithetic else self.n_paths
+            rank, world, all_reduce = self._group()
+            _, cnt = shard_draws(num_draws, rank, world)
+            want_vega = "vega" in greeks and "sigma" in model.params
+            one_sim_vega = want_vega and kind in self._ONE_FACTOR_KINDS
+            aux = eng.buffer("aux_wj", 3 * cnt) if one_sim_vega else None
+            self.rng.bit_generator.state = state0
+            with crn(self.rng), self._steps_for(T) as steps:
+                mom, _, seed = self._sweep(model, S0, r, q, T, strikes, [1 if call else 0] * 5,
+                                           _aux=aux, **kw)
+                c_mean = control_mean(kind, model.params, S0, r, q, T, steps)
+                vals = []
+                for (f, hh), m in zip(scen, mom):
+                    st = summarize(m, r, T, c_mean)
+                    use_cv = self.control_variate and "cv_price" in st and math.isfinite(c_mean)
+                    vals.append(f * float(st["cv_price"] if use_cv else st["price"]))
+                    if (f, hh) == (1.0, 0.0):
+                        st["seed"] = seed
+                        self.last_stats = st
+                price, up, dn, r_up, r_dn = vals
+                h = S0 * h_frac
+                if "delta" in greeks:
+                    out["delta"] = (up - dn) / (2 * h)
+                if "gamma" in greeks:
+                    out["gamma"] = (up - 2 * price + dn) / (h * h)
+                if "rho" in greeks:
+                    out["rho"] = (r_up - r_dn) / (2 * h_rho)
+                if one_sim_vega:
+                    out["vega"] = self._vega_from_aux(eng, aux, cnt, kind, model, S0, K, T, r, q,
+                                                      call, h_vega, steps, all_reduce)
+            if "vega" in greeks and "sigma" not in model.params:
+                out["vega"] = float("nan")
+            via_mixin([g for g in greeks if g not in out])
+        else:
+            self.rng.bit_generator.state = state0
+            with crn(self.rng):
+                price = self.price(option, stock, model, rate, **kw).price
+            via_mixin(list(greeks))
+        # advance the stream once, as one price() call does
+        self.rng.bit_generator.state = state0
+        self.rng.integers(0, 2**63 - 1, dtype=np.int64)
+        return PricingResult(price=float(price), greeks={g: out[g] for g in greeks})
+
+    def _vega_from_aux(self, eng, aux, cnt, kind, model, S0, K, T, r, q, call, h, steps,
+                       all_reduce):
+        """Central difference in sigma from the (W, J) one simulation stored (see ``vega``)."""
+        p = model.params
+        dt = T / steps
+        comp = 0.0
+        if kind == "merton":
+            comp = p["lambda"] * (math.exp(p["mu_j"] + 0.5 * p["sigma_j"] ** 2) - 1)
+        elif kind == "kou":
+            comp = p["lambda"] * ((p["p_up"] * p["eta1"] / (p["eta1"] - 1))
+                                  + ((1 - p["p_up"]) * p["eta2"] / (p["eta2"] + 1)) - 1)
+        sigmas = [p["sigma"] + h, p["sigma"] - h]
+        a0 = [math.log(S0) + steps * ((r - q - 0.5 * s * s - comp) * dt) for s in sigmas]
+        dev = eng.sigma_sweep(aux, cnt, self.antithetic, a0, sigmas, [float(K)] * 2,
+                              [1 if call else 0] * 2)
+        if all_reduce is not None:
+            all_reduce(dev[: 2 * _engine.NMOM])
+        mom = dev[: 2 * _engine.NMOM].cpu().numpy().reshape(2, _engine.NMOM)
+        c_mean = control_mean(kind, p, S0, r, q, T, steps)
+        prices = []
+        for row in mom:
+            st = summarize(row, r, T, c_mean)
+            use_cv = self.control_variate and "cv_price" in st and math.isfinite(c_mean)
+            prices.append(st["cv_price"] if use_cv else st["price"])
+        return float((prices[0] - prices[1]) / (2 * h))
 
     # ------------------------------------------- single-step models (SURVEY 8 f3)
     def _device_single_step(self, model) -> bool:

@@ -654,10 +654,62 @@ def test_fused_greeks_with_control_variate(kind):
     assert a.rho(CALL, STQ, model, RT) == pytest.approx(GreekMixin.rho(b, CALL, STQ, model, RT), rel=1e-7)
 
 
-def test_sabr_greeks_fall_back_to_repricing():
-    t = ob.MonteCarloTechnique(n_paths=1 << 18, n_steps=24, seed=8)
-    d = t.delta(CALL, STQ, ob.SABRModel(), RT)
-    assert 0.4 < d < 0.8
+@pytest.mark.parametrize("cv", (False, True))
+@pytest.mark.parametrize("anti", (True, False))
+@pytest.mark.parametrize("kind", ("sabr", "sabr_jump"))
+def test_sabr_spot_scenarios_equal_bump_and_reprice(kind, anti, cv, jump_schedule):
+    """SABR kinds: bumped-spot prices carried side by side through ONE simulation
+    (k_european_scen) equal GreekMixin's re-pricings on common random numbers."""
+    import dataclasses
+    from optpricing_b200.techniques.base import GreekMixin
+    if kind == "sabr" and jump_schedule == 0:
+        pytest.skip("no jumps")
+    model = MODELS[kind]()
+    mk = lambda: ob.MonteCarloTechnique(n_paths=200_001, n_steps=37, seed=21, antithetic=anti,  # noqa: E731
+                                        control_variate=cv)
+    a, b = mk(), mk()
+    fs = (1.001, 1.0, 0.999)
+    launches0 = _engine.get_engine().launch_count()
+    got = a._scenario_prices(PUT, STQ, model, RT, fs)
+    assert _engine.get_engine().launch_count() - launches0 == 2        # one simulation + finish
+    want = GreekMixin._reprice(b, [(PUT, dataclasses.replace(STQ, spot=STQ.spot * f), model, RT)
+                                   for f in fs])
+    np.testing.assert_allclose(got, want, rtol=1e-9)
+    assert a.delta(CALL, STQ, model, RT) == pytest.approx(GreekMixin.delta(b, CALL, STQ, model, RT), rel=1e-6)
+    assert a.gamma(CALL, STQ, model, RT) == pytest.approx(GreekMixin.gamma(b, CALL, STQ, model, RT),
+                                                          rel=1e-4, abs=1e-7)
+    assert np.isnan(a.vega(CALL, STQ, model, RT))                       # greek_mixin.py:156-157
+    assert a.price(CALL, STQ, model, RT).price == b.price(CALL, STQ, model, RT).price
+
+
+@pytest.mark.parametrize("cv", (False, True))
+@pytest.mark.parametrize("kind", ("bsm", "heston", "kou", "bates", "sabr_jump"))
+def test_price_with_greeks_is_one_simulation_and_equals_the_mixin(kind, cv):
+    from optpricing_b200.techniques.base import GreekMixin
+    model = MODELS[kind]()
+    mk = lambda: ob.MonteCarloTechnique(n_paths=1 << 18, n_steps=24, seed=5, control_variate=cv)  # noqa: E731
+    a, b = mk(), mk()
+    eng = _engine.get_engine()
+    sims0 = eng.n_simulations
+    res = a.price_with_greeks(CALL, STQ, model, RT, greeks=("delta", "gamma", "vega", "rho")
+                              if kind != "sabr_jump" else ("delta", "gamma", "vega"))
+    assert eng.n_simulations - sims0 == 1
+    assert isinstance(res, ob.PricingResult)
+    # the mixin's estimators on the same stream position
+    want_delta = GreekMixin.delta(b, CALL, STQ, model, RT)
+    want_gamma = GreekMixin.gamma(b, CALL, STQ, model, RT)
+    assert res.greeks["delta"] == pytest.approx(want_delta, rel=1e-6)
+    assert res.greeks["gamma"] == pytest.approx(want_gamma, rel=1e-4, abs=1e-7)
+    if kind != "sabr_jump":
+        assert res.greeks["rho"] == pytest.approx(GreekMixin.rho(b, CALL, STQ, model, RT), rel=1e-6)
+    if "sigma" in model.params:
+        assert res.greeks["vega"] == pytest.approx(GreekMixin.vega(b, CALL, STQ, model, RT), rel=1e-6)
+    else:
+        assert np.isnan(res.greeks["vega"])
+    # same seed as one price() (the sweep adds the payoffs in another order: last-bit differences)
+    assert res.price == pytest.approx(b.price(CALL, STQ, model, RT).price, rel=1e-12)
+    # both generators advanced once
+    assert a.rng.bit_generator.state == b.rng.bit_generator.state
 
 
 # ------------------------------------------------------------------ BASELINE.json configs at full size
