@@ -593,8 +593,13 @@ using wide_layout_t = std::conditional_t<kind_sabr(KIND), WideExpLayout, WideLay
 template <int KIND>
 constexpr uint32_t wide_smem_bytes() { return wide_layout_t<KIND>::bytes(kind_two_factor(KIND)); }
 
-template <int KIND, bool ANTI, bool SCHED = false, bool BGEN = false>
-__global__ void __launch_bounds__(wide_threads(KIND, SCHED), 1) k_european_wide(const EuroArgs A) {
+// THREADS: the launch bound.  Heston / Bates also exist with 1024 threads (64 registers, ~2 %
+// slower per draw): one draw per thread per "row" of sm_count * THREADS draws, so a shard of
+// 2^20 draws -- 2^24 paths over 8 GPUs -- is 9.2 rows of 768 threads (a tenth row runs mostly
+// idle) but 6.9 rows of 1024; the host takes the cheaper one (optmc.cu: launch_euro_wide).
+template <int KIND, bool ANTI, bool SCHED = false, bool BGEN = false,
+          int THREADS = wide_threads(KIND, SCHED)>
+__global__ void __launch_bounds__(THREADS, 1) k_european_wide(const EuroArgs A) {
     static_assert(KIND != OPTMC_DUPIRE, "Dupire keeps the compact kernel");
     extern __shared__ __align__(16) unsigned char wide_smem[];
     __shared__ double scratch[5 * 32];

@@ -27,6 +27,7 @@ struct optmc_ctx {
     int euro_blocks_per_sm = 0; // 0: occupancy API decides
     int euro_threads = EURO_THREADS;
     int euro_wide = 1;          // 1: lane-replicated tables, one block per SM (k_european_wide)
+    int euro_threads_auto = 1;  // 1: Heston / Bates take the 1024-thread variant where it idles less
     int lsmc_mode = 1;          // 1: one persistent launch for all dates, 0: one launch per date
     int jump_schedule = 1;      // 1: pre-drawn jump schedule where it applies, 0: Poisson word per step
     int fed_stream = 1;         // 1: k_fed_stream for the models without jumps, 0: tiled k_fed for all
@@ -186,6 +187,9 @@ extern "C" int optmc_set_int(optmc_ctx *ctx, const char *key, int64_t value) {
     } else if (!strcmp(key, "euro_threads")) {
         if (value != 64 && value != 128 && value != 256) FAIL("euro_threads must be 64, 128 or 256");
         ctx->euro_threads = (int)value;
+    } else if (!strcmp(key, "euro_threads_auto")) {
+        if (value != 0 && value != 1) FAIL("euro_threads_auto must be 0 or 1");
+        ctx->euro_threads_auto = (int)value;
     } else if (!strcmp(key, "euro_wide")) {
         if (value != 0 && value != 1) FAIL("euro_wide must be 0 or 1");
         ctx->euro_wide = (int)value;
@@ -368,23 +372,35 @@ static int launch_euro_t(optmc_ctx *ctx, EuroArgs &A, cudaStream_t st, int *grid
 }
 
 // One block per SM on the lane-replicated tables (european.cuh: k_european_wide).
-template <int KIND, bool ANTI, bool SCHED = false, bool BGEN = false>
-static int launch_euro_wide(optmc_ctx *ctx, EuroArgs &A, cudaStream_t st, int *grid_out) {
-    auto kern = k_european_wide<KIND, ANTI, SCHED, BGEN>;
-    constexpr int threads = wide_threads(KIND, SCHED);
+template <int KIND, bool ANTI, bool SCHED, bool BGEN, int THREADS>
+static int launch_euro_wide_t(optmc_ctx *ctx, EuroArgs &A, cudaStream_t st, int *grid_out) {
+    auto kern = k_european_wide<KIND, ANTI, SCHED, BGEN, THREADS>;
     const int smem = (int)wide_smem_bytes<KIND>();
     static bool attr_set[64] = {};                 // per device
     if (!attr_set[ctx->device & 63]) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set[ctx->device & 63] = true;
     }
-    const int64_t need = (A.n_local + threads - 1) / threads;
+    const int64_t need = (A.n_local + THREADS - 1) / THREADS;
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(need, ctx->sm_count));
-    kern<<<grid, threads, smem, st>>>(A);
+    kern<<<grid, THREADS, smem, st>>>(A);
     ctx->launches++;
     CK(cudaGetLastError());
     *grid_out = grid;
     return 0;
+}
+
+template <int KIND, bool ANTI, bool SCHED = false, bool BGEN = false>
+static int launch_euro_wide(optmc_ctx *ctx, EuroArgs &A, cudaStream_t st, int *grid_out) {
+    constexpr int T = wide_threads(KIND, SCHED);
+    if constexpr (KIND == OPTMC_HESTON || KIND == OPTMC_BATES) {
+        // rows of sm_count * threads draws, one draw per thread per row; the last row costs a
+        // whole row's time however few draws it holds.  1024 threads run ~2 % slower per draw.
+        auto rows = [&](int t) { return (A.n_local + (int64_t)ctx->sm_count * t - 1) / ((int64_t)ctx->sm_count * t); };
+        if (ctx->euro_threads_auto && rows(1024) * 1024 * 102 < rows(T) * T * 100)
+            return launch_euro_wide_t<KIND, ANTI, SCHED, BGEN, 1024>(ctx, A, st, grid_out);
+    }
+    return launch_euro_wide_t<KIND, ANTI, SCHED, BGEN, T>(ctx, A, st, grid_out);
 }
 
 // Which kernel prices a job: a property of the whole job (n_draws), not of this rank's shard,
