@@ -312,8 +312,11 @@ def c2_device(cx, args, w, scaling, steps, sampler=None):
         if kev is not None:
             kev.record()
         if cx.dist:
-            cx.dist.all_reduce(moments)
+            all_reduce(moments)
 
+    # what MonteCarloTechnique.price does after the kernel: the engine's own all-reduce kernel
+    # over NVLink peer memory (csrc/lsmc.cuh: k_peer_allreduce) on an NCCL group
+    all_reduce = eng.group_all_reduce() if cx.dist else None
     for i in range(max(args.warmup, 3)):
         step(1000 + i)
     cx.barrier()
@@ -588,7 +591,7 @@ def parity_multi(cx, w, dist_moments_seed=2000):
     sim = eng.make_sim(w["S0"], w["T"], n_draws, w["n_steps"], True, 77, _engine.CORR_REFERENCE_EUROPEAN,
                        off, cnt)
     eng.european_async(mdl, sim, [w["K"]], [1], mom)
-    cx.dist.all_reduce(mom)
+    eng.group_all_reduce()(mom)
     got = mom.cpu().numpy()
     if cx.rank == 0:
         sim1 = eng.make_sim(w["S0"], w["T"], n_draws, w["n_steps"], True, 77,
@@ -657,7 +660,9 @@ def run_ours(args, w):
         "ms_per_step": main["ms_per_step"], "higher_is_better": True,
         "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": w["name"], "paths_per_step": main["n_job"], "n_steps": w["n_steps"],
-                   "partition": f"draws sharded over {cx.world} rank(s), one all-reduce of 6 doubles",
+                   "partition": f"draws sharded over {cx.world} rank(s), one all-reduce of 6 doubles"
+                                + (" by k_peer_allreduce over NVLink peer memory (NCCL sets up the group)"
+                                   if cx.world > 1 else ""),
                    "l2": "256 MiB written between timed steps (outside the per-step events); "
                          "the kernel reads no HBM input"},
         "e2e": {"value": e2e["value"], "unit": "path-steps/s", "h2d_bytes_per_step": h2d,

@@ -332,6 +332,18 @@ int optmc_lsmc_peer_export(optmc_ctx *ctx, void *handle_out);
 int optmc_lsmc_peer_attach(optmc_ctx *ctx, int32_t rank, int32_t world, const void *handles);
 
 /*
+ * The all-reduce that ends a partitioned pricing (the payoff moments, 48 bytes
+ * per contract), as ONE kernel of this library on the pricing's stream instead of a library
+ * collective: every rank stores its n doubles into every attached rank's exchange buffer
+ * (peer stores over NVLink, flag-carrying 16-byte slots) and adds the world's rows from its
+ * local copy in rank order -- bit-identical sums on every rank.  vals_dev is reduced in place.
+ * Needs optmc_lsmc_peer_attach (the same exported buffer); ranks must make the same sequence
+ * of calls (SPMD).  A rank that never arrives ends the others in a wall-clock time-out
+ * (20 s): the values come back as NaN 0x7FF8DEADDEADDEAD and the next synchronising call fails.
+ */
+int optmc_peer_allreduce_async(optmc_ctx *ctx, double *vals_dev, int32_t n, void *stream);
+
+/*
  * Diagnostics used by the tests and by bench.py's roofline.
  *   optmc_philox_raw     out_dev[4*i..] = Philox4x32-10(counter = (lo(i), hi(i), c2, c3), key = seed)
  *   optmc_normals        out_dev[2*i], out_dev[2*i+1] = the two N(0,1) of Box-Muller pair

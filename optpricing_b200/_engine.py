@@ -83,6 +83,7 @@ SIGNATURES = [
     ("optmc_european_scen_async", c_int, [c_void_p, ctypes.POINTER(OptmcModel),
                                           ctypes.POINTER(OptmcSim), c_i32, _dp, c_double, c_i32,
                                           c_void_p, c_void_p]),
+    ("optmc_peer_allreduce_async", c_int, [c_void_p, c_void_p, c_i32, c_void_p]),
     ("optmc_sigma_sweep_async", c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i32, _dp, _dp, _dp,
                                         _ip, c_void_p, c_void_p]),
     ("optmc_payoff_sweep_async", c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i32, _dp, _ip,
@@ -518,6 +519,36 @@ class Engine:
                               + (f" (here: {err})" if err else ""))
         self._peer_key = key
         return rank, world
+
+    PEER_AR_MAX = 1536
+
+    def peer_all_reduce(self, t):
+        """Sum the float64 device tensor ``t`` (<= 1536 elements per call, else in chunks) over
+        the attached ranks in place: optmc_peer_allreduce_async, a kernel of this library doing
+        the exchange over NVLink peer memory on the current stream."""
+        n = t.numel()
+        for lo in range(0, n, self.PEER_AR_MAX):
+            m = min(self.PEER_AR_MAX, n - lo)
+            self._check(self.lib.optmc_peer_allreduce_async(
+                self.ctx, c_void_p(t.data_ptr() + 8 * lo), m, self.stream()),
+                "optmc_peer_allreduce_async")
+
+    def group_all_reduce(self):
+        """The all-reduce a technique ends a partitioned pricing with: over NVLink peer memory
+        when the process group is NCCL and the ranks' buffers map into each other (attached on
+        first use, agreed on by all ranks), else torch.distributed's."""
+        import torch.distributed as dist
+        mode = getattr(self, "_ar_mode", None)
+        if mode is None:
+            mode = "dist"
+            if dist.get_backend() == "nccl" and os.environ.get("OPTMC_PEER_ALLREDUCE", "1") != "0":
+                try:
+                    self.lsmc_peer_attach()
+                    mode = "peer"
+                except EngineError:
+                    mode = "dist"
+            self._ar_mode = mode
+        return self.peer_all_reduce if mode == "peer" else dist.all_reduce
 
     def lsmc_peer_detach(self):
         if getattr(self, "_peer_key", None) is not None:

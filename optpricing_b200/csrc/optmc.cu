@@ -46,6 +46,7 @@ struct optmc_ctx {
     int peer_rank = 0, peer_world = 1;
     int use_peers = 0;                           // "lsmc_use_peers": next optmc_lsmc is a joint call
     uint32_t peer_nonce = 0;
+    uint32_t euro_peer_nonce = 0;                // k_peer_allreduce: one per call, same on all ranks
     std::string err;
 };
 
@@ -70,6 +71,10 @@ static std::string g_create_err;
     } while (0)
 
 static constexpr size_t SCRATCH_BYTES = 8u << 20;
+// The buffer every rank exports over CUDA IPC: the LSMC exchange rows, then the slots of the
+// small all-reduce (k_peer_allreduce): [2 call parity][OPTMC_MAX_PEERS][PEER_AR_MAX].
+static constexpr size_t RANK_SLOTS_LSMC = (size_t)4 * OPTMC_MAX_PEERS * LSMC_P_STRIDE;
+static constexpr size_t RANK_SLOTS_TOTAL = RANK_SLOTS_LSMC + (size_t)2 * OPTMC_MAX_PEERS * PEER_AR_MAX;
 static constexpr int MAX_GRID = 148 * 16 * 2;   // partial rows the scratch is carved for
 
 extern "C" int optmc_version(void) { return 100; }
@@ -117,7 +122,7 @@ extern "C" int optmc_ctx_create(int device, optmc_ctx **out) {
                            cudaHostAllocDefault)) != cudaSuccess)
         return fail(e, "cudaHostAlloc");
     {
-        const size_t bytes = sizeof(uint4) * 4 * OPTMC_MAX_PEERS * LSMC_P_STRIDE;
+        const size_t bytes = sizeof(uint4) * RANK_SLOTS_TOTAL;
         if ((e = cudaMalloc(&ctx->rank_slots, bytes)) != cudaSuccess) return fail(e, "cudaMalloc");
         if ((e = cudaMemset(ctx->rank_slots, 0, bytes)) != cudaSuccess) return fail(e, "cudaMemset");
     }
@@ -1184,7 +1189,8 @@ extern "C" int optmc_lsmc_peer_attach(optmc_ctx *ctx, int32_t rank, int32_t worl
     ctx->peer_world = 1;
     ctx->peer_nonce = 0;
     ctx->use_peers = 0;
-    CK(cudaMemset(ctx->rank_slots, 0, sizeof(uint4) * 4 * OPTMC_MAX_PEERS * LSMC_P_STRIDE));
+    CK(cudaMemset(ctx->rank_slots, 0, sizeof(uint4) * RANK_SLOTS_TOTAL));
+    ctx->euro_peer_nonce = 0;
     if (world == 1) return 0;
     if (!handles) FAIL("handles is null");
     for (int r = 0; r < world; ++r) {
@@ -1200,6 +1206,29 @@ extern "C" int optmc_lsmc_peer_attach(optmc_ctx *ctx, int32_t rank, int32_t worl
     }
     ctx->peer_rank = rank;
     ctx->peer_world = world;
+    return 0;
+}
+
+extern "C" int optmc_peer_allreduce_async(optmc_ctx *ctx, double *vals_dev, int32_t n,
+                                          void *stream) {
+    if (!ctx) return -2;
+    CK(cudaSetDevice(ctx->device));
+    if (!vals_dev || n < 1 || n > PEER_AR_MAX) FAIL("bad arguments (1 <= n <= 1536)");
+    if (ctx->peer_world < 2) FAIL("no peers attached (optmc_lsmc_peer_attach)");
+    PeerReduceArgs A;
+    memset(&A, 0, sizeof A);
+    A.vals = vals_dev;
+    A.n = n;
+    A.rank = ctx->peer_rank;
+    A.world = ctx->peer_world;
+    ctx->euro_peer_nonce = ctx->euro_peer_nonce == 0xFFFFFFFFu ? 1u : ctx->euro_peer_nonce + 1u;
+    A.tag = ctx->euro_peer_nonce;
+    A.euro_off = RANK_SLOTS_LSMC;
+    for (int r = 0; r < OPTMC_MAX_PEERS; ++r) A.peer_rank_slots[r] = ctx->peer_rank_slots[r];
+    A.error = ctx->ticket + 9;
+    k_peer_allreduce<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(A);
+    ctx->launches++;
+    CK(cudaGetLastError());
     return 0;
 }
 

@@ -113,7 +113,7 @@ class AmericanMonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
             return 0, 1, None
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return 0, 1, None
-        return dist.get_rank(), dist.get_world_size(), dist.all_reduce
+        return dist.get_rank(), dist.get_world_size(), dist.all_reduce   # per-date sums: NCCL path
 
     def _get_path_kernel_and_params(self, model, r: float, q: float, dt: float, **kwargs: Any):
         """(path kernel, keyword arguments) as american_monte_carlo.py:75-150 pairs them."""

@@ -84,8 +84,30 @@ def control_mean(kind: str, params: dict, S0: float, r: float, q: float, T: floa
     return S0 * math.exp((r - q) * T)
 
 
+def _group_all_reduce(dist):
+    """The all-reduce of a partitioned pricing: the engine's own kernel over NVLink peer memory
+    on an NCCL group (csrc/lsmc.cuh: k_peer_allreduce), torch.distributed's otherwise."""
+    try:
+        pick = getattr(_engine.get_engine(), "group_all_reduce", None)
+    except _engine.EngineError:          # no GPU in this process (gloo tests of the host logic)
+        pick = None
+    return pick() if pick is not None else dist.all_reduce
+
+
+_POISON = np.uint64(0x7FF8DEADDEADDEAD)
+
+
+def _check_reduced(mom: np.ndarray) -> None:
+    """A rank that never arrived at a peer all-reduce leaves poison, not numbers."""
+    m = np.ascontiguousarray(mom, dtype=np.float64)
+    if np.isnan(m).any() and (m.view(np.uint64) == _POISON).any():
+        raise _engine.EngineError("peer all-reduce timed out: a rank of the group did not make "
+                                  "this call (the techniques must be called by all ranks, SPMD)")
+
+
 def summarize(moments, r: float, T: float, c_mean: float) -> dict:
     """Price, standard error and control-variate estimate from (n, Sp, Spp, Sc, Scc, Spc)."""
+    _check_reduced(np.asarray(moments))
     n, sp, spp, sc, scc, spc = (float(x) for x in moments)
     disc = math.exp(-r * T)
     if n <= 0.0:        # no samples: the mean of an empty array, as np.mean gives the reference
@@ -109,6 +131,7 @@ def summarize(moments, r: float, T: float, c_mean: float) -> dict:
 
 def prices_from_moments(mom: np.ndarray, r: float, T: float, c_mean: float, use_cv: bool):
     """Vectorised ``summarize`` for the price only: mom is (n, 6)."""
+    _check_reduced(mom)
     n, sp, spp, sc, scc, spc = (mom[:, k] for k in range(6))
     disc = math.exp(-r * T)
     with np.errstate(divide="ignore", invalid="ignore"):      # n = 0 rows price to nan
@@ -315,7 +338,7 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
             return 0, 1, None
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return 0, 1, None
-        return dist.get_rank(), dist.get_world_size(), dist.all_reduce
+        return dist.get_rank(), dist.get_world_size(), _group_all_reduce(dist)
 
     # ------------------------------------------------------------- simulators
     def _simulate_sde_path(self, model, S0: float, r: float, q: float, T: float, **kwargs: Any):

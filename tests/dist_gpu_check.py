@@ -37,6 +37,22 @@ for name, model in (("heston", ob.HestonModel()), ("bates", ob.BatesModel()),
         print(f"european {name:9s} world={world}: distributed {d:.12f} single {s:.12f} {'ok' if ok else 'MISMATCH'}")
     if not ok:
         fails.append(name)
+# the engine's own all-reduce kernel (NVLink peer memory) against NCCL's, several sizes and calls
+from optpricing_b200 import _engine
+eng = _engine.get_engine()
+ar = eng.group_all_reduce()
+if rank == 0:
+    print("group all-reduce:", "k_peer_allreduce over NVLink peer memory" if ar == eng.peer_all_reduce
+          else "torch.distributed (NCCL)")
+for n in (1, 6, 384, 1536, 4000):
+    for rep in range(3):
+        g = torch.Generator(device="cuda").manual_seed(1000 * rank + n + rep)
+        a = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+        b = a.clone()
+        ar(a)
+        dist.all_reduce(b)
+        if not torch.allclose(a, b, rtol=1e-14, atol=1e-14):
+            fails.append(f"peer_allreduce_{n}")
 import time
 for name, model, deg in (("bsm", ob.BSMModel(), 3), ("heston", ob.HestonModel(), 2)):
     kw = dict(n_paths=(1 << 19) + 2, n_steps=20, seed=5, lsm_degree=deg)
