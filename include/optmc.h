@@ -332,6 +332,14 @@ int optmc_lsmc_peer_export(optmc_ctx *ctx, void *handle_out);
 int optmc_lsmc_peer_attach(optmc_ctx *ctx, int32_t rank, int32_t world, const void *handles);
 
 /*
+ * Read n (<= 384) doubles of device memory -- payoff moments -- into host memory through the
+ * context's pinned buffer: one asynchronous copy on `stream`, one synchronisation.  What
+ * optmc_european does at its end, for callers of the *_async entry points.
+ */
+int optmc_read_doubles(optmc_ctx *ctx, const double *src_dev, int32_t n, double *out_host,
+                       void *stream);
+
+/*
  * The all-reduce that ends a partitioned pricing (the payoff moments, 48 bytes
  * per contract), as ONE kernel of this library on the pricing's stream instead of a library
  * collective: every rank stores its n doubles into every attached rank's exchange buffer

@@ -84,6 +84,7 @@ SIGNATURES = [
                                           ctypes.POINTER(OptmcSim), c_i32, _dp, c_double, c_i32,
                                           c_void_p, c_void_p]),
     ("optmc_peer_allreduce_async", c_int, [c_void_p, c_void_p, c_i32, c_void_p]),
+    ("optmc_read_doubles", c_int, [c_void_p, c_void_p, c_i32, _dp, c_void_p]),
     ("optmc_sigma_sweep_async", c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i32, _dp, _dp, _dp,
                                         _ip, c_void_p, c_void_p]),
     ("optmc_payoff_sweep_async", c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i32, _dp, _ip,
@@ -328,6 +329,10 @@ class Engine:
 
     @staticmethod
     def _contracts(strikes, is_call):
+        if len(strikes) == 1 and len(is_call) == 1:          # one contract: no numpy round trip
+            k = np.array([strikes[0]], dtype=np.float64)
+            c = np.array([1 if is_call[0] else 0], dtype=np.int32)
+            return k, c, k.ctypes.data_as(_dp), c.ctypes.data_as(_ip)
         k = np.ascontiguousarray(np.atleast_1d(strikes), dtype=np.float64)
         c = np.ascontiguousarray(np.broadcast_to(np.atleast_1d(is_call), k.shape), dtype=np.int32)
         return k, c, k.ctypes.data_as(_dp), c.ctypes.data_as(_ip)
@@ -519,6 +524,18 @@ class Engine:
                               + (f" (here: {err})" if err else ""))
         self._peer_key = key
         return rank, world
+
+    def read(self, t, n):
+        """The first n doubles of the device tensor ``t`` as a numpy array: through the
+        context's pinned buffer (optmc_read_doubles) while they fit, else a torch copy."""
+        n = int(n)
+        if n > 384:
+            return t[:n].cpu().numpy()
+        out = np.empty(n)
+        self._check(self.lib.optmc_read_doubles(self.ctx, c_void_p(t.data_ptr()), n,
+                                                out.ctypes.data_as(_dp), self.stream()),
+                    "optmc_read_doubles")
+        return out
 
     PEER_AR_MAX = 1536
 

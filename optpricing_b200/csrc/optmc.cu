@@ -1209,6 +1209,19 @@ extern "C" int optmc_lsmc_peer_attach(optmc_ctx *ctx, int32_t rank, int32_t worl
     return 0;
 }
 
+extern "C" int optmc_read_doubles(optmc_ctx *ctx, const double *src_dev, int32_t n,
+                                  double *out_host, void *stream) {
+    if (!ctx) return -2;
+    CK(cudaSetDevice(ctx->device));
+    if (!src_dev || !out_host || n < 1 || n > SWEEP_MAX * OPTMC_NMOM)
+        FAIL("bad arguments (1 <= n <= 384)");
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(ctx->moments_host, src_dev, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(out_host, ctx->moments_host, sizeof(double) * (size_t)n);
+    return 0;
+}
+
 extern "C" int optmc_peer_allreduce_async(optmc_ctx *ctx, double *vals_dev, int32_t n,
                                           void *stream) {
     if (!ctx) return -2;

@@ -107,8 +107,9 @@ def _check_reduced(mom: np.ndarray) -> None:
 
 def summarize(moments, r: float, T: float, c_mean: float) -> dict:
     """Price, standard error and control-variate estimate from (n, Sp, Spp, Sc, Scc, Spc)."""
-    _check_reduced(np.asarray(moments))
     n, sp, spp, sc, scc, spc = (float(x) for x in moments)
+    if sp != sp or sc != sc:
+        _check_reduced(np.asarray(moments))
     disc = math.exp(-r * T)
     if n <= 0.0:        # no samples: the mean of an empty array, as np.mean gives the reference
         return {"n_samples": 0.0, "price": float("nan"), "stderr": float("nan"),
@@ -373,7 +374,7 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
             dev = eng.buffer("moments", _engine.NMOM)
             eng.european_async(mdl, sim, [K], [1 if call else 0], dev)
             all_reduce(dev[: _engine.NMOM])
-            mom = dev[: _engine.NMOM].cpu().numpy()
+            mom = eng.read(dev, _engine.NMOM)
         return DeviceTerminal(mom, kind, seed)
 
     def _device_model(self, eng, kind, model, S0, r, q, T, **kwargs):
@@ -467,7 +468,7 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
         _, _, all_reduce = self._group()
         if all_reduce is not None:
             all_reduce(dev[: n * _engine.NMOM])
-        return dev[: n * _engine.NMOM].cpu().numpy().reshape(n, _engine.NMOM), kind, seed
+        return eng.read(dev, n * _engine.NMOM).reshape(n, _engine.NMOM), kind, seed
 
     @_engine.serialized
     def price_many(self, options, stock, model, rate, **kwargs: Any) -> np.ndarray:
@@ -505,7 +506,7 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
         _, _, all_reduce = self._group()
         if all_reduce is not None:
             all_reduce(dev[: total * _engine.NMOM])
-        mom_all = dev[: total * _engine.NMOM].cpu().numpy().reshape(total, _engine.NMOM)
+        mom_all = eng.read(dev, total * _engine.NMOM).reshape(total, _engine.NMOM)
         for T, r, idx, pos, kind, seed, steps in jobs:
             c_mean = control_mean(kind, model.params, S0, r, q, T, steps)
             block = mom_all[pos:pos + len(idx)]
@@ -605,7 +606,7 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
             eng.european_scen_async(mdl, sim, spot_factors, K, _is_call(option), dev)
             if all_reduce is not None:
                 all_reduce(dev[: n * _engine.NMOM])
-            mom = dev[: n * _engine.NMOM].cpu().numpy().reshape(n, _engine.NMOM)
+            mom = eng.read(dev, n * _engine.NMOM).reshape(n, _engine.NMOM)
             out = []
             for f, row in zip(spot_factors, mom):
                 c_mean = control_mean(kind, model.params, S0 * f, r, q, T, self.n_steps)
@@ -760,7 +761,7 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
                               [1 if call else 0] * 2)
         if all_reduce is not None:
             all_reduce(dev[: 2 * _engine.NMOM])
-        mom = dev[: 2 * _engine.NMOM].cpu().numpy().reshape(2, _engine.NMOM)
+        mom = eng.read(dev, 2 * _engine.NMOM).reshape(2, _engine.NMOM)
         c_mean = control_mean(kind, p, S0, r, q, T, steps)
         prices = []
         for row in mom:
@@ -801,7 +802,7 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
         eng.levy_terminal_async(levy, S0, drift, seed, off, cnt, [K], [1 if call else 0], dev)
         if all_reduce is not None:
             all_reduce(dev[: _engine.NMOM])
-        return DeviceTerminal(dev[: _engine.NMOM].cpu().numpy(), kind, seed)
+        return DeviceTerminal(eng.read(dev, _engine.NMOM), kind, seed)
 
     _ONE_FACTOR_KINDS = ("bsm", "merton", "kou")
 
@@ -847,7 +848,7 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
                               [1 if call else 0] * 2)
         if all_reduce is not None:
             all_reduce(dev[: 2 * _engine.NMOM])
-        mom = dev[: 2 * _engine.NMOM].cpu().numpy().reshape(2, _engine.NMOM)
+        mom = eng.read(dev, 2 * _engine.NMOM).reshape(2, _engine.NMOM)
         c_mean = control_mean(kind, p, S0, r, q, T, self.n_steps)
         prices = []
         for row in mom:
@@ -895,7 +896,7 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
                                   [1 if call else 0])
             if all_reduce is not None:
                 all_reduce(dev[: _engine.NMOM])
-            m = dev[: _engine.NMOM].cpu().numpy()
+            m = eng.read(dev, _engine.NMOM)
             p = disc * m[1] / m[0]
             return p - target_price if np.isfinite(p) else 1e6
 

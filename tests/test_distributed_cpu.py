@@ -53,6 +53,9 @@ class FakeEuropeanEngine:
     def buffer(self, name, n, dtype=None):
         return self._buf.setdefault(name, torch.zeros(n, dtype=torch.float64))
 
+    def read(self, t, n):
+        return t[:n].cpu().numpy()
+
     def make_sim(self, s0, maturity, n_draws, n_steps, antithetic, seed, correlation,
                  draw_offset=0, n_local=None, precision=0):
         return dict(seed=seed, off=draw_offset, cnt=n_local, n_draws=n_draws)
