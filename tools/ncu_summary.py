@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Summarise .ncu-rep files (read with `ncu -i ... --page raw --csv`) as a markdown table.
+"""Summarise .ncu-rep files (read with `ncu -i ... --page raw --csv`), or that page saved as .csv, as a markdown table.
 
 usage: tools/ncu_summary.py [--kernel REGEX] [--row N] label=path.ncu-rep [label=path ...]
 
@@ -44,9 +44,12 @@ METRICS = [
 
 
 def load(path, pat, nth):
-    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True,
-                         text=True).stdout
-    rows = list(csv.reader(txt.splitlines()))
+    if path.endswith(".csv"):          # `ncu -i x.ncu-rep --page raw --csv` made on the GPU box
+        txt = open(path).read()
+    else:
+        txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True,
+                             text=True).stdout
+    rows = [r for r in csv.reader(txt.splitlines()) if r and not r[0].startswith("==")]
     hdr, units = rows[0], rows[1]
     kcol = hdr.index("Kernel Name")
     sel = [r for r in rows[2:] if re.search(pat, r[kcol])]
