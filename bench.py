@@ -58,7 +58,7 @@ sys.path.insert(0, ROOT)
 #   reads  32-bit vector-register operand reads (B200: 2 per cycle per SM sub-partition,
 #          profiles/r01_pipe_probe3.log -- a DFMA with three distinct register operands
 #          takes 3 cycles, not 2)
-SASS = {"heston": {"i64": 13.0, "instr": 39.25, "reads": 88.75},
+SASS = {"heston": {"i64": 13.0, "instr": 38.75, "reads": 88.0},
         "bsm": {"i64": 3.75, "instr": 15.5, "reads": 31.6}}
 # Algorithmic flops per path-step (antithetic pairs share the draws)
 FLOPS_PER_PATH_STEP = {"heston": 28.0, "bsm": 6.0}

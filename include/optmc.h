@@ -350,6 +350,16 @@ int optmc_read_doubles(optmc_ctx *ctx, const double *src_dev, int32_t n, double 
  * (20 s): the values come back as NaN 0x7FF8DEADDEADDEAD and the next synchronising call fails.
  */
 int optmc_peer_allreduce_async(optmc_ctx *ctx, double *vals_dev, int32_t n, void *stream);
+/*
+ * optmc_european for one rank of a partitioned pricing: simulation of this rank's draws, the
+ * all-reduce of the moments over the attached ranks (optmc_peer_allreduce_async) and the read
+ * into host memory in ONE call and one synchronisation -- what MonteCarloTechnique.price runs
+ * per rank under an NCCL process group (monte_carlo.py:65-116 has no counterpart: it is
+ * single-process).  moments_host receives the GLOBAL moments, identical on every rank.
+ */
+int optmc_european_allreduce(optmc_ctx *ctx, const optmc_model *model, const optmc_sim *sim,
+                             int32_t n_contracts, const double *strikes, const int32_t *is_call,
+                             double *moments_host, double *terminal_dev, void *stream);
 
 /*
  * Diagnostics used by the tests and by bench.py's roofline.

@@ -84,6 +84,9 @@ SIGNATURES = [
                                           ctypes.POINTER(OptmcSim), c_i32, _dp, c_double, c_i32,
                                           c_void_p, c_void_p]),
     ("optmc_peer_allreduce_async", c_int, [c_void_p, c_void_p, c_i32, c_void_p]),
+    ("optmc_european_allreduce", c_int, [c_void_p, ctypes.POINTER(OptmcModel),
+                                         ctypes.POINTER(OptmcSim), c_i32, _dp, _ip, _dp, c_void_p,
+                                         c_void_p]),
     ("optmc_read_doubles", c_int, [c_void_p, c_void_p, c_i32, _dp, c_void_p]),
     ("optmc_sigma_sweep_async", c_int, [c_void_p, c_void_p, c_i64, c_i32, c_i32, _dp, _dp, _dp,
                                         _ip, c_void_p, c_void_p]),
@@ -349,6 +352,18 @@ class Engine:
         self._check(self.lib.optmc_european(self.ctx, ctypes.byref(model), ctypes.byref(sim),
                                             k.size, kp, cp, out.ctypes.data_as(_dp), tptr,
                                             self.stream()), "optmc_european")
+        return out
+
+    def european_allreduce(self, model: OptmcModel, sim: OptmcSim, strikes, is_call):
+        """optmc_european_allreduce: this rank's shard, the all-reduce over the attached ranks and
+        the read in one call -> host moments (n_contracts, 6), global and identical on all ranks."""
+        self.n_simulations += 1
+        k, c, kp, cp = self._contracts(strikes, is_call)
+        out = np.empty((k.size, NMOM))
+        self._check(self.lib.optmc_european_allreduce(self.ctx, ctypes.byref(model),
+                                                      ctypes.byref(sim), k.size, kp, cp,
+                                                      out.ctypes.data_as(_dp), None, self.stream()),
+                    "optmc_european_allreduce")
         return out
 
     def european_async(self, model, sim, strikes, is_call, moments, terminal=None, aux=None):

@@ -1209,6 +1209,29 @@ extern "C" int optmc_lsmc_peer_attach(optmc_ctx *ctx, int32_t rank, int32_t worl
     return 0;
 }
 
+static int peer_allreduce_launch(optmc_ctx *ctx, double *vals_dev, int32_t n, cudaStream_t st);
+
+extern "C" int optmc_european_allreduce(optmc_ctx *ctx, const optmc_model *model,
+                                        const optmc_sim *sim, int32_t n_contracts,
+                                        const double *strikes, const int32_t *is_call,
+                                        double *moments_host, double *terminal_dev, void *stream) {
+    if (!ctx) return -2;
+    if (!moments_host) FAIL("moments_host is null");
+    if (n_contracts > SWEEP_MAX) FAIL("optmc_european_allreduce handles at most 64 contracts per call");
+    if (ctx->peer_world < 2) FAIL("no peers attached (optmc_lsmc_peer_attach)");
+    int rc = optmc_european_async(ctx, model, sim, n_contracts, strikes, is_call, ctx->moments_dev,
+                                  terminal_dev, stream);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = peer_allreduce_launch(ctx, ctx->moments_dev, OPTMC_NMOM * n_contracts, st);
+    if (rc) return rc;
+    const size_t bytes = sizeof(double) * OPTMC_NMOM * (size_t)n_contracts;
+    CK(cudaMemcpyAsync(ctx->moments_host, ctx->moments_dev, bytes, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(moments_host, ctx->moments_host, bytes);
+    return 0;
+}
+
 extern "C" int optmc_read_doubles(optmc_ctx *ctx, const double *src_dev, int32_t n,
                                   double *out_host, void *stream) {
     if (!ctx) return -2;
@@ -1222,10 +1245,7 @@ extern "C" int optmc_read_doubles(optmc_ctx *ctx, const double *src_dev, int32_t
     return 0;
 }
 
-extern "C" int optmc_peer_allreduce_async(optmc_ctx *ctx, double *vals_dev, int32_t n,
-                                          void *stream) {
-    if (!ctx) return -2;
-    CK(cudaSetDevice(ctx->device));
+static int peer_allreduce_launch(optmc_ctx *ctx, double *vals_dev, int32_t n, cudaStream_t st) {
     if (!vals_dev || n < 1 || n > PEER_AR_MAX) FAIL("bad arguments (1 <= n <= 1536)");
     if (ctx->peer_world < 2) FAIL("no peers attached (optmc_lsmc_peer_attach)");
     PeerReduceArgs A;
@@ -1239,10 +1259,17 @@ extern "C" int optmc_peer_allreduce_async(optmc_ctx *ctx, double *vals_dev, int3
     A.euro_off = RANK_SLOTS_LSMC;
     for (int r = 0; r < OPTMC_MAX_PEERS; ++r) A.peer_rank_slots[r] = ctx->peer_rank_slots[r];
     A.error = ctx->ticket + 9;
-    k_peer_allreduce<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(A);
+    k_peer_allreduce<<<(n + 255) / 256, 256, 0, st>>>(A);
     ctx->launches++;
     CK(cudaGetLastError());
     return 0;
+}
+
+extern "C" int optmc_peer_allreduce_async(optmc_ctx *ctx, double *vals_dev, int32_t n,
+                                          void *stream) {
+    if (!ctx) return -2;
+    CK(cudaSetDevice(ctx->device));
+    return peer_allreduce_launch(ctx, vals_dev, n, (cudaStream_t)stream);
 }
 
 extern "C" int optmc_lsmc(optmc_ctx *ctx, const double *store_dev, int64_t ld, int64_t n_paths,

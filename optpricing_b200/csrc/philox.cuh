@@ -482,12 +482,12 @@ __device__ __forceinline__ void normal_pair_lib2(uint32_t wa, uint32_t wb, doubl
 //   MIXED = true : (t1, t2) = M (cos, sin)(angle)^T
 // and the pair is (z1, z2) = sqrt(L) (t1, t2).  Heston's step needs the normals only as
 // sqrt(v) z, so it takes the parts and draws ONE root, sqrt(v L) (models.cuh).
-// L is floored at 0: for the two largest u of the top binade the table + polynomial
-// value of -2 ln u (abs. error 5e-16 there) comes out at -2e-16 instead of +2e-16.
 template <bool MIXED, class V>
 __device__ __forceinline__ void normal_parts_fast(uint32_t wa, uint32_t wb, double &L, double &t1,
                                                   double &t2, V t) {
-    L = relu64(neg2_log_u(radius_lo(wb), wa, t));
+    // (no floor at 0: the largest u of the 46-bit grid is 1 - 2^-47, where -2 ln u = 1.4e-14,
+    //  thirty times the table + polynomial's absolute error -- tests/test_host_api.py emulates it)
+    L = neg2_log_u(radius_lo(wb), wa, t);
     const uint32_t row = t.coarse_at(wb), fin = t.template fine_at<MIXED>(wb);
     const double2 f = lds_f64x2(fin);                              // (cos b_j, sin b_j)
     if constexpr (MIXED) {

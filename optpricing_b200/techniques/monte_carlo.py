@@ -370,6 +370,9 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
         K, call = self._hint
         if all_reduce is None:
             mom = eng.european(mdl, sim, [K], [1 if call else 0])[0]
+        elif all_reduce == getattr(eng, "peer_all_reduce", None):
+            # simulation, all-reduce over NVLink peer memory and read: one call, one sync
+            mom = eng.european_allreduce(mdl, sim, [K], [1 if call else 0])[0]
         else:
             dev = eng.buffer("moments", _engine.NMOM)
             eng.european_async(mdl, sim, [K], [1 if call else 0], dev)

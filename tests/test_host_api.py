@@ -321,12 +321,12 @@ def test_price_frame_validates_without_a_gpu():
     assert t.price_frame(empty, stock, ob.BSMModel(), rate).shape == (0,)
 
 
-def test_box_muller_log_table_needs_its_floor_at_zero():
-    """Why normal_parts_fast floors -2 ln u at 0 (csrc/philox.cuh): an exact emulation of the
-    512-entry table + degree-4 polynomial (neg2_log_poly, same constants, fused multiply-adds
-    in exact rational arithmetic) returns about -2e-16 instead of +2e-16 for the two largest
-    uniforms of the top binade -- and a negative radicand would turn the one-correction square
-    root into -inf.  Everywhere else in that bucket the value is positive."""
+def test_box_muller_log_table_is_positive_on_the_46_bit_grid():
+    """normal_parts_fast (csrc/philox.cuh) takes -2 ln u from a 512-entry table + degree-4
+    polynomial with an absolute error of ~5e-16 and feeds it to a square root WITHOUT a floor
+    at zero.  That is safe on the pair mapping's grid u = (x + 1/2) 2^-46: an exact emulation
+    (neg2_log_poly, same constants, fused multiply-adds in exact rational arithmetic) stays
+    positive and accurate for the largest uniforms of the top binade."""
     from fractions import Fraction as F
 
     def fma(a, b, c):
@@ -337,16 +337,113 @@ def test_box_muller_log_table_needs_its_floor_at_zero():
     def neg2_log(m, kfac):
         i = int((m - 1.0) * log_n)
         c = 1.0 + (i + 0.5) / log_n
-        tx, ty = -2.0 / c, -2.0 * math.log(c) + 24.0 * math.log(2.0)       # optmc.cu: RngBase.logt
+        tx, ty = -2.0 / c, -2.0 * math.log(c)                              # optmc.cu: RngBase.logt
         r = fma(m, tx, 2.0)
         p = fma(r, 0.03125, c_1_12)
         p = fma(p, r, 0.25)
         p = fma(p, r, 1.0)
         return fma(p, r, fma(kfac, c_n2ln2, ty))
 
-    top = [neg2_log(2.0 - k * 2.0 ** -52, 11.0) for k in (1, 2)]           # u = 1 - k 2^-53
-    assert all(-1e-15 < v < 0.0 for v in top), top
-    rest = [neg2_log(2.0 - k * 2.0 ** -52, 11.0) for k in list(range(3, 400)) + [2 ** j for j in range(9, 43)]]
-    assert min(rest) > 0.0
-    for v, k in zip(rest, list(range(3, 400)) + [2 ** j for j in range(9, 43)]):
-        assert v == pytest.approx(-2.0 * math.log1p(-k * 2.0 ** -53), abs=1e-15)
+    # u = m 2^kfac with kfac = -1 in the top binade; x = 2^46 - j  ->  m = 2 - (2 j - 1) 2^-46
+    js = list(range(1, 400)) + [2 ** e for e in range(9, 40)]
+    for j in js:
+        m = 2.0 - (2 * j - 1) * 2.0 ** -46
+        u = 0.5 * m
+        got = neg2_log(m, -1.0)
+        assert got > 0.0
+        assert got == pytest.approx(-2.0 * math.log(u), abs=1e-15)
+    # even the two largest uniforms of a 64-bit grid (Kou's jump sizes draw from one) stay
+    # positive now that the table's y carries no exponent offset (round 1's y = -2 ln c + 24 ln 2
+    # made them come out at -2e-16, the reason that generator carried a floor)
+    top = [neg2_log(2.0 - k * 2.0 ** -52, -1.0) for k in (1, 2)]
+    assert all(0.0 < v < 1e-15 for v in top), top
+
+
+def test_default_rng_mode_switches():
+    """overlay.install(rng_mode=...) / OPTPRICING_B200_RNG_MODE choose the draw source of
+    techniques constructed without rng_mode= (the mode in which the reference's lucky-seed
+    acceptance test passes by construction is "numpy")."""
+    from optpricing_b200.techniques import monte_carlo as m
+    assert ob.MonteCarloTechnique().rng_mode == "philox"
+    assert ob.AmericanMonteCarloTechnique().rng_mode == "philox"
+    m.set_default_rng_mode("numpy")
+    try:
+        assert ob.MonteCarloTechnique().rng_mode == "numpy"
+        assert ob.AmericanMonteCarloTechnique().rng_mode == "numpy"
+        assert ob.MonteCarloTechnique(rng_mode="philox").rng_mode == "philox"
+    finally:
+        m.set_default_rng_mode(None)
+    with patch.dict(os.environ, {"OPTPRICING_B200_RNG_MODE": "numpy"}):
+        assert ob.MonteCarloTechnique().rng_mode == "numpy"
+    assert ob.MonteCarloTechnique().rng_mode == "philox"
+    with pytest.raises(ValueError):
+        m.set_default_rng_mode("sobol")
+
+
+def test_poisoned_moments_raise():
+    """A rank that never arrived at k_peer_allreduce leaves NaN 0x7FF8DEADDEADDEAD, not numbers."""
+    mom = np.array([8.0, 1.0, 2.0, 3.0, 4.0, 5.0])
+    mc_mod.summarize(mom, 0.05, 1.0, 100.0)
+    bad = mom.copy()
+    bad.view(np.uint64)[1] = 0x7FF8DEADDEADDEAD
+    with pytest.raises(_engine.EngineError, match="peer all-reduce"):
+        mc_mod.summarize(bad, 0.05, 1.0, 100.0)
+    with pytest.raises(_engine.EngineError, match="peer all-reduce"):
+        mc_mod.prices_from_moments(np.stack([mom, bad]), 0.05, 1.0, 100.0, False)
+    plain_nan = mom.copy()
+    plain_nan[1] = float("nan")                       # an ordinary NaN is not poison
+    assert math.isnan(mc_mod.summarize(plain_nan, 0.05, 1.0, 100.0)["price"])
+
+
+def test_price_with_greeks_validates_its_arguments(setup):
+    opt, st, rt = setup
+    with pytest.raises(ValueError, match="unknown greeks"):
+        ob.MonteCarloTechnique().price_with_greeks(opt, st, ob.BSMModel(), rt, greeks=("delta", "speed"))
+
+
+def test_pricings_are_serialised_by_a_reentrant_lock():
+    import threading
+    order = []
+
+    @_engine.serialized
+    def inner(tag):
+        order.append(("in", tag))
+        return tag
+
+    @_engine.serialized
+    def outer(tag):
+        order.append(("enter", tag))
+        inner(tag)                                   # re-entrant: greeks call price()
+        order.append(("leave", tag))
+
+    ts = [threading.Thread(target=outer, args=(i,)) for i in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for k in range(0, len(order), 3):                # no interleaving between threads
+        tags = {t for _, t in order[k:k + 3]}
+        assert len(tags) == 1 and [w for w, _ in order[k:k + 3]] == ["enter", "in", "leave"]
+
+
+def test_bench_sass_constants_match_the_built_kernel():
+    """bench.py's roofline multiplies path-steps/s by static SASS counts of the headline
+    kernel's step loop: hold them to what tools/sass_stats.py reads off the built library."""
+    import shutil
+    import subprocess
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("no cuobjdump")
+    from optpricing_b200.build import build
+    build()
+    sys.path.insert(0, ROOT)
+    import bench
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_stats.py"),
+                          r"k_european_wide<1, true, false, false, 768>"], capture_output=True,
+                         text=True, cwd=ROOT, timeout=600).stdout
+    loops = re.findall(r"loop \S+: (\d+) instr, fp64-pipe (\d+) .*?MUFU (\d+), .*?reg reads (\d+)", out)
+    main = [tuple(map(int, l)) for l in loops if int(l[2]) == 4]    # two pair-steps: four roots
+    assert main, out[-2000:]
+    instr, fp64, _, reads = min(main)                              # the whole-call loop body
+    sass = bench.SASS["heston"]                                    # per PATH-step: body / 4
+    assert fp64 / 4 == pytest.approx(sass["i64"], rel=0.01)
+    assert instr / 4 == pytest.approx(sass["instr"], rel=0.04)
+    assert reads / 4 == pytest.approx(sass["reads"], rel=0.04)
