@@ -580,6 +580,8 @@ class Engine:
                 except EngineError:
                     mode = "dist"
             self._ar_mode = mode
+        if mode == "peer":
+            self.lsmc_peer_attach()          # idempotent per group: re-attaches after a new group
         return self.peer_all_reduce if mode == "peer" else dist.all_reduce
 
     def lsmc_peer_detach(self):

@@ -205,7 +205,11 @@ __device__ __forceinline__ double lsmc_path(double y_in, double s_dec, double s_
                                             const double *beta, double K, double inv_K, bool call,
                                             double disc, LsmcAcc<DEG> &acc) {
     double y;
-    const double iv_dec = call ? s_dec - K : K - s_dec;
+    // intrinsic value sgn (S - K) as ONE fused multiply-add, sgn = +-1: the products are exact,
+    // so the single rounding is that of S - K or K - S -- the same bits as the two-sided form,
+    // without computing both sides and selecting (2 DADD + 2 FSEL per use)
+    const double sgn = call ? 1.0 : -1.0, nsK = call ? -K : K;
+    const double iv_dec = fma(sgn, s_dec, nsK);
     if constexpr (INIT) {
         y = fmax(iv_dec, 0.0);                                        // american_mc_kernels.py:48-51
     } else {
@@ -224,7 +228,7 @@ __device__ __forceinline__ double lsmc_path(double y_in, double s_dec, double s_
         acc.a[2] = fma(y, y, acc.a[2]);
     } else {
         constexpr int NP = LsmcAcc<DEG>::NP, NQ = LsmcAcc<DEG>::NQ;
-        const double iv = call ? s_acc - K : K - s_acc;               // :57-60
+        const double iv = fma(sgn, s_acc, nsK);                       // :57-60
         const double w = iv > 0.0 ? 1.0 : 0.0;
         const double x = fma(s_acc, inv_K, -1.0);
         double pw[NP];
@@ -459,27 +463,36 @@ __device__ __forceinline__ void lsmc_sweep(const double *__restrict__ row_dec,
     double2 *cf2 = reinterpret_cast<double2 *>(cashflow);
     const double2 zero = make_double2(0.0, 0.0);
     const bool need_dec = INIT || use_fit;
-    for (int64_t qa = q0 + threadIdx.x; qa < q1; qa += (int64_t)U * T) {
+    int64_t qa = q0 + threadIdx.x;
+    // whole groups of U trips: no bounds tests, no zero fills
+    for (; qa + (int64_t)(U - 1) * T < q1; qa += (int64_t)U * T) {
         double2 sd[U], sa[U], y[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int64_t q = qa + (int64_t)u * T;
-            const bool in = u == 0 || q < q1;
-            sd[u] = (in && need_dec) ? __ldcs(dec2 + q) : zero;
-            y[u] = (in && !INIT) ? cf2[q] : zero;
-            sa[u] = (in && !FINAL) ? acc2[q] : zero;
+            sd[u] = need_dec ? __ldcs(dec2 + q) : zero;
+            y[u] = !INIT ? cf2[q] : zero;
+            sa[u] = !FINAL ? acc2[q] : zero;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int64_t q = qa + (int64_t)u * T;
-            if (u == 0 || q < q1) {
-                y[u].x = lsmc_path<DEG, INIT, FINAL>(y[u].x, sd[u].x, sa[u].x, use_fit, beta, K,
-                                                     inv_K, call, disc, acc);
-                y[u].y = lsmc_path<DEG, INIT, FINAL>(y[u].y, sd[u].y, sa[u].y, use_fit, beta, K,
-                                                     inv_K, call, disc, acc);
-                if (!FINAL) cf2[q] = y[u];
-            }
+            y[u].x = lsmc_path<DEG, INIT, FINAL>(y[u].x, sd[u].x, sa[u].x, use_fit, beta, K, inv_K,
+                                                 call, disc, acc);
+            y[u].y = lsmc_path<DEG, INIT, FINAL>(y[u].y, sd[u].y, sa[u].y, use_fit, beta, K, inv_K,
+                                                 call, disc, acc);
+            if (!FINAL) cf2[q] = y[u];
         }
+    }
+    // the ragged rest of the slice, one trip at a time
+#pragma unroll 1
+    for (; qa < q1; qa += T) {
+        const double2 sd = need_dec ? __ldcs(dec2 + qa) : zero;
+        double2 y = !INIT ? cf2[qa] : zero;
+        const double2 sa = !FINAL ? acc2[qa] : zero;
+        y.x = lsmc_path<DEG, INIT, FINAL>(y.x, sd.x, sa.x, use_fit, beta, K, inv_K, call, disc, acc);
+        y.y = lsmc_path<DEG, INIT, FINAL>(y.y, sd.y, sa.y, use_fit, beta, K, inv_K, call, disc, acc);
+        if (!FINAL) cf2[qa] = y;
     }
 }
 
