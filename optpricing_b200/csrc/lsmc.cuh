@@ -496,6 +496,116 @@ __device__ __forceinline__ void lsmc_sweep(const double *__restrict__ row_dec,
     }
 }
 
+// ---- the same sweep fed by an asynchronous-copy ring ------------------------------------
+// Loads held in registers are issued in a burst and then waited for: the four warps of a
+// sub-partition, in step with each other, all stall at once (ncu: long_scoreboard 4.6 cycles
+// per issue, issue slots 39 % busy).  Here every thread keeps S trips in flight as
+// cp.async (LDGSTS) copies into its own slots of a shared-memory ring -- no registers, no
+// burst: one new trip is requested per trip consumed -- and reads a trip back with three
+// LDS.128 once cp.async.wait_group says it has landed.  Only the owning thread touches a slot,
+// so no barrier is needed.  L2 policy per stream, as before: the decision row is read for the
+// last time (evict-first), the cashflows live in L2 for the whole launch (evict-last).
+#ifndef OPTMC_LSMC_ASYNC_STAGES
+#define OPTMC_LSMC_ASYNC_STAGES 4            // ring stages of the RING instantiation (a power of two)
+#endif
+#ifndef OPTMC_LSMC_ASYNC_TRIPS
+#define OPTMC_LSMC_ASYNC_TRIPS 1             // trips (pairs of paths) per ring stage
+#endif
+// Measured at degree 3 (tools/lsmc_phases.py, us per date, register-staged -> ring of 4): 2^22
+// paths 16.7 -> 14.5, 2^20 paths 7.0 -> 8.2 (the blocks drift apart and the exchange waits
+// longer), so the host takes the ring from 2^21 paths per GPU up (optmc.cu).
+__host__ __device__ constexpr bool lsmc_has_ring(int deg) { return deg <= 3; }
+__host__ __device__ constexpr size_t lsmc_ring_bytes(int deg) {
+    return (size_t)OPTMC_LSMC_ASYNC_STAGES * OPTMC_LSMC_ASYNC_TRIPS * 3u * (size_t)lsmc_p_threads(deg) * 16u;
+}
+
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void cp_async16_hint(uint32_t dst, const void *src, uint64_t pol) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src),
+                 "l"(pol)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int DEG, bool INIT, bool FINAL, int S>
+__device__ __forceinline__ void lsmc_sweep_async(const double *__restrict__ row_dec,
+                                                 const double *__restrict__ row_acc,
+                                                 double *__restrict__ cashflow, int64_t q0,
+                                                 int64_t q1, bool use_fit, const double *beta,
+                                                 double K, double inv_K, bool call, double disc,
+                                                 LsmcAcc<DEG> &acc, uint32_t ring, uint64_t pol_first,
+                                                 uint64_t pol_last) {
+    static_assert(S >= 2 && (S & (S - 1)) == 0, "stages: a power of two");
+    constexpr int T = lsmc_p_threads(DEG), U = OPTMC_LSMC_ASYNC_TRIPS;
+    const double2 *dec2 = reinterpret_cast<const double2 *>(row_dec);
+    const double2 *acc2 = reinterpret_cast<const double2 *>(row_acc);
+    double2 *cf2 = reinterpret_cast<double2 *>(cashflow);
+    const double2 zero = make_double2(0.0, 0.0);
+    const bool need_dec = INIT || use_fit;
+    // slot of (stage, trip, array) for this thread: consecutive threads, consecutive 16 bytes
+    const uint32_t mine = ring + threadIdx.x * 16u;
+    auto slot = [&](int stage, int u, int arr) {
+        return mine + (uint32_t)(((stage * U + u) * 3 + arr) * T) * 16u;
+    };
+    auto request = [&](int stage, int64_t qa) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t q = qa + (int64_t)u * T;
+            if (q < q1) {
+                if (need_dec) cp_async16_hint(slot(stage, u, 0), dec2 + q, pol_first);
+                if (!INIT) cp_async16_hint(slot(stage, u, 1), cf2 + q, pol_last);
+                if (!FINAL) cp_async16(slot(stage, u, 2), acc2 + q);
+            }
+        }
+        cp_async_commit();                   // one group per stage, requested or not
+    };
+    int64_t qa = q0 + threadIdx.x;
+#pragma unroll
+    for (int s = 0; s < S - 1; ++s) request(s, qa + (int64_t)s * U * T);
+    int stage = 0;
+#pragma unroll 1
+    for (; qa < q1; qa += (int64_t)U * T) {
+        request((stage + S - 1) & (S - 1), qa + (int64_t)(S - 1) * U * T);
+        cp_async_wait<S - 1>();              // everything but the S - 1 newest groups has landed
+        double2 sd[U], y[U], sa[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            sd[u] = need_dec ? lds_f64x2(slot(stage, u, 0)) : zero;
+            y[u] = !INIT ? lds_f64x2(slot(stage, u, 1)) : zero;
+            sa[u] = !FINAL ? lds_f64x2(slot(stage, u, 2)) : zero;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t q = qa + (int64_t)u * T;
+            if (u == 0 || q < q1) {
+                y[u].x = lsmc_path<DEG, INIT, FINAL>(y[u].x, sd[u].x, sa[u].x, use_fit, beta, K,
+                                                     inv_K, call, disc, acc);
+                y[u].y = lsmc_path<DEG, INIT, FINAL>(y[u].y, sd[u].y, sa[u].y, use_fit, beta, K,
+                                                     inv_K, call, disc, acc);
+                if (!FINAL) cf2[q] = y[u];
+            }
+        }
+        stage = (stage + 1) & (S - 1);
+    }
+    cp_async_wait<0>();
+}
+
 // Sum P (16 or 32) values per lane over the warp with P - 1 (+1) shuffles instead
 // of 5 P: at every halving step a lane keeps one half of its values and trades
 // the other half with its partner.  Afterwards v[0] of lane l is the warp total of
@@ -517,7 +627,7 @@ __device__ __forceinline__ void warp_transpose_sum(double (&v)[P], int lane) {
     if constexpr (P == 16) v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
-template <int DEG>
+template <int DEG, bool USE_RING = false>
 __global__ void __launch_bounds__(lsmc_p_threads(DEG), 1)
 k_lsmc_persistent(const LsmcPersistArgs A) {
     constexpr int NV = LsmcAcc<DEG>::NV, NP = LsmcAcc<DEG>::NP;
@@ -530,6 +640,15 @@ k_lsmc_persistent(const LsmcPersistArgs A) {
     __shared__ double tot[OPTMC_LSMC_GRAM];
     __shared__ double beta[8];
     __shared__ bool ok;
+    constexpr int RING = USE_RING ? OPTMC_LSMC_ASYNC_STAGES : 0;
+    extern __shared__ __align__(16) unsigned char ring_smem[];
+    uint32_t ring = 0;
+    uint64_t pol_first = 0, pol_last = 0;
+    if constexpr (RING > 0) {
+        ring = (uint32_t)__cvta_generic_to_shared(ring_smem);
+        pol_first = l2_policy_evict_first();
+        pol_last = l2_policy_evict_last();
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int G = gridDim.x;
     const bool call = A.is_call != 0;
@@ -626,8 +745,13 @@ k_lsmc_persistent(const LsmcPersistArgs A) {
         acc.clear();
 #define OPTMC_SWEEP(I, F)                                                                       \
     do {                                                                                        \
-        lsmc_sweep<DEG, I, F>(row_dec, row_acc, A.cashflow, q0, q1, use_fit, beta, A.K,         \
-                              A.inv_K, call, A.disc, acc);                                      \
+        if constexpr (RING > 0)                                                                 \
+            lsmc_sweep_async<DEG, I, F, (RING > 0 ? RING : 2)>(row_dec, row_acc, A.cashflow, q0, q1, use_fit, \
+                                              beta, A.K, A.inv_K, call, A.disc, acc, ring,      \
+                                              pol_first, pol_last);                             \
+        else                                                                                    \
+            lsmc_sweep<DEG, I, F>(row_dec, row_acc, A.cashflow, q0, q1, use_fit, beta, A.K,     \
+                                  A.inv_K, call, A.disc, acc);                                  \
         if (odd_owner) {                                                                        \
             const int64_t p = A.n - 1;                                                          \
             double y = lsmc_path<DEG, I, F>(I ? 0.0 : A.cashflow[p], row_dec[p],                \

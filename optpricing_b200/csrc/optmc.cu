@@ -29,6 +29,7 @@ struct optmc_ctx {
     int euro_wide = 1;          // 1: lane-replicated tables, one block per SM (k_european_wide)
     int euro_threads_auto = 1;  // 1: Heston / Bates take the 1024-thread variant where it idles less
     int lsmc_mode = 1;          // 1: one persistent launch for all dates, 0: one launch per date
+    int lsmc_ring = 2;          // cp.async ring in the persistent sweep: 0 never, 1 always, 2 from 2^21 paths
     int jump_schedule = 1;      // 1: pre-drawn jump schedule where it applies, 0: Poisson word per step
     int fed_stream = 1;         // 1: k_fed_stream for the models without jumps, 0: tiled k_fed for all
     int64_t launches = 0;
@@ -208,6 +209,9 @@ extern "C" int optmc_set_int(optmc_ctx *ctx, const char *key, int64_t value) {
         if (value != 0 && value != 1) FAIL("lsmc_use_peers must be 0 or 1");
         if (value == 1 && ctx->peer_world < 2) FAIL("no peers attached (optmc_lsmc_peer_attach)");
         ctx->use_peers = (int)value;
+    } else if (!strcmp(key, "lsmc_ring")) {
+        if (value < 0 || value > 2) FAIL("lsmc_ring must be 0 (never), 1 (always) or 2 (by size)");
+        ctx->lsmc_ring = (int)value;
     } else if (!strcmp(key, "lsmc_mode")) {
         if (value != 0 && value != 1) FAIL("lsmc_mode must be 0 (launch per date) or 1 (persistent)");
         ctx->lsmc_mode = (int)value;
@@ -1109,7 +1113,24 @@ template <int D>
 static int launch_persistent(optmc_ctx *ctx, LsmcPersistArgs &A, cudaStream_t st) {
     if (ctx->sm_count > 160) FAIL("k_lsmc_persistent is sized for at most 160 SMs");
     void *args[] = {&A};
-    CK(cudaLaunchCooperativeKernel((const void *)k_lsmc_persistent<D>, dim3(ctx->sm_count),
+    if constexpr (lsmc_has_ring(D)) {
+        // large shards: the sweep fed by a cp.async ring in shared memory (lsmc.cuh)
+        if (ctx->lsmc_ring != 0 && (ctx->lsmc_ring == 1 || A.n >= (int64_t)1 << 21)) {
+            const size_t ring = lsmc_ring_bytes(D);
+            static bool attr_set[64] = {};
+            if (!attr_set[ctx->device & 63]) {
+                CK(cudaFuncSetAttribute(k_lsmc_persistent<D, true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring));
+                attr_set[ctx->device & 63] = true;
+            }
+            CK(cudaLaunchCooperativeKernel((const void *)k_lsmc_persistent<D, true>,
+                                           dim3(ctx->sm_count), dim3(lsmc_p_threads(D)), args, ring,
+                                           st));
+            ctx->launches++;
+            return 0;
+        }
+    }
+    CK(cudaLaunchCooperativeKernel((const void *)k_lsmc_persistent<D, false>, dim3(ctx->sm_count),
                                    dim3(lsmc_p_threads(D)), args, 0, st));
     ctx->launches++;
     return 0;
