@@ -339,7 +339,10 @@ constexpr int LSMC_P_STRIDE = 24;           // slots per block row (NV <= 23)
 // One 512-thread block per SM: 128 registers per thread hold the 3d+2 running sums
 // next to the loads in flight without spilling (1024 threads x 64 registers
 // spilled in the sweep and measured 7 % slower at degree 3).
-__host__ __device__ constexpr int lsmc_p_threads(int) { return 512; }
+#ifndef OPTMC_LSMC_THREADS
+#define OPTMC_LSMC_THREADS 512
+#endif
+__host__ __device__ constexpr int lsmc_p_threads(int) { return OPTMC_LSMC_THREADS; }
 #ifndef OPTMC_LSMC_UNROLL
 #define OPTMC_LSMC_UNROLL 4
 #endif
@@ -543,6 +546,38 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// Request the first S - 1 stages of a sweep.  They depend on nothing the exchange produces, so
+// the persistent kernel issues them for the NEXT date before it publishes its sums: the first
+// trips' HBM latency then overlaps the ~4 us of exchange and solve.  (The decision row is
+// requested whether or not the fit will be used.)
+template <int DEG, bool INIT, bool FINAL, int S>
+__device__ __forceinline__ void lsmc_ring_prologue(const double *__restrict__ row_dec,
+                                                   const double *__restrict__ row_acc,
+                                                   const double *__restrict__ cashflow, int64_t q0,
+                                                   int64_t q1, uint32_t ring, uint64_t pol_first,
+                                                   uint64_t pol_last) {
+    constexpr int T = lsmc_p_threads(DEG), U = OPTMC_LSMC_ASYNC_TRIPS;
+    const double2 *dec2 = reinterpret_cast<const double2 *>(row_dec);
+    const double2 *acc2 = reinterpret_cast<const double2 *>(row_acc);
+    const double2 *cf2 = reinterpret_cast<const double2 *>(cashflow);
+    const uint32_t mine = ring + threadIdx.x * 16u;
+    const int64_t qa = q0 + threadIdx.x;
+#pragma unroll
+    for (int s = 0; s < S - 1; ++s) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t q = qa + (int64_t)(s * U + u) * T;
+            if (q < q1) {
+                const uint32_t base = mine + (uint32_t)(((s * U + u) * 3) * T) * 16u;
+                cp_async16_hint(base, dec2 + q, pol_first);
+                if (!INIT) cp_async16_hint(base + (uint32_t)T * 16u, cf2 + q, pol_last);
+                if (!FINAL) cp_async16(base + 2u * (uint32_t)T * 16u, acc2 + q);
+            }
+        }
+        cp_async_commit();
+    }
+}
+
 template <int DEG, bool INIT, bool FINAL, int S>
 __device__ __forceinline__ void lsmc_sweep_async(const double *__restrict__ row_dec,
                                                  const double *__restrict__ row_acc,
@@ -550,7 +585,7 @@ __device__ __forceinline__ void lsmc_sweep_async(const double *__restrict__ row_
                                                  int64_t q1, bool use_fit, const double *beta,
                                                  double K, double inv_K, bool call, double disc,
                                                  LsmcAcc<DEG> &acc, uint32_t ring, uint64_t pol_first,
-                                                 uint64_t pol_last) {
+                                                 uint64_t pol_last, bool prologue_done) {
     static_assert(S >= 2 && (S & (S - 1)) == 0, "stages: a power of two");
     constexpr int T = lsmc_p_threads(DEG), U = OPTMC_LSMC_ASYNC_TRIPS;
     const double2 *dec2 = reinterpret_cast<const double2 *>(row_dec);
@@ -576,8 +611,9 @@ __device__ __forceinline__ void lsmc_sweep_async(const double *__restrict__ row_
         cp_async_commit();                   // one group per stage, requested or not
     };
     int64_t qa = q0 + threadIdx.x;
-#pragma unroll
-    for (int s = 0; s < S - 1; ++s) request(s, qa + (int64_t)s * U * T);
+    if (!prologue_done)
+        lsmc_ring_prologue<DEG, INIT, FINAL, S>(row_dec, row_acc, cashflow, q0, q1, ring, pol_first,
+                                                pol_last);
     int stage = 0;
 #pragma unroll 1
     for (; qa < q1; qa += (int64_t)U * T) {
@@ -660,6 +696,7 @@ k_lsmc_persistent(const LsmcPersistArgs A) {
     const bool odd_owner = (A.n & 1) && blockIdx.x == 0 && threadIdx.x == 0;
     unsigned int epoch = 0;
     bool timed_out = false;
+    bool ring_ready = false;       // the ring already holds the first stages of the coming sweep
     const bool stamp = A.timing && blockIdx.x == 0 && threadIdx.x == 0;
     for (int date = A.n_steps - 1; date >= -1; --date) {
         const bool first = date == A.n_steps - 1;
@@ -748,7 +785,7 @@ k_lsmc_persistent(const LsmcPersistArgs A) {
         if constexpr (RING > 0)                                                                 \
             lsmc_sweep_async<DEG, I, F, (RING > 0 ? RING : 2)>(row_dec, row_acc, A.cashflow, q0, q1, use_fit, \
                                               beta, A.K, A.inv_K, call, A.disc, acc, ring,      \
-                                              pol_first, pol_last);                             \
+                                              pol_first, pol_last, ring_ready);                 \
         else                                                                                    \
             lsmc_sweep<DEG, I, F>(row_dec, row_acc, A.cashflow, q0, q1, use_fit, beta, A.K,     \
                                   A.inv_K, call, A.disc, acc);                                  \
@@ -765,6 +802,21 @@ k_lsmc_persistent(const LsmcPersistArgs A) {
         else if (final_) OPTMC_SWEEP(false, true);
         else OPTMC_SWEEP(false, false);
 #undef OPTMC_SWEEP
+        if constexpr (RING > 0) {
+            // the next date's first stages, requested before this date's sums are exchanged
+            ring_ready = false;
+            if (date >= 1) {
+                const double *nd = A.store + (size_t)(date - 1) * A.ld;
+                if (date - 1 == 0)
+                    lsmc_ring_prologue<DEG, false, true, (RING > 0 ? RING : 2)>(nd, nullptr, A.cashflow, q0, q1, ring,
+                                                               pol_first, pol_last);
+                else
+                    lsmc_ring_prologue<DEG, false, false, (RING > 0 ? RING : 2)>(nd, A.store + (size_t)(date - 2) * A.ld,
+                                                                A.cashflow, q0, q1, ring, pol_first,
+                                                                pol_last);
+                ring_ready = true;
+            }
+        }
         if (stamp) A.timing[(size_t)(date + 1) * 4 + 3] = globaltimer_ns();
         // The next sweep streams row date-2 of the store from HBM.  Ask L2 for this block's
         // slice of it now: the fetch overlaps the block sums, the exchange and the solve
