@@ -65,8 +65,8 @@ FLOPS_PER_PATH_STEP = {"heston": 28.0, "bsm": 6.0}
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
 # `ncu --set full` captures summarised in profiles/ (r02_ncu_heston_summary.md,
-# r01_ncu_lsmc_summary.md).  The European kernel reads its tables and code only.
-NCU_TRAFFIC_BYTES = {"heston_c2": 47_872 + 0, "lsmc_c4_induction": 1_729_129_000 + 123_759_616,
+# r02_ncu_lsmc_summary.md).  The European kernel reads its tables and code only.
+NCU_TRAFFIC_BYTES = {"heston_c2": 50_944 + 0, "lsmc_c4_induction": 1_742_771_000 + 111_612_000,
                      "lsmc_c4_fill": 1_677_721_600}
 
 HESTON = {"v0": 0.04, "kappa": 2.0, "theta": 0.04, "rho": -0.7, "vol_of_vol": 0.5}
@@ -556,11 +556,11 @@ def c4_roofline(cx, price_ms):
     traffic = NCU_TRAFFIC_BYTES["lsmc_c4_induction"]
     ach = traffic / (best * 1e-3) / 1e9
     floor_ms = 2 * store_bytes / (peak * 1e9) * 1e3
-    return {"bound": "hbm", "kernel": "k_lsmc_persistent<3>: 50 exercise dates in one launch "
+    return {"bound": "hbm", "kernel": "k_lsmc_persistent<3, ring>: 50 exercise dates in one launch "
                                       "(induction only)",
             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
             "traffic": traffic,
-            "traffic_note": "DRAM bytes per launch measured by ncu (profiles/r01_ncu_lsmc_summary.md): "
+            "traffic_note": "DRAM bytes per launch measured by ncu (profiles/r02_ncu_lsmc_summary.md): "
                             "the 1.68 GB path store read once + cashflow write-backs; `achieved` is "
                             "these bytes over the launch time.  The 32 B per path-date of SURVEY 8 d4 "
                             "(6.7 GB) are mostly L2 hits at this size, so the launch is latency / "
