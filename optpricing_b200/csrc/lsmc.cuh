@@ -53,8 +53,12 @@ __global__ void __launch_bounds__(EURO_THREADS) k_lsmc_paths(const EuroArgs A, d
 
 // The same fill on lane-replicated tables, one block per SM (european.cuh: k_european_wide).
 // Every kind takes the layout with the exp table: the log models exponentiate each stored spot.
+#ifndef OPTMC_PATHS_SCHED_THREADS
+#define OPTMC_PATHS_SCHED_THREADS 640
+#endif
 __host__ __device__ constexpr int paths_wide_threads(int kind, bool sched) {
-    return sched ? 512 : kind_two_factor(kind) ? 768 : 1024;
+    // (jump schedule: 640 threads measured 3 % faster than 512 for Merton / Kou / Bates, 2 % slower for SABR-jump)
+    return sched ? (kind == OPTMC_SABR_JUMP ? 512 : OPTMC_PATHS_SCHED_THREADS) : kind_two_factor(kind) ? 768 : 1024;
 }
 template <int KIND>
 constexpr uint32_t paths_wide_smem_bytes() { return WideExpLayout::bytes(kind_two_factor(KIND)); }
