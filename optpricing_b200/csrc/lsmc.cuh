@@ -198,6 +198,20 @@ struct LsmcAcc {
     }
 };
 
+// a > 0 && a > c ? a : alt with ONE select: the second comparison takes the first one's
+// predicate as its AND input (the compiler emits a select per condition otherwise: 4 more
+// instructions per path in a loop that is bound by instruction issue).
+__device__ __forceinline__ double select_if_positive_and_above(double a, double c, double alt) {
+    double r;
+    asm("{\n\t.reg .pred p, q;\n\t"
+        "setp.gt.f64 p, %1, 0d0000000000000000;\n\t"
+        "setp.gt.and.f64 q, %1, %2, p;\n\t"
+        "selp.f64 %0, %1, %3, q;\n\t}"
+        : "=d"(r)
+        : "d"(a), "d"(c), "d"(alt));
+    return r;
+}
+
 // One path of the fused sweep (see k_lsmc_step).  Returns the discounted
 // cashflow to store.
 // Branch-free on purpose: within a warp some lanes are almost always in the
@@ -222,8 +236,7 @@ __device__ __forceinline__ double lsmc_path(double y_in, double s_dec, double s_
 #pragma unroll
         for (int k = DEG - 1; k >= 0; --k) cont = fma(cont, x, beta[k]);   // X @ beta, :73
         // in the money (:62) and intrinsic above the fitted continuation (:75-80)
-        const bool ex = use_fit && iv_dec > 0.0 && iv_dec > cont;
-        y = ex ? iv_dec : y_in;
+        y = use_fit ? select_if_positive_and_above(iv_dec, cont, y_in) : y_in;
     }
     y *= disc;                                                        // :54 / :84
     if constexpr (FINAL) {
@@ -347,6 +360,9 @@ constexpr int LSMC_P_STRIDE = 24;           // slots per block row (NV <= 23)
 #define OPTMC_LSMC_THREADS 512
 #endif
 __host__ __device__ constexpr int lsmc_p_threads(int) { return OPTMC_LSMC_THREADS; }
+#ifndef OPTMC_LSMC_SLICE_ALIGN
+#define OPTMC_LSMC_SLICE_ALIGN 8      // pairs: block slices start on 128-byte lines
+#endif
 #ifndef OPTMC_LSMC_UNROLL
 #define OPTMC_LSMC_UNROLL 4
 #endif
@@ -372,6 +388,7 @@ struct LsmcPersistArgs {
     unsigned int *error;       // set to 1 if an exchange times out
     double *gram;              // [n_steps][OPTMC_LSMC_GRAM], written by block 0
     unsigned long long *timing;   // optional [n_steps + 1][4] clock64 stamps of block 0 (SM cycles)
+    int timing_all;               // every block stamps: [gridDim.x][n_steps + 1][4]
 };
 
 // SM cycle counter: block 0 stays on one SM for the whole launch, so differences of its
@@ -518,9 +535,11 @@ __device__ __forceinline__ void lsmc_sweep(const double *__restrict__ row_dec,
 #ifndef OPTMC_LSMC_ASYNC_TRIPS
 #define OPTMC_LSMC_ASYNC_TRIPS 1             // trips (pairs of paths) per ring stage
 #endif
-// Measured at degree 3 (tools/lsmc_phases.py, us per date, register-staged -> ring of 4): 2^22
-// paths 16.7 -> 14.5, 2^20 paths 7.0 -> 8.2 (the blocks drift apart and the exchange waits
-// longer), so the host takes the ring from 2^21 paths per GPU up (optmc.cu).
+// Measured at degree 3 (tools/lsmc_phases.py, us per date, register-staged -> ring of 4, block
+// slices on 128-byte lines): 2^22 paths 16.6 -> 13.8, 2^21 9.7 -> 9.3, 2^20 6.9 -> 6.8, 2^19
+// 6.1 -> 5.4, 2^17 4.25 -> 4.35: the host takes the ring from 2^19 paths per GPU up (optmc.cu).
+// (With slices starting 16 bytes into a 32-byte sector the ring LOST at 2^20 and 2^21 paths:
+// every other block's sweep took 7-9 us instead of 5.8 and the exchange waited for them.)
 __host__ __device__ constexpr bool lsmc_has_ring(int deg) { return deg <= 3; }
 __host__ __device__ constexpr size_t lsmc_ring_bytes(int deg) {
     return (size_t)OPTMC_LSMC_ASYNC_STAGES * OPTMC_LSMC_ASYNC_TRIPS * 3u * (size_t)lsmc_p_threads(deg) * 16u;
@@ -566,7 +585,11 @@ __device__ __forceinline__ void lsmc_ring_prologue(const double *__restrict__ ro
     const double2 *cf2 = reinterpret_cast<const double2 *>(cashflow);
     const uint32_t mine = ring + threadIdx.x * 16u;
     const int64_t qa = q0 + threadIdx.x;
-#pragma unroll
+    // Rolled on purpose: unrolled, ptxas 12.9 encoded these hinted copies of one instantiation as
+    // `LDGSTS [R+UR0], desc[UR1]` with neither uniform register ever written -- "an illegal
+    // instruction was encountered" at run time.  tests/test_host_api.py scans the built library
+    // for that encoding.
+#pragma unroll 1
     for (int s = 0; s < S - 1; ++s) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -596,49 +619,61 @@ __device__ __forceinline__ void lsmc_sweep_async(const double *__restrict__ row_
     const double2 *acc2 = reinterpret_cast<const double2 *>(row_acc);
     double2 *cf2 = reinterpret_cast<double2 *>(cashflow);
     const double2 zero = make_double2(0.0, 0.0);
-    const bool need_dec = INIT || use_fit;
+    // The coefficients live in registers for the whole sweep (the cp.async statements are
+    // memory barriers to the compiler: read through the pointer they were re-loaded from shared
+    // memory every trip).  "No usable fit" is folded into them: a continuation value of +inf
+    // is never exceeded, so the loop carries no use_fit predicate.
+    double b[DEG + 1];
+#pragma unroll
+    for (int k = 0; k <= DEG; ++k) b[k] = use_fit ? beta[k] : (k == 0 ? __longlong_as_double(0x7FF0000000000000ll) : 0.0);
     // slot of (stage, trip, array) for this thread: consecutive threads, consecutive 16 bytes
     const uint32_t mine = ring + threadIdx.x * 16u;
     auto slot = [&](int stage, int u, int arr) {
         return mine + (uint32_t)(((stage * U + u) * 3 + arr) * T) * 16u;
     };
-    auto request = [&](int stage, int64_t qa) {
+    // 32-bit byte offsets into the block's slice (the host bounds a slice at 2^31 bytes): one
+    // offset register serves the three streams
+    const char *dec_b = reinterpret_cast<const char *>(dec2 + q0);
+    const char *acc_b = FINAL ? nullptr : reinterpret_cast<const char *>(acc2 + q0);   // (no row at the last date)
+    char *cf_b = reinterpret_cast<char *>(cf2 + q0);
+    const uint32_t end = (uint32_t)(q1 - q0) * 16u;
+    constexpr uint32_t TRIP = (uint32_t)T * 16u;
+    auto request = [&](int stage, uint32_t oa) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int64_t q = qa + (int64_t)u * T;
-            if (q < q1) {
-                if (need_dec) cp_async16_hint(slot(stage, u, 0), dec2 + q, pol_first);
-                if (!INIT) cp_async16_hint(slot(stage, u, 1), cf2 + q, pol_last);
-                if (!FINAL) cp_async16(slot(stage, u, 2), acc2 + q);
+            const uint32_t o = oa + (uint32_t)u * TRIP;
+            if (o < end) {
+                cp_async16_hint(slot(stage, u, 0), dec_b + o, pol_first);   // (also when no fit is usable)
+                if (!INIT) cp_async16_hint(slot(stage, u, 1), cf_b + o, pol_last);
+                if (!FINAL) cp_async16(slot(stage, u, 2), acc_b + o);
             }
         }
         cp_async_commit();                   // one group per stage, requested or not
     };
-    int64_t qa = q0 + threadIdx.x;
     if (!prologue_done)
         lsmc_ring_prologue<DEG, INIT, FINAL, S>(row_dec, row_acc, cashflow, q0, q1, ring, pol_first,
                                                 pol_last);
     int stage = 0;
 #pragma unroll 1
-    for (; qa < q1; qa += (int64_t)U * T) {
-        request((stage + S - 1) & (S - 1), qa + (int64_t)(S - 1) * U * T);
+    for (uint32_t oa = threadIdx.x * 16u; oa < end; oa += (uint32_t)U * TRIP) {
+        request((stage + S - 1) & (S - 1), oa + (uint32_t)(S - 1) * U * TRIP);
         cp_async_wait<S - 1>();              // everything but the S - 1 newest groups has landed
         double2 sd[U], y[U], sa[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            sd[u] = need_dec ? lds_f64x2(slot(stage, u, 0)) : zero;
+            sd[u] = lds_f64x2(slot(stage, u, 0));
             y[u] = !INIT ? lds_f64x2(slot(stage, u, 1)) : zero;
             sa[u] = !FINAL ? lds_f64x2(slot(stage, u, 2)) : zero;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int64_t q = qa + (int64_t)u * T;
-            if (u == 0 || q < q1) {
-                y[u].x = lsmc_path<DEG, INIT, FINAL>(y[u].x, sd[u].x, sa[u].x, use_fit, beta, K,
-                                                     inv_K, call, disc, acc);
-                y[u].y = lsmc_path<DEG, INIT, FINAL>(y[u].y, sd[u].y, sa[u].y, use_fit, beta, K,
-                                                     inv_K, call, disc, acc);
-                if (!FINAL) cf2[q] = y[u];
+            const uint32_t o = oa + (uint32_t)u * TRIP;
+            if (u == 0 || o < end) {
+                y[u].x = lsmc_path<DEG, INIT, FINAL>(y[u].x, sd[u].x, sa[u].x, true, b, K, inv_K, call,
+                                                     disc, acc);
+                y[u].y = lsmc_path<DEG, INIT, FINAL>(y[u].y, sd[u].y, sa[u].y, true, b, K, inv_K, call,
+                                                     disc, acc);
+                if (!FINAL) *reinterpret_cast<double2 *>(cf_b + o) = y[u];
             }
         }
         stage = (stage + 1) & (S - 1);
@@ -678,6 +713,7 @@ k_lsmc_persistent(const LsmcPersistArgs A) {
     __shared__ double scratch[NV * 32];
     __shared__ double vals[NV * GPAD];
     __shared__ double tot[OPTMC_LSMC_GRAM];
+    __shared__ double peer_vals[OPTMC_MAX_PEERS * OPTMC_LSMC_GRAM];
     __shared__ double beta[8];
     __shared__ bool ok;
     constexpr int RING = USE_RING ? OPTMC_LSMC_ASYNC_STAGES : 0;
@@ -694,17 +730,23 @@ k_lsmc_persistent(const LsmcPersistArgs A) {
     const bool call = A.is_call != 0;
     // this block's slice of path pairs
     const int64_t n2 = A.n >> 1;
-    const int64_t chunk = (n2 + G - 1) / G;
+    // Slices start on 128-byte lines (8 pairs): with slices of 7085 pairs (2^21 paths) every other
+    // block started 16 bytes into a 32-byte sector and its cp.async sweep took 7-9 us instead
+    // of 5.8 (tools/lsmc_block_phases.py).
+    const int64_t chunk = (((n2 + G - 1) / G) + OPTMC_LSMC_SLICE_ALIGN - 1) / OPTMC_LSMC_SLICE_ALIGN *
+                          OPTMC_LSMC_SLICE_ALIGN;
     const int64_t q0 = min((int64_t)blockIdx.x * chunk, n2);
     const int64_t q1 = min(q0 + chunk, n2);
     const bool odd_owner = (A.n & 1) && blockIdx.x == 0 && threadIdx.x == 0;
     unsigned int epoch = 0;
     bool timed_out = false;
     bool ring_ready = false;       // the ring already holds the first stages of the coming sweep
-    const bool stamp = A.timing && blockIdx.x == 0 && threadIdx.x == 0;
+    const bool stamp = A.timing && (blockIdx.x == 0 || A.timing_all) && threadIdx.x == 0;
+    unsigned long long *const stamps =
+        A.timing + (A.timing_all ? (size_t)blockIdx.x * (A.n_steps + 1) * 4 : 0);
     for (int date = A.n_steps - 1; date >= -1; --date) {
         const bool first = date == A.n_steps - 1;
-        if (stamp) A.timing[(size_t)(date + 1) * 4 + 0] = globaltimer_ns();
+        if (stamp) stamps[(size_t)(date + 1) * 4 + 0] = globaltimer_ns();
         if (!first) {
             // totals of the previous sweep.  All threads poll: slot i = b * NV + e goes to
             // thread i mod T, every thread has its (<= SLOTS) loads in flight at once, and
@@ -734,7 +776,7 @@ k_lsmc_persistent(const LsmcPersistArgs A) {
                 }
             }
             timed_out = __syncthreads_or(timed_out);     // block-wide: one lost slot poisons the block
-            if (stamp) A.timing[(size_t)(date + 1) * 4 + 1] = globaltimer_ns();
+            if (stamp) stamps[(size_t)(date + 1) * 4 + 1] = globaltimer_ns();
             for (int e = warp; e < NV; e += NW) {
                 double t = 0.0;
                 for (unsigned int b = lane; b < G; b += 32) t += vals[e * GPAD + b];
@@ -755,19 +797,22 @@ k_lsmc_persistent(const LsmcPersistArgs A) {
                     ll_store_sys(A.peer_rank_slots[r] + base + (size_t)A.rank * LSMC_P_STRIDE + e,
                                  timed_out ? ll_poison() : tot[e], ptag);
                 }
-                __syncthreads();         // everyone has read its own tot[] before it is overwritten
-                double v = 0.0;
+                // one thread per (rank, entry): the W polls are in flight together (one L2 round
+                // trip, not W), then entry e is added over the ranks in rank order
+                if (threadIdx.x < OPTMC_LSMC_GRAM * A.world) {
+                    const int r = threadIdx.x / OPTMC_LSMC_GRAM, e = threadIdx.x % OPTMC_LSMC_GRAM;
+                    const uint4 *slot = A.peer_rank_slots[A.rank] + base + (size_t)r * LSMC_P_STRIDE + e;
+                    double x = 0.0;
+                    if (!ll_wait(slot, ptag, ll_peek(slot), x, timed_out)) timed_out = true;
+                    peer_vals[threadIdx.x] = x;
+                }
+                timed_out = __syncthreads_or(timed_out);   // (block 0 has also read tot[] for its stores)
                 if (threadIdx.x < OPTMC_LSMC_GRAM) {
-                    const uint4 *mine = A.peer_rank_slots[A.rank] + base + threadIdx.x;
-                    for (int r = 0; r < A.world; ++r) {
-                        double x = 0.0;
-                        const uint4 *slot = mine + (size_t)r * LSMC_P_STRIDE;
-                        if (!ll_wait(slot, ptag, ll_peek(slot), x, timed_out)) timed_out = true;
-                        v += x;
-                    }
+                    double v = 0.0;
+                    for (int r = 0; r < A.world; ++r) v += peer_vals[r * OPTMC_LSMC_GRAM + threadIdx.x];
                     tot[threadIdx.x] = v;
                 }
-                timed_out = __syncthreads_or(timed_out);
+                __syncwarp();            // OPTMC_LSMC_GRAM <= 32: writers and the solving lane share warp 0
             }
             if (warp == 0) {
                 if (blockIdx.x == 0 && lane < OPTMC_LSMC_GRAM)
@@ -777,7 +822,7 @@ k_lsmc_persistent(const LsmcPersistArgs A) {
             __syncthreads();
             if (date < 0) break;
         }
-        if (stamp) A.timing[(size_t)(date + 1) * 4 + 2] = globaltimer_ns();
+        if (stamp) stamps[(size_t)(date + 1) * 4 + 2] = globaltimer_ns();
         const bool use_fit = first ? false : ok;
         const bool final_ = date == 0;
         const double *row_dec = A.store + (size_t)date * A.ld;
@@ -821,7 +866,7 @@ k_lsmc_persistent(const LsmcPersistArgs A) {
                 ring_ready = true;
             }
         }
-        if (stamp) A.timing[(size_t)(date + 1) * 4 + 3] = globaltimer_ns();
+        if (stamp) stamps[(size_t)(date + 1) * 4 + 3] = globaltimer_ns();
         // The next sweep streams row date-2 of the store from HBM.  Ask L2 for this block's
         // slice of it now: the fetch overlaps the block sums, the exchange and the solve
         // (~5 us, about one row at HBM speed), and the sweep then starts on L2 hits.

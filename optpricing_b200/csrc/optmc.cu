@@ -29,7 +29,7 @@ struct optmc_ctx {
     int euro_wide = 1;          // 1: lane-replicated tables, one block per SM (k_european_wide)
     int euro_threads_auto = 1;  // 1: Heston / Bates take the 1024-thread variant where it idles less
     int lsmc_mode = 1;          // 1: one persistent launch for all dates, 0: one launch per date
-    int lsmc_ring = 2;          // cp.async ring in the persistent sweep: 0 never, 1 always, 2 from 2^21 paths
+    int lsmc_ring = 2;          // cp.async ring in the persistent sweep: 0 never, 1 always, 2 from 2^19 paths
     int jump_schedule = 1;      // 1: pre-drawn jump schedule where it applies, 0: Poisson word per step
     int fed_stream = 1;         // 1: k_fed_stream for the models without jumps, 0: tiled k_fed for all
     int64_t launches = 0;
@@ -41,6 +41,7 @@ struct optmc_ctx {
     uint4 *lsmc_slots = nullptr;       // device: flag-carrying partial sums of k_lsmc_persistent
     uint32_t lsmc_nonce = 0;
     unsigned long long *lsmc_timing = nullptr;   // diagnostics: see optmc_set_ptr("lsmc_timing")
+    int lsmc_timing_all = 0;                     // 1: every block stamps (buffer gridDim.x times as large)
     // multi-GPU exchange of k_lsmc_persistent (optmc_lsmc_peer_*)
     uint4 *rank_slots = nullptr;                 // local buffer, exported over CUDA IPC
     uint4 *peer_rank_slots[OPTMC_MAX_PEERS] = {};
@@ -212,6 +213,8 @@ extern "C" int optmc_set_int(optmc_ctx *ctx, const char *key, int64_t value) {
     } else if (!strcmp(key, "lsmc_ring")) {
         if (value < 0 || value > 2) FAIL("lsmc_ring must be 0 (never), 1 (always) or 2 (by size)");
         ctx->lsmc_ring = (int)value;
+    } else if (!strcmp(key, "lsmc_timing_all")) {
+        ctx->lsmc_timing_all = value != 0;
     } else if (!strcmp(key, "lsmc_mode")) {
         if (value != 0 && value != 1) FAIL("lsmc_mode must be 0 (launch per date) or 1 (persistent)");
         ctx->lsmc_mode = (int)value;
@@ -1115,7 +1118,10 @@ static int launch_persistent(optmc_ctx *ctx, LsmcPersistArgs &A, cudaStream_t st
     void *args[] = {&A};
     if constexpr (lsmc_has_ring(D)) {
         // large shards: the sweep fed by a cp.async ring in shared memory (lsmc.cuh)
-        if (ctx->lsmc_ring != 0 && (ctx->lsmc_ring == 1 || A.n >= (int64_t)1 << 21)) {
+        // (measured per date, tools/lsmc_phases.py: 2^19 paths 5.4 us against 6.1 without, 2^18 the
+        // same, 2^17 4.35 against 4.25.)  The ring addresses a block's slice by 32-bit byte offsets.
+        const bool slice_fits = (A.n / 2 / ctx->sm_count + 16) * 16 < ((int64_t)1 << 31);
+        if (ctx->lsmc_ring != 0 && slice_fits && (ctx->lsmc_ring == 1 || A.n >= (int64_t)1 << 19)) {
             const size_t ring = lsmc_ring_bytes(D);
             static bool attr_set[64] = {};
             if (!attr_set[ctx->device & 63]) {
@@ -1163,6 +1169,7 @@ static int lsmc_persistent(optmc_ctx *ctx, const double *store_dev, int64_t ld, 
     A.error = ctx->ticket + 8;
     A.gram = gram_dev;
     A.timing = ctx->lsmc_timing;
+    A.timing_all = ctx->lsmc_timing_all;
     const bool joint = ctx->use_peers && ctx->peer_world > 1;
     A.rank = joint ? ctx->peer_rank : 0;
     A.world = joint ? ctx->peer_world : 1;

@@ -259,7 +259,7 @@ def test_lsmc_persistent_launch_equals_per_date_launches(eng, n_paths, n_steps, 
         finally:
             eng.set_int("lsmc_mode", 1)
     assert got[1] == pytest.approx(got[0], rel=1e-9 if degree >= 4 else 1e-11, abs=1e-13)
-    # the sweep fed by the cp.async ring (taken from 2^21 paths up by default): forced on here --
+    # the sweep fed by the cp.async ring (taken from 2^19 paths up by default): forced on here --
     # same paths per thread, same order of the sums, so the very same number
     eng.set_int("lsmc_ring", 1)
     try:

@@ -447,3 +447,21 @@ def test_bench_sass_constants_match_the_built_kernel():
     assert fp64 / 4 == pytest.approx(sass["i64"], rel=0.01)
     assert instr / 4 == pytest.approx(sass["instr"], rel=0.04)
     assert reads / 4 == pytest.approx(sass["reads"], rel=0.04)
+
+
+def test_no_cp_async_with_unset_uniform_registers_in_the_built_library():
+    """ptxas 12.9 has encoded hinted cp.async copies of one k_lsmc_persistent instantiation as
+    `LDGSTS [R+UR0], desc[UR1]` with neither uniform register ever written; the GPU reports "an
+    illegal instruction was encountered".  The trigger is a code-generation detail (an unrolled
+    request loop), so the built library is scanned for that addressing form."""
+    import shutil
+    import subprocess
+
+    if shutil.which("cuobjdump") is None or not os.path.exists(_engine.LIB_PATH):
+        pytest.skip("cuobjdump or the built library is not available")
+    sass = subprocess.run(["cuobjdump", "-sass", _engine.LIB_PATH], capture_output=True, text=True,
+                          check=True).stdout
+    copies = [ln for ln in sass.splitlines() if "LDGSTS" in ln]
+    assert len(copies) >= 30                      # the ring kernels are in the library
+    bad = [ln.strip() for ln in copies if re.search(r"\[R\d+\+UR\d+", ln)]
+    assert not bad, bad[:3]

@@ -12,7 +12,9 @@ HESTON = {"v0": 0.04, "kappa": 2.0, "theta": 0.04, "rho": -0.7, "vol_of_vol": 0.
 PARAMS = {"heston": HESTON, "bsm": {"sigma": 0.2},
           "bates": {**HESTON, "lambda": 0.5, "mu_j": -0.1, "sigma_j": 0.15},
           "merton": {"sigma": 0.2, "lambda": 0.5, "mu_j": -0.1, "sigma_j": 0.15},
-          "kou": {"sigma": 0.15, "lambda": 1.0, "p_up": 0.6, "eta1": 10.0, "eta2": 5.0}}
+          "kou": {"sigma": 0.15, "lambda": 1.0, "p_up": 0.6, "eta1": 10.0, "eta2": 5.0},
+          "sabr": {"alpha": 0.5, "beta": 0.8, "rho": -0.6},
+          "sabr_jump": {"alpha": 0.5, "beta": 0.8, "rho": -0.6, "lambda": 0.4, "mu_j": -0.1, "sigma_j": 0.15}}
 kinds = sys.argv[1:] or ["heston", "bsm", "bates", "merton", "kou"]
 n_paths, n_steps = int(os.environ.get("N_PATHS", 1 << 24)), int(os.environ.get("N_STEPS", 252))
 mom = torch.zeros(6, dtype=torch.float64, device=eng.device)

@@ -8,8 +8,10 @@ import numpy as np, torch
 from optpricing_b200 import _engine
 eng = _engine.get_engine()
 n_steps, degree = 50, int(os.environ.get("DEGREE", 3))
+if "LSMC_RING" in os.environ:
+    eng.set_int("lsmc_ring", int(os.environ["LSMC_RING"]))
 mdl = _engine.make_model("bsm", {"sigma": 0.2}, 0.05, 0.01)
-for n_paths in (1 << 18, 1 << 20, 1 << 22):
+for n_paths in [int(x) for x in os.environ.get("SIZES", "262144,1048576,2097152,4194304").split(",")]:
     store, ld = eng.lsmc_store(n_paths, n_steps)
     sim = eng.make_sim(100.0, 1.0, n_paths // 2, n_steps, True, 7, 1)
     eng.lsmc_fill_paths(mdl, sim, store, ld)

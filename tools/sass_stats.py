@@ -8,11 +8,12 @@ Prints, for each matching kernel, the opcode histogram of every loop body
 DFMA DADD DMUL DSETP DMNMX (+ F2F.F64/I2F.F64 conversions listed separately).
 """
 import collections
+import os
 import re
 import subprocess
 import sys
 
-SO = "optpricing_b200/liboptmc.so"
+SO = os.environ.get("OPTMC_LIB", "optpricing_b200/liboptmc.so")
 FP64 = ("DFMA", "DADD", "DMUL", "DSETP", "DMNMX")
 
 
