@@ -196,6 +196,43 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, S 
     // GROUPJ keeps two registers per path: the jump count and the step of the next jump
     // (0xFFFFFFFF: none); the indices are recomputed when a jump group is reached
     uint32_t nxt = 0xFFFFFFFFu;
+    // Path kernels (PENDJ): the NEXT jump of the path is kept ready -- its step and what it does
+    // to the state of the draw and of its partner (the log-jump, or the factor exp(J) for
+    // SABR-jump) -- and every step applies it branch-free (+0 / x1 when it is not due).  The
+    // Philox calls and size transforms of a jump then run once per jump, in a pass shared by
+    // all jumping lanes of the warp for the first one, instead of in a divergent branch at
+    // every step at which some lane of the warp jumps (27 % of the steps at lambda dt = 0.01).
+    constexpr bool PENDJ = SCHEDULED && PER_STEP;
+    uint32_t pend_step = 0xFFFFFFFFu;
+    double pend_a = 0.0, pend_b = 0.0;
+    auto fetch_pending = [&]() {                 // requires k_j < n_j <= SCHED_SLOTS
+        pend_step = sch[0] & 0xFFFFu;
+        sch[0] = (sch[0] >> 16) | (sch[1] << 16);
+        sch[1] = (sch[1] >> 16) | (sch[2] << 16);
+        sch[2] = (sch[2] >> 16) | (sch[3] << 16);
+        sch[3] = (sch[3] >> 16) | 0xFFFF0000u;
+        // sizes: fresh draws for the partner, as in the reference's second pass
+        pend_a = jump_size<KIND, NIMPL>(
+            philox4x32_10(make_uint4(id_lo, id_hi, 0xFFFFFFFDu, 1u | ((uint32_t)k_j << 8)), A.key), c, tab);
+        if constexpr (ANTI)
+            pend_b = jump_size<KIND, NIMPL>(
+                philox4x32_10(make_uint4(id_lo, id_hi, 0xFFFFFFFDu, 2u | ((uint32_t)k_j << 8)), A.key), c,
+                tab);
+        if constexpr (KIND == OPTMC_SABR_JUMP) {      // multiplicative on S (mc_kernels.py:274)
+            pend_a = exp(pend_a);
+            if constexpr (ANTI) pend_b = exp(pend_b);
+        }
+        ++k_j;
+    };
+    auto apply_pending = [&](bool due) {
+        if constexpr (KIND == OPTMC_SABR_JUMP) {
+            sa.x *= due ? pend_a : 1.0;
+            if constexpr (ANTI) sb.x *= due ? pend_b : 1.0;
+        } else {
+            sa.x += due ? pend_a : 0.0;                   // additive in log space (:115,174,323)
+            if constexpr (ANTI) sb.x += due ? pend_b : 0.0;
+        }
+    };
     if constexpr (SCHEDULED) {
         const uint4 e = philox4x32_10(make_uint4(id_lo, id_hi, 0xFFFFFFFFu, 0xFEu), A.key);
         if (__builtin_expect(poisson_maybe(e.x, A.pois_p0_path_bits), 0)) {
@@ -219,6 +256,9 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, S 
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) sch[q] = v[2 * q] | (v[2 * q + 1] << 16);
+                if constexpr (PENDJ) {
+                    if (n_j > 0) fetch_pending();
+                }
             }
         }
     }
@@ -277,6 +317,23 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, S 
                 static_assert(KIND == OPTMC_SABR_JUMP, "multiplicative jumps");
                 sa.x *= ja[T];
                 if constexpr (ANTI) sb.x *= jb[T];
+            }
+        } else if constexpr (PENDJ) {
+            static_assert(!DEFER, "path kernels carry the drift in the state");
+            const bool due = pend_step == (uint32_t)i;
+            apply_pending(due);
+            if (__builtin_expect(due, 0)) {
+                pend_step = 0xFFFFFFFFu;
+                while (k_j < n_j) {                  // the path's next jump; may fall on this step too
+                    fetch_pending();
+                    if (pend_step != (uint32_t)i) break;
+                    apply_pending(true);
+                    pend_step = 0xFFFFFFFFu;
+                }
+            }
+            if (__builtin_expect(n_j > SCHED_SLOTS, 0)) {
+                for (int j = 0; j < n_j; ++j)
+                    if (sched_index(j) == (uint32_t)i) one_jump(j);
             }
         } else if constexpr (SCHEDULED) {
             if (__builtin_expect(n_j != 0, 0)) {
@@ -392,7 +449,9 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, S 
             call += 2;
         }
     } else if constexpr (SCHEDULED) {
-        // one copy of the step body (it carries the inlined jump code): the four words of a
+        // one copy of the step body (it carries the inlined jump code; for the path kernels the
+        // whole-group loops of the diffusion kinds measured the same or 5 % slower, with 768 or
+        // 1024 threads too: profiles/r02_experiments.md): the four words of a
         // call are handed out pair by pair
         uint32_t call = 0;
         uint4 a = make_uint4(0u, 0u, 0u, 0u);
