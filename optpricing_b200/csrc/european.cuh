@@ -143,11 +143,14 @@ __device__ __forceinline__ double2 jumps_slow(uint32_t w, double mu, double p0, 
 // times of a Poisson process given their number are iid uniform, so the per-step counts
 // have exactly the law of the reference's independent Poisson(lambda dt) draws
 // (monte_carlo.py:238-240).  The step loop then needs no Poisson word (the packed
-// Philox layout applies, one-factor path kernels use both normals of a pair) and the
-// divergent jump branch costs one integer compare per step.  Up to eight indices are
-// kept sorted in four registers; a path with more jumps (P = 2e-4 at lambda T = 2)
-// recomputes its indices at every step.  The terminal-only SABR-jump kernel uses the
-// schedule group-wise instead (GROUPJ below).  The host selects SCHED while lambda T <= 2.
+// Philox layout applies, one-factor path kernels use both normals of a pair).  Up to eight
+// indices are kept sorted in four registers, and the path's NEXT jump -- its step and what it
+// does to the draw and to its partner -- is kept ready and applied branch-free at every step;
+// a path with more than eight jumps (P = 2e-4 at lambda T = 2) recomputes its indices at every
+// step.  The host selects SCHED while lambda T <= 2.
+// (Until late in round 2 the terminal-only SABR-jump kernel ran groups of four steps, jump-free
+// groups through a copy of the body without jump code: the same speed for one spot, 15 % slower
+// with three spot scenarios side by side -- profiles/r02_experiments.md.)
 template <int KIND, bool ANTI, int NIMPL, bool PER_STEP, bool SCHED, bool BGEN = false, class S,
           class V, class Sink>
 __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, S &sa, S &sb,
@@ -166,10 +169,6 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, S 
     constexpr bool STEP_JUMPS = JUMPS && !JUMPS_AT_END;
     constexpr bool SCHEDULED = STEP_JUMPS && SCHED;       // pre-drawn jump schedule
     constexpr bool LEGACY = STEP_JUMPS && !SCHED;         // one Poisson word per step
-    // terminal-only kernel with scheduled jumps (SABR-jump): groups of four steps; groups in
-    // which no path of the warp jumps run the packed, unrolled body of plain SABR
-    constexpr bool GROUPJ = SCHEDULED && !PER_STEP;
-    static_assert(!GROUPJ || TWO, "group-wise jumps: one step per Box-Muller pair");
     // terminal-only kernels of the log models defer the deterministic drift
     constexpr bool DEFER = !PER_STEP && !kind_sabr(KIND) && KIND != OPTMC_DUPIRE;
     // one-factor log models with deferred drift: the partner's Brownian sum is minus the
@@ -193,16 +192,12 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, S 
         const uint4 u = philox4x32_10(make_uint4(id_lo, id_hi, 0xFFFFFFFCu, (uint32_t)j), A.key);
         return __umulhi(u.x, (uint32_t)A.n_steps);          // floor(U n_steps)
     };
-    // GROUPJ keeps two registers per path: the jump count and the step of the next jump
-    // (0xFFFFFFFF: none); the indices are recomputed when a jump group is reached
-    uint32_t nxt = 0xFFFFFFFFu;
-    // Path kernels (PENDJ): the NEXT jump of the path is kept ready -- its step and what it does
+    // The NEXT jump of the path is kept ready -- its step and what it does
     // to the state of the draw and of its partner (the log-jump, or the factor exp(J) for
     // SABR-jump) -- and every step applies it branch-free (+0 / x1 when it is not due).  The
     // Philox calls and size transforms of a jump then run once per jump, in a pass shared by
     // all jumping lanes of the warp for the first one, instead of in a divergent branch at
     // every step at which some lane of the warp jumps (27 % of the steps at lambda dt = 0.01).
-    constexpr bool PENDJ = SCHEDULED && PER_STEP;
     uint32_t pend_step = 0xFFFFFFFFu;
     double pend_a = 0.0, pend_b = 0.0;
     auto fetch_pending = [&]() {                 // requires k_j < n_j <= SCHED_SLOTS
@@ -238,9 +233,7 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, S 
         if (__builtin_expect(poisson_maybe(e.x, A.pois_p0_path_bits), 0)) {
             const uint4 x = philox4x32_10(make_uint4(id_lo, id_hi, 0xFFFFFFFFu, 0xFFu), A.key);
             n_j = poisson_slow(e.x, x.x, A.pois_mu_path, A.pois_p0_path);
-            if constexpr (GROUPJ) {
-                for (int j = 0; j < n_j; ++j) nxt = min(nxt, sched_index(j));
-            } else if (n_j <= SCHED_SLOTS) {
+            if (n_j <= SCHED_SLOTS) {
                 // insertion sort of the n_j indices into 8 ascending 16-bit slots (0xFFFF = none)
                 uint32_t v[SCHED_SLOTS];
 #pragma unroll
@@ -256,9 +249,7 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, S 
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) sch[q] = v[2 * q] | (v[2 * q + 1] << 16);
-                if constexpr (PENDJ) {
-                    if (n_j > 0) fetch_pending();
-                }
+                if (n_j > 0) fetch_pending();
             }
         }
     }
@@ -275,51 +266,10 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, S 
             apply_jump<KIND, DEFER>(sb, Jb);
         }
     };
-    // GROUPJ: what the jumps of the four steps from `first` do to S, per step and path -- the
-    // product of exp(J) over the step's jumps (mc_kernels.py:274), 1 where there is none
-    double ja[4], jb[4];
-    auto group_jumps = [&](int first) {
-#pragma unroll
-        for (int t = 0; t < 4; ++t) ja[t] = jb[t] = 1.0;
-        if (nxt < (uint32_t)(first + 4)) {
-            uint32_t later = 0xFFFFFFFFu;
-            for (int j = 0; j < n_j; ++j) {
-                const uint32_t at = sched_index(j);
-                if (at >= (uint32_t)(first + 4)) later = min(later, at);
-                if (at < (uint32_t)first || at >= (uint32_t)(first + 4)) continue;
-                // sizes: fresh draws for the partner, as in the reference's second pass; the
-                // draw index labels the jump
-                const double fa = exp(jump_size<KIND, NIMPL>(
-                    philox4x32_10(make_uint4(id_lo, id_hi, 0xFFFFFFFDu, 1u | ((uint32_t)j << 8)), A.key),
-                    c, tab));
-                double fb = 1.0;
-                if constexpr (ANTI)
-                    fb = exp(jump_size<KIND, NIMPL>(
-                        philox4x32_10(make_uint4(id_lo, id_hi, 0xFFFFFFFDu, 2u | ((uint32_t)j << 8)),
-                                      A.key), c, tab));
-#pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                    if (at == (uint32_t)(first + t)) {
-                        ja[t] *= fa;
-                        jb[t] *= fb;
-                    }
-                }
-            }
-            nxt = later;
-        }
-    };
     // after the diffusion part of step i: scheduled jumps of that step, then the sink.
-    // `slot` (GROUPJ): position of the step in a jump group, -1 in a jump-free group.
-    auto after_step = [&](int i, auto slot) {
-        if constexpr (GROUPJ) {
-            constexpr int T = decltype(slot)::value;
-            if constexpr (T >= 0) {
-                static_assert(KIND == OPTMC_SABR_JUMP, "multiplicative jumps");
-                sa.x *= ja[T];
-                if constexpr (ANTI) sb.x *= jb[T];
-            }
-        } else if constexpr (PENDJ) {
-            static_assert(!DEFER, "path kernels carry the drift in the state");
+    auto after_step = [&](int i) {
+        if constexpr (SCHEDULED) {
+            static_assert(!DEFER, "kernels with jumps inside the loop carry the drift in the state");
             const bool due = pend_step == (uint32_t)i;
             apply_pending(due);
             if (__builtin_expect(due, 0)) {
@@ -335,21 +285,6 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, S 
                 for (int j = 0; j < n_j; ++j)
                     if (sched_index(j) == (uint32_t)i) one_jump(j);
             }
-        } else if constexpr (SCHEDULED) {
-            if (__builtin_expect(n_j != 0, 0)) {
-                if (n_j <= SCHED_SLOTS) {
-                    while ((sch[0] & 0xFFFFu) == (uint32_t)i) {
-                        one_jump(k_j++);
-                        sch[0] = (sch[0] >> 16) | (sch[1] << 16);
-                        sch[1] = (sch[1] >> 16) | (sch[2] << 16);
-                        sch[2] = (sch[2] >> 16) | (sch[3] << 16);
-                        sch[3] = (sch[3] >> 16) | 0xFFFF0000u;
-                    }
-                } else {
-                    for (int j = 0; j < n_j; ++j)
-                        if (sched_index(j) == (uint32_t)i) one_jump(j);
-                }
-            }
         }
         if constexpr (PER_STEP) sink(i, sa, sb);
     };
@@ -357,7 +292,7 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, S 
     // One Box-Muller pair (two Philox words, philox.cuh) and the SPC steps it feeds,
     // starting at step i.
     // `whole` (a std::bool_constant): the caller knows that step i + 1 exists too
-    auto advance = [&](uint32_t wa, uint32_t wb, int i, auto whole, auto slot) {
+    auto advance = [&](uint32_t wa, uint32_t wb, int i, auto whole) {
         // (z1, z2): two-factor models -- the mixed, scaled increments (dW_S, xi-weighted
         // dW_v); one-factor models -- sqrt(dt) N(0,1) for this step and the next.
         // Heston / Bates on the hand-written maths: the parts of the pair, one root per path
@@ -366,7 +301,7 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, S 
             normal_parts_fast<true>(wa, wb, L, t1, t2, tab);
             step_heston_parts<DEFER>(sa, L, t1, t2, c);
             if constexpr (ANTI) step_heston_parts<DEFER>(sb, L, -t1, -t2, c);
-            if constexpr (!LEGACY) after_step(i, slot);
+            if constexpr (!LEGACY) after_step(i);
             return;
         }
         double z1, z2;
@@ -386,69 +321,26 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, S 
         if constexpr (TWO) {
             step_diffusion<KIND, DEFER, LOGV>(sa, z1, z2, c, tab, i);
             if constexpr (ANTI) step_diffusion<KIND, DEFER, LOGV>(sb, -z1, -z2, c, tab, i);
-            if constexpr (!LEGACY) after_step(i, slot);
+            if constexpr (!LEGACY) after_step(i);
         } else {
             step_diffusion<KIND, DEFER>(sa, z1, 0.0, c, tab, i);
             if constexpr (ANTI && !MIRROR) step_diffusion<KIND, DEFER>(sb, -z1, 0.0, c, tab, i);
-            if constexpr (!LEGACY) after_step(i, slot);
+            if constexpr (!LEGACY) after_step(i);
             if constexpr (SPC == 2) {
                 if (decltype(whole)::value || i + 1 < A.n_steps) {
                     step_diffusion<KIND, DEFER>(sa, z2, 0.0, c, tab, i + 1);
                     if constexpr (ANTI && !MIRROR)
                         step_diffusion<KIND, DEFER>(sb, -z2, 0.0, c, tab, i + 1);
-                    after_step(i + 1, slot);
+                    after_step(i + 1);
                 }
             }
         }
     };
     constexpr std::true_type WHOLE{};
     constexpr std::false_type RAGGED{};
-    constexpr std::integral_constant<int, -1> NOSLOT{};
     // Without a Poisson word per step all 128 bits of a Philox call are used: call g feeds
     // pairs 2g = (x, y) and 2g + 1 = (z, w), see philox_pair_words.
-    if constexpr (GROUPJ) {
-        // The warp finds the first group of four steps in which one of its paths jumps (one
-        // min-reduction), runs the groups before it through the jump-free body -- a loop with a
-        // warp-uniform trip count and no jump code -- and that one group through a second copy
-        // of the body in which every step is followed by its jump factor; the warp stays in
-        // lockstep throughout.
-        const unsigned lanes = __activemask();      // the lanes of this warp that simulate a draw
-        uint32_t call = 0;
-        int i = 0;
-        while (i < A.n_steps) {
-            const uint32_t hit_group = __reduce_min_sync(lanes, nxt >> 2);
-            const int stop = (int)min((uint64_t)A.n_steps, (uint64_t)hit_group * 4u);
-            for (; i < stop; i += 4, call += 2) {
-                const uint4 a = philox4x32_10(make_uint4(id_lo, id_hi, call, 0u), A.key);
-                advance(a.x, a.y, i, RAGGED, NOSLOT);
-                if (i + 1 < A.n_steps) {
-                    advance(a.z, a.w, i + 1, RAGGED, NOSLOT);
-                    if (i + 2 < A.n_steps) {
-                        const uint4 b = philox4x32_10(make_uint4(id_lo, id_hi, call + 1u, 0u), A.key);
-                        advance(b.x, b.y, i + 2, RAGGED, NOSLOT);
-                        if (i + 3 < A.n_steps) advance(b.z, b.w, i + 3, RAGGED, NOSLOT);
-                    }
-                }
-            }
-            if (i >= A.n_steps) break;
-            group_jumps(i);
-            {
-                const uint4 a = philox4x32_10(make_uint4(id_lo, id_hi, call, 0u), A.key);
-                advance(a.x, a.y, i, RAGGED, std::integral_constant<int, 0>{});
-                if (i + 1 < A.n_steps) {
-                    advance(a.z, a.w, i + 1, RAGGED, std::integral_constant<int, 1>{});
-                    if (i + 2 < A.n_steps) {
-                        const uint4 b = philox4x32_10(make_uint4(id_lo, id_hi, call + 1u, 0u), A.key);
-                        advance(b.x, b.y, i + 2, RAGGED, std::integral_constant<int, 2>{});
-                        if (i + 3 < A.n_steps)
-                            advance(b.z, b.w, i + 3, RAGGED, std::integral_constant<int, 3>{});
-                    }
-                }
-            }
-            i += 4;
-            call += 2;
-        }
-    } else if constexpr (SCHEDULED) {
+    if constexpr (SCHEDULED && PER_STEP) {
         // one copy of the step body (it carries the inlined jump code; for the path kernels the
         // whole-group loops of the diffusion kinds measured the same or 5 % slower, with 768 or
         // 1024 threads too: profiles/r02_experiments.md): the four words of a
@@ -465,7 +357,7 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, S 
             } else {
                 wa = a.z; wb = a.w;
             }
-            advance(wa, wb, i, RAGGED, NOSLOT);
+            advance(wa, wb, i, RAGGED);
         }
     } else if constexpr (!LEGACY && TWO) {
         // Whole calls (two steps) without a bounds test: with the branch-free logarithm the
@@ -477,12 +369,12 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, S 
         OPTMC_UNROLL_STEPS
         for (; i + 2 <= A.n_steps; i += 2, ++call) {
             const uint4 a = philox4x32_10(make_uint4(id_lo, id_hi, call, 0u), A.key);
-            advance(a.x, a.y, i, RAGGED, NOSLOT);
-            advance(a.z, a.w, i + 1, RAGGED, NOSLOT);
+            advance(a.x, a.y, i, RAGGED);
+            advance(a.z, a.w, i + 1, RAGGED);
         }
         if (i < A.n_steps) {
             const uint4 a = philox4x32_10(make_uint4(id_lo, id_hi, call, 0u), A.key);
-            advance(a.x, a.y, i, RAGGED, NOSLOT);
+            advance(a.x, a.y, i, RAGGED);
         }
     } else if constexpr (!LEGACY) {
         // one-factor models: whole groups of four steps without a single bounds test, then
@@ -493,19 +385,19 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, S 
         OPTMC_UNROLL_STEPS
         for (; i + GS <= A.n_steps; i += GS, ++call) {
             const uint4 a = philox4x32_10(make_uint4(id_lo, id_hi, call, 0u), A.key);
-            advance(a.x, a.y, i, WHOLE, NOSLOT);
-            advance(a.z, a.w, i + SPC, WHOLE, NOSLOT);
+            advance(a.x, a.y, i, WHOLE);
+            advance(a.z, a.w, i + SPC, WHOLE);
         }
         if (i < A.n_steps) {
             const uint4 a = philox4x32_10(make_uint4(id_lo, id_hi, call, 0u), A.key);
-            advance(a.x, a.y, i, RAGGED, NOSLOT);
-            if (i + SPC < A.n_steps) advance(a.z, a.w, i + SPC, RAGGED, NOSLOT);
+            advance(a.x, a.y, i, RAGGED);
+            if (i + SPC < A.n_steps) advance(a.z, a.w, i + SPC, RAGGED);
         }
     } else {
         OPTMC_UNROLL_STEPS
         for (int i = 0; i < A.n_steps; ++i) {
             const uint4 w = philox4x32_10(make_uint4(id_lo, id_hi, (uint32_t)i, 0u), A.key);
-            advance(w.x, w.y, i, RAGGED, NOSLOT);
+            advance(w.x, w.y, i, RAGGED);
             if (__builtin_expect(poisson_maybe(w.w, A.pois_p0_bits[0]), 0)) {
                 double2 J = jumps_slow<KIND, ANTI, NIMPL>(w.w, A.pois_mu[0], A.pois_p0[0], A.key,
                                                           id_lo, id_hi, (uint32_t)i, c, tab);
@@ -636,14 +528,14 @@ k_european(const EuroArgs A) {
 // models (64) -- whose warps share 160 - 224 KB of (nearly) conflict-free tables in dynamic
 // shared memory.
 #ifndef OPTMC_SJ_THREADS
-#define OPTMC_SJ_THREADS 512
+#define OPTMC_SJ_THREADS 640
 #endif
 __host__ __device__ constexpr int wide_threads(int kind, bool sched = false) {
 #ifdef OPTMC_WIDE_THREADS
     return OPTMC_WIDE_THREADS;
 #else
-    // (SABR-jump on the jump schedule keeps eight jump factors in its jump groups: 512
-    // threads = 128 registers; 15.3 ms at 2^24 x 252 against 15.8 with 640, 16.0 with 768)
+    // (SABR-jump on the jump schedule -- the schedule and the pending jump on top of the SABR
+    // state: 15.0 ms at 2^24 x 252 with 640 threads, 15.4 with 512, 15.3 with 768)
     return kind == OPTMC_SABR_JUMP && sched ? OPTMC_SJ_THREADS : kind_two_factor(kind) ? 768 : 1024;
 #endif
 }
@@ -688,9 +580,13 @@ __global__ void __launch_bounds__(THREADS, 1) k_european_wide(const EuroArgs A) 
 // repeated.  Same draws, same arithmetic per scenario as k_european_wide: the scenario prices
 // equal separate simulations with the bumped spot to rounding.
 // partials: [NS][gridDim.x][NPART], the layout k_finish_sweep adds up.
-// 512 threads = 128 registers (three spot states for path and partner); on the jump schedule,
-// whose jump groups keep eight jump factors more, 384 threads = 168 registers
-__host__ __device__ constexpr int scen_threads(bool sched) { return sched ? 384 : 512; }
+// 512 threads = 128 registers (three spot states for path and partner); on the jump schedule
+// (schedule + pending jump in registers) 384 threads = 168 registers: C5 45.1 ms, 448 threads
+// 51.0, 512 threads 45.3 (both spill)
+#ifndef OPTMC_SCEN_SCHED_THREADS
+#define OPTMC_SCEN_SCHED_THREADS 384
+#endif
+__host__ __device__ constexpr int scen_threads(bool sched) { return sched ? OPTMC_SCEN_SCHED_THREADS : 512; }
 template <int KIND, bool ANTI, int NS, bool SCHED = false, bool BGEN = false>
 __global__ void __launch_bounds__(scen_threads(SCHED), 1) k_european_scen(const EuroArgs A) {
     static_assert(kind_sabr(KIND), "spot scenarios share the vol path: SABR kinds");
