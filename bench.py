@@ -66,7 +66,7 @@ FLOPS_PER_PATH_STEP = {"heston": 28.0, "bsm": 6.0}
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
 # `ncu --set full` captures summarised in profiles/ (r02_ncu_heston_summary.md,
 # r02_ncu_lsmc_summary.md).  The European kernel reads its tables and code only.
-NCU_TRAFFIC_BYTES = {"heston_c2": 50_944 + 0, "lsmc_c4_induction": 1_742_771_000 + 111_612_000,
+NCU_TRAFFIC_BYTES = {"heston_c2": 48_896 + 0, "lsmc_c4_induction": 1_778_023_000 + 178_389_000,
                      "lsmc_c4_fill": 1_677_721_600}
 
 HESTON = {"v0": 0.04, "kappa": 2.0, "theta": 0.04, "rho": -0.7, "vol_of_vol": 0.5}
