@@ -529,11 +529,47 @@ def test_philox_path_store_law(kind, jump_schedule):
     assert lr.var() == pytest.approx(lr_ref.var(), rel=0.05)
 
 
+@pytest.mark.parametrize("kind", ("merton", "kou", "bates", "sabr_jump"))
+def test_path_kernels_many_jumps_per_step_schedule_against_per_step_poisson(eng, kind):
+    """Path kernels at lambda T = 2 on THREE dates: most paths jump, many twice on the same date
+    (the pending jump is refilled and applied again within the step), and a few hundred of the
+    2^20 paths have more than the eight jumps the schedule keeps in registers (the fallback that
+    recomputes the indices).  The schedule and the per-step Poisson sampler are two samplers of
+    one law: every date's mean, the second moment of every date's increment and the terminal put
+    agree within 4.5 combined standard errors."""
+    params = dict(MODELS[kind]().params)
+    params["lambda"] = 2.0
+    model = MODELS[kind](params=params)
+    n, m = 1 << 20, 3
+    opt = ob.Option(strike=105.0, maturity=1.0, option_type=ob.OptionType.PUT)
+    out = {}
+    try:
+        for mode in (1, 0):
+            eng.set_int("jump_schedule", mode)
+            t = ob.AmericanMonteCarloTechnique(n_paths=n, n_steps=m, seed=23)
+            out[mode] = np.asarray(t._simulate_full_sde_paths(opt, STQ, model, RT))
+    finally:
+        eng.set_int("jump_schedule", 1)
+    half = n // 2
+
+    def pair_stat(x):                       # mean and standard error over antithetic pairs
+        pm = 0.5 * (x[:half] + x[half:])
+        return pm.mean(), pm.std(ddof=1) / math.sqrt(half)
+
+    for i in (1, 2, 3):
+        # (squared increments, not log-returns: a SABR path may sit at its absorbing zero)
+        for f in (lambda p: p[:, i], lambda p: ((p[:, i] - p[:, i - 1]) / 100.0) ** 2):
+            (a, ea), (b, eb) = pair_stat(f(out[1])), pair_stat(f(out[0]))
+            assert abs(a - b) < 4.5 * math.hypot(ea, eb), (kind, i, a, b, ea, eb)
+    (a, ea), (b, eb) = (pair_stat(np.maximum(105.0 - out[k][:, m], 0.0)) for k in (1, 0))
+    assert abs(a - b) < 4.5 * math.hypot(ea, eb), (kind, a, b)
+
+
 @pytest.mark.parametrize("n_steps,antithetic,lam", [(37, True, 1.5), (64, False, 0.4), (3, True, 0.9),
                                                     (50, True, 0.05)])
 def test_european_sabr_jump_schedule_matches_per_step_poisson(eng, n_steps, antithetic, lam):
-    """European SABR-jump (jumps act on S inside the step loop): the group-wise jump schedule
-    and the per-step Poisson draw are two samplers of one law -- prices, second moments and the
+    """European SABR-jump (jumps act on S inside the step loop): the jump schedule (next jump kept
+    ready, applied branch-free) and the per-step Poisson draw are two samplers of one law -- prices, second moments and the
     martingale mean of S_T agree within 4 combined standard errors; ragged last groups, no
     antithetic partner, many and few jumps."""
     params = dict(ob.SABRJumpModel().params)
