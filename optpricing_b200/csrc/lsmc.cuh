@@ -385,6 +385,7 @@ struct LsmcPersistArgs {
     int rank, world;
     uint32_t peer_nonce;       // per distributed call, identical on every rank
     uint4 *peer_rank_slots[OPTMC_MAX_PEERS];
+    uint4 *local_rank_slots;   // = peer_rank_slots[rank]
     unsigned int *error;       // set to 1 if an exchange times out
     double *gram;              // [n_steps][OPTMC_LSMC_GRAM], written by block 0
     unsigned long long *timing;   // optional [n_steps + 1][4] clock64 stamps of block 0 (SM cycles)
@@ -801,7 +802,7 @@ k_lsmc_persistent(const LsmcPersistArgs A) {
                 // trip, not W), then entry e is added over the ranks in rank order
                 if (threadIdx.x < OPTMC_LSMC_GRAM * A.world) {
                     const int r = threadIdx.x / OPTMC_LSMC_GRAM, e = threadIdx.x % OPTMC_LSMC_GRAM;
-                    const uint4 *slot = A.peer_rank_slots[A.rank] + base + (size_t)r * LSMC_P_STRIDE + e;
+                    const uint4 *slot = A.local_rank_slots + base + (size_t)r * LSMC_P_STRIDE + e;
                     double x = 0.0;
                     if (!ll_wait(slot, ptag, ll_peek(slot), x, timed_out)) timed_out = true;
                     peer_vals[threadIdx.x] = x;
@@ -918,6 +919,8 @@ struct PeerReduceArgs {
     uint32_t tag;                             // per call, identical on every rank, never 0
     size_t euro_off;                          // offset (uint4) of the European region in a buffer
     uint4 *peer_rank_slots[OPTMC_MAX_PEERS];
+    uint4 *local_slots;                       // = peer_rank_slots[rank] (a dynamic index into the
+                                              // parameter array would cost a local-memory copy of it)
     unsigned int *error;
 };
 
@@ -926,15 +929,27 @@ __global__ void __launch_bounds__(256) k_peer_allreduce(const PeerReduceArgs A) 
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.n; i += gridDim.x * blockDim.x) {
         const size_t base = A.euro_off + ((size_t)(A.tag & 1u) * A.world) * PEER_AR_MAX + i;
         const double v = A.vals[i];
-        for (int r = 0; r < A.world; ++r)
-            ll_store_sys(A.peer_rank_slots[r] + base + (size_t)A.rank * PEER_AR_MAX, v, A.tag);
+        // (loops over the peers unrolled with static indices: the pointer array stays in the
+        // constant bank instead of a local-memory copy)
+        const uint4 *mine = A.local_slots + base;
+#pragma unroll
+        for (int r = 0; r < OPTMC_MAX_PEERS; ++r)
+            if (r < A.world)
+                ll_store_sys(A.peer_rank_slots[r] + base + (size_t)A.rank * PEER_AR_MAX, v, A.tag);
+        // first looks at the W slots in flight together: one L2 round trip when the values are
+        // there, not W; then the sum in rank order
+        uint4 w[OPTMC_MAX_PEERS];
+#pragma unroll
+        for (int r = 0; r < OPTMC_MAX_PEERS; ++r)
+            if (r < A.world) w[r] = ll_peek(mine + (size_t)r * PEER_AR_MAX);
         double sum = 0.0;
-        const uint4 *mine = A.peer_rank_slots[A.rank] + base;
-        for (int r = 0; r < A.world; ++r) {
-            double x = 0.0;
-            const uint4 *slot = mine + (size_t)r * PEER_AR_MAX;
-            if (!ll_wait(slot, A.tag, ll_peek(slot), x, bad)) bad = true;
-            sum += x;
+#pragma unroll
+        for (int r = 0; r < OPTMC_MAX_PEERS; ++r) {
+            if (r < A.world) {
+                double x = 0.0;
+                if (!ll_wait(mine + (size_t)r * PEER_AR_MAX, A.tag, w[r], x, bad)) bad = true;
+                sum += x;
+            }
         }
         A.vals[i] = bad ? ll_poison() : sum;
     }

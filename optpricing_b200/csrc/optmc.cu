@@ -1174,6 +1174,7 @@ static int lsmc_persistent(optmc_ctx *ctx, const double *store_dev, int64_t ld, 
     A.rank = joint ? ctx->peer_rank : 0;
     A.world = joint ? ctx->peer_world : 1;
     for (int r = 0; r < OPTMC_MAX_PEERS; ++r) A.peer_rank_slots[r] = ctx->peer_rank_slots[r];
+    A.local_rank_slots = ctx->peer_rank_slots[ctx->peer_rank];
     if (joint) {
         ctx->peer_nonce = (ctx->peer_nonce + 1) & 0xFFFFFu;
         if (ctx->peer_nonce == 0) ctx->peer_nonce = 2;       // keeps the call parity alternating
@@ -1286,6 +1287,7 @@ static int peer_allreduce_launch(optmc_ctx *ctx, double *vals_dev, int32_t n, cu
     A.tag = ctx->euro_peer_nonce;
     A.euro_off = RANK_SLOTS_LSMC;
     for (int r = 0; r < OPTMC_MAX_PEERS; ++r) A.peer_rank_slots[r] = ctx->peer_rank_slots[r];
+    A.local_slots = ctx->peer_rank_slots[ctx->peer_rank];
     A.error = ctx->ticket + 9;
     k_peer_allreduce<<<(n + 255) / 256, 256, 0, st>>>(A);
     ctx->launches++;
