@@ -650,6 +650,14 @@ __global__ void __launch_bounds__(256) k_finish_moments(const double *partials, 
     }
 }
 
+// max(x, 0) on the integer pipe: both words AND-ed with the complement of the sign (one shift,
+// two logic instructions, nothing on the fp64 pipe; written as a comparison the compiler emits
+// fmax()'s NaN-quieting sequence).  -0 and negatives give +0; a NaN stays a NaN.
+__device__ __forceinline__ double relu_bits(double x) {
+    const int hi = __double2hiint(x), keep = ~(hi >> 31);
+    return __hiloint2double(hi & keep, __double2loint(x) & keep);
+}
+
 // Strike sweep over stored terminal spots: block (x = path chunk, y = contract).
 constexpr int SWEEP_MAX = 64;
 struct SweepArgs {
@@ -671,13 +679,18 @@ __global__ void __launch_bounds__(256) k_payoff_sweep(const SweepArgs A) {
     constexpr int NACC = 3 * SWEEP_G + 2;
     __shared__ double scratch[NACC * 32];
     const int c0 = blockIdx.y * SWEEP_G;
-    double K[SWEEP_G], sgn[SWEEP_G];
+    // payoff = max(sgn (S - K), 0) with sgn = +-1 as ONE fused multiply-add per spot: sgn S is
+    // exact, so the single rounding is that of S - K or K - S -- the same bits as the two-step
+    // form, and the maximum on the integer pipe (relu_bits): 31 instructions per pair and contract
+    // with fmax(sgn (S - K), 0) before, 13 now.
+    double nsK[SWEEP_G], sgn[SWEEP_G];
 #pragma unroll
     for (int j = 0; j < SWEEP_G; ++j) {
         const int cidx = min(c0 + j, A.n_contracts - 1);
-        K[j] = A.strikes[cidx];
-        sgn[j] = A.is_call[cidx] ? 1.0 : -1.0;          // payoff = max(sgn (S - K), 0)
+        sgn[j] = A.is_call[cidx] ? 1.0 : -1.0;
+        nsK[j] = -sgn[j] * A.strikes[cidx];
     }
+    const double half = A.antithetic ? 0.5 : 1.0;
     double acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
@@ -688,14 +701,22 @@ __global__ void __launch_bounds__(256) k_payoff_sweep(const SweepArgs A) {
         const double ctl = A.antithetic ? 0.5 * (ST + STb) : ST;
         acc[3 * SWEEP_G] += ctl;
         acc[3 * SWEEP_G + 1] = fma(ctl, ctl, acc[3 * SWEEP_G + 1]);
+        // sums of q = pay + pay_partner (q = pay without antithetic partners); the pair mean
+        // 0.5 q enters the moments through exact scalings by 0.5 and 0.25 after the loop
 #pragma unroll
         for (int j = 0; j < SWEEP_G; ++j) {
-            double pay = fmax(sgn[j] * (ST - K[j]), 0.0);
-            if (A.antithetic) pay = 0.5 * (pay + fmax(sgn[j] * (STb - K[j]), 0.0));
-            acc[3 * j] += pay;
-            acc[3 * j + 1] = fma(pay, pay, acc[3 * j + 1]);
-            acc[3 * j + 2] = fma(pay, ctl, acc[3 * j + 2]);
+            double q = relu_bits(fma(sgn[j], ST, nsK[j]));
+            if (A.antithetic) q += relu_bits(fma(sgn[j], STb, nsK[j]));
+            acc[3 * j] += q;
+            acc[3 * j + 1] = fma(q, q, acc[3 * j + 1]);
+            acc[3 * j + 2] = fma(q, ctl, acc[3 * j + 2]);
         }
+    }
+#pragma unroll
+    for (int j = 0; j < SWEEP_G; ++j) {
+        acc[3 * j] *= half;
+        acc[3 * j + 1] *= half * half;
+        acc[3 * j + 2] *= half;
     }
     block_sum<NACC>(acc, scratch);
     if (threadIdx.x == 0) {
