@@ -665,7 +665,9 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
           sweep over the (W, J) stored by the same launch;
         * SABR kinds: ONE simulation carrying the spot scenarios (up, base, down) side by side
           for price, delta and gamma; vega is NaN as in the reference (no ``sigma``); rho re-prices;
-        * anything else (theta, numpy mode, fp32, single-step models): the mixin's re-pricings.
+        * theta: GBM from the Brownian sums the same launch stores (a (drift, sigma) scenario of
+          the vega sweep); every other model re-prices (the whole step depends on T);
+        * anything else (numpy mode, fp32, single-step models): the mixin's re-pricings.
         The generator advances once, as for one ``price`` call.
         """
         greeks = tuple(greeks)
@@ -709,7 +711,9 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
             _, cnt = shard_draws(num_draws, rank, world)
             want_vega = "vega" in greeks and "sigma" in model.params
             one_sim_vega = want_vega and kind in self._ONE_FACTOR_KINDS
-            aux = eng.buffer("aux_wj", 3 * cnt) if one_sim_vega else None
+            one_sim_theta = ("theta" in greeks and kind == "bsm" and self.precision == "fp64" and not kw
+                             and self._theta_steps_ok(T, 1e-5))
+            aux = eng.buffer("aux_wj", 3 * cnt) if (one_sim_vega or one_sim_theta) else None
             self.rng.bit_generator.state = state0
             with crn(self.rng), self._steps_for(T) as steps:
                 mom, _, seed = self._sweep(model, S0, r, q, T, strikes, [1 if call else 0] * 5,
@@ -734,6 +738,9 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
                 if one_sim_vega:
                     out["vega"] = self._vega_from_aux(eng, aux, cnt, kind, model, S0, K, T, r, q,
                                                       call, h_vega, steps, all_reduce)
+                if one_sim_theta:
+                    out["theta"] = self._theta_from_aux(eng, aux, cnt, model, S0, K, T, q, rate, call,
+                                                        1e-5, steps, all_reduce)
             if "vega" in greeks and "sigma" not in model.params:
                 out["vega"] = float("nan")
             via_mixin([g for g in greeks if g not in out])
@@ -772,6 +779,72 @@ class MonteCarloTechnique(BaseTechnique, GreekMixin, IVMixin):
             use_cv = self.control_variate and "cv_price" in st and math.isfinite(c_mean)
             prices.append(st["cv_price"] if use_cv else st["price"])
         return float((prices[0] - prices[1]) / (2 * h))
+
+    def _theta_steps_ok(self, T: float, h: float) -> bool:
+        """The maturity bumps keep the step count (always, unless ``steps_per_year`` rounds
+        T + h or T - h to another grid)."""
+        if self.steps_per_year is None:
+            return True
+        n = [max(1, int(round(self.steps_per_year * t))) for t in (T, T + h, max(T - h, 1e-12))]
+        return n[0] == n[1] == n[2]
+
+    def _theta_from_aux(self, eng, aux, cnt, model, S0, K, T, q, rate, call, h, steps, all_reduce):
+        """
+        GreekMixin.theta (greek_mixin.py:175-218) for the GBM kind from the Brownian sums W of
+        ONE simulation: on the same draws a maturity T' has dt' = T'/n, so
+        log S_T' = log S_0 + n drift dt' + sigma sqrt(T'/T) W -- a (drift, sigma) scenario of the
+        sweep that computes vega.  (Jump kinds: the per-path jump count depends on lambda T', so
+        their bumped prices are not functions of the stored (W, J); they re-price.)
+        """
+        p = model.params
+        sig = p["sigma"]
+        Ts = [T + h, max(T - h, 1e-12)]
+        rs = [rate.get_rate(t) for t in Ts]
+        a0 = [math.log(S0) + steps * ((rr - q - 0.5 * sig * sig) * (t / steps)) for t, rr in zip(Ts, rs)]
+        dev = eng.sigma_sweep(aux, cnt, self.antithetic, a0, [sig * math.sqrt(t / T) for t in Ts],
+                              [float(K)] * 2, [1 if call else 0] * 2)
+        if all_reduce is not None:
+            all_reduce(dev[: 2 * _engine.NMOM])
+        mom = eng.read(dev, 2 * _engine.NMOM).reshape(2, _engine.NMOM)
+        prices = []
+        for row, t, rr in zip(mom, Ts, rs):
+            c_mean = control_mean("bsm", p, S0, rr, q, t, steps)
+            st = summarize(row, rr, t, c_mean)
+            use_cv = self.control_variate and "cv_price" in st and math.isfinite(c_mean)
+            prices.append(st["cv_price"] if use_cv else st["price"])
+        return float((prices[1] - prices[0]) / (2 * h))
+
+    @_engine.serialized
+    def theta(self, option, stock, model, rate, h: float = 1e-5, **kw: Any) -> float:
+        """
+        GreekMixin.theta (greek_mixin.py:175-218): central difference in the maturity on common
+        random numbers.  GBM on the device RNG: both bumped prices are read off ONE simulation
+        that stores the Brownian sums (``_theta_from_aux``); every other model re-prices twice,
+        as the reference does.
+        """
+        kind = model_kind(model) if self._philox_sde(model) else None
+        T = option.maturity
+        if (kind != "bsm" or self.precision != "fp64" or kw or T <= 0
+                or not self._theta_steps_ok(T, h)):
+            return super().theta(option, stock, model, rate, h, **kw)
+        eng = _engine.get_engine()
+        S0, K = stock.spot, option.strike
+        r, q = rate.get_rate(T), stock.dividend
+        call = _is_call(option)
+        num_draws = self.n_paths // 2 if self.antithetic else self.n_paths
+        with crn(self.rng):                       # greeks do not advance the stream
+            seed = int(self.rng.integers(0, 2**63 - 1, dtype=np.int64))
+        mdl = _engine.make_model(kind, model.params, r, q)
+        rank, world, all_reduce = self._group()
+        off, cnt = shard_draws(num_draws, rank, world)
+        with self._steps_for(T) as steps:
+            sim = eng.make_sim(float(S0), T, num_draws, steps, self.antithetic, seed,
+                               _engine.CORR_REFERENCE_EUROPEAN, off, cnt)
+            aux = eng.buffer("aux_wj", 3 * cnt)
+            eng.european_async(mdl, sim, [float(K)], [1 if call else 0],
+                               eng.buffer("moments", _engine.NMOM), aux=aux)
+            return self._theta_from_aux(eng, aux, cnt, model, S0, K, T, q, rate, call, h, steps,
+                                        all_reduce)
 
     # ------------------------------------------- single-step models (SURVEY 8 f3)
     def _device_single_step(self, model) -> bool:

@@ -757,6 +757,40 @@ def test_price_with_greeks_is_one_simulation_and_equals_the_mixin(kind, cv):
     assert a.rng.bit_generator.state == b.rng.bit_generator.state
 
 
+@pytest.mark.parametrize("cv", (False, True))
+@pytest.mark.parametrize("anti", (True, False))
+def test_bsm_theta_from_one_simulation_equals_the_mixin(anti, cv):
+    """GBM theta: both maturity-bumped prices read off the Brownian sums of ONE simulation
+    (a (drift, sigma) scenario of the vega sweep) equal GreekMixin.theta's two re-pricings on
+    common random numbers; price_with_greeks delivers it from the same single simulation; a
+    jump model falls back to the re-pricings."""
+    from optpricing_b200.techniques.base import GreekMixin
+    model = ob.BSMModel({"sigma": 0.25})
+    mk = lambda **k: ob.MonteCarloTechnique(n_paths=1 << 18, n_steps=24, seed=5, antithetic=anti,  # noqa: E731
+                                            control_variate=cv, **k)
+    a, b = mk(), mk()
+    eng = _engine.get_engine()
+    sims0 = eng.n_simulations
+    got = a.theta(PUT, STQ, model, RT)
+    assert eng.n_simulations - sims0 == 1
+    want = GreekMixin.theta(b, PUT, STQ, model, RT)
+    assert got == pytest.approx(want, rel=1e-5)
+    assert a.rng.bit_generator.state == b.rng.bit_generator.state      # greeks do not advance it
+    sims0 = eng.n_simulations
+    res = a.price_with_greeks(CALL, STQ, model, RT, greeks=("delta", "vega", "theta"))
+    assert eng.n_simulations - sims0 == 1
+    assert res.greeks["theta"] == pytest.approx(GreekMixin.theta(b, CALL, STQ, model, RT), rel=1e-5)
+    # the time grid follows the maturity: same step count for T +- h, still one simulation
+    c, d = mk(steps_per_year=24), mk(steps_per_year=24)
+    assert c.theta(PUT, STQ, model, RT) == pytest.approx(GreekMixin.theta(d, PUT, STQ, model, RT), rel=1e-5)
+    # jump kinds re-price (their jump counts depend on lambda T)
+    e, f = mk(), mk()
+    sims0 = eng.n_simulations
+    t_m = e.theta(PUT, STQ, ob.MertonJumpModel(), RT)
+    assert eng.n_simulations - sims0 == 2
+    assert t_m == pytest.approx(GreekMixin.theta(f, PUT, STQ, ob.MertonJumpModel(), RT), rel=1e-9)
+
+
 # ------------------------------------------------------------------ BASELINE.json configs at full size
 def test_config1_bsm_100k_x_252(price_goldens):
     """C1: BSM European call, 100k paths x 252 steps, antithetic (the reference's CPU case:
