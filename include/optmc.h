@@ -396,12 +396,18 @@ int optmc_fp64_peak(optmc_ctx *ctx, int64_t iters, double *fma_per_sec, double *
    and European SABR-jump, optmc_european*: 1 = draw the path's Poisson(lambda T) count
    and its jump steps once, default while lambda T <= 2; 0 = one Poisson(lambda dt) draw
    per step; two samplers of the same law), "fed_stream" (optmc_fed_async: 1 = one thread streams one row, default;
-   0 = the shared-memory tiled kernel). */
+   0 = the shared-memory tiled kernel), "euro_wide" (European kernels on lane-replicated tables,
+   one block per SM: 1 = always, 0 = never, default: by job size), "lsmc_ring" (sweep of the
+   persistent Longstaff-Schwartz kernel fed by a cp.async ring in shared memory: 0 = never,
+   1 = always, 2 = from 2^19 paths per GPU, default), "lsmc_timing_all" (diagnostics: every
+   block stamps, see "lsmc_timing"). */
 int optmc_set_int(optmc_ctx *ctx, const char *key, int64_t value);
 
 /* Pointer-valued options: "lsmc_timing" (diagnostics: device memory for
    (n_steps + 1) * 4 uint64 that block 0 of the persistent Longstaff-Schwartz kernel
-   fills with clock64 stamps per date; NULL = off -- tools/lsmc_phases.py). */
+   fills with clock64 stamps per date; NULL = off -- tools/lsmc_phases.py; with
+   "lsmc_timing_all" = 1 every block stamps and the buffer is gridDim.x times as large,
+   [block][n_steps + 1][4] -- tools/lsmc_block_phases.py). */
 int optmc_set_ptr(optmc_ctx *ctx, const char *key, void *value);
 
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
