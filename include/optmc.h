@@ -396,8 +396,8 @@ int optmc_fp64_peak(optmc_ctx *ctx, int64_t iters, double *fma_per_sec, double *
    and European SABR-jump, optmc_european*: 1 = draw the path's Poisson(lambda T) count
    and its jump steps once, default while lambda T <= 2; 0 = one Poisson(lambda dt) draw
    per step; two samplers of the same law), "fed_stream" (optmc_fed_async: 1 = one thread streams one row, default;
-   0 = the shared-memory tiled kernel), "euro_wide" (European kernels on lane-replicated tables,
-   one block per SM: 1 = always, 0 = never, default: by job size), "lsmc_ring" (sweep of the
+   0 = the shared-memory tiled kernel), "euro_wide" (1, default: European jobs of at least one row of draws run on
+   lane-replicated tables, one block per SM; 0 = always the compact kernel), "lsmc_ring" (sweep of the
    persistent Longstaff-Schwartz kernel fed by a cp.async ring in shared memory: 0 = never,
    1 = always, 2 = from 2^19 paths per GPU, default), "lsmc_timing_all" (diagnostics: every
    block stamps, see "lsmc_timing"). */
