@@ -473,7 +473,7 @@ class Engine:
 
     # -- Longstaff-Schwartz ---------------------------------------------------
     def lsmc_store(self, n_paths, n_steps):
-        ld = (int(n_paths) + 1) // 2 * 2 + int(os.environ.get("OPTMC_LD_PAD", 0))
+        ld = (int(n_paths) + 1) // 2 * 2
         return self.buffer("lsmc_store", ld * int(n_steps)), ld
 
     def lsmc_fill_paths(self, model, sim, store, ld):
