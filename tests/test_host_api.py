@@ -465,3 +465,28 @@ def test_no_cp_async_with_unset_uniform_registers_in_the_built_library():
     assert len(copies) >= 30                      # the ring kernels are in the library
     bad = [ln.strip() for ln in copies if re.search(r"\[R\d+\+UR\d+", ln)]
     assert not bad, bad[:3]
+
+
+def test_theta_from_one_simulation_guards():
+    """GBM theta is read off one simulation only where the identity behind it holds: the
+    maturity bumps keep the step count (steps_per_year may round T +- h to another grid), the
+    device RNG is in use, and the model is GBM; everything else goes through the mixin's two
+    re-pricings (here: a model with its own exact sampler, counted)."""
+    t = ob.MonteCarloTechnique(n_paths=100, n_steps=10)
+    assert t._theta_steps_ok(1.0, 1e-5)
+    t = ob.MonteCarloTechnique(n_paths=100, n_steps=10, steps_per_year=252)
+    assert t._theta_steps_ok(1.0, 1e-5)
+    assert not t._theta_steps_ok(10.5 / 252 - 1e-6, 1e-5)       # T + h rounds to 11 steps, T to 10
+    model = MagicMock()
+    model.supports_sde = True
+    model.has_exact_sampler = True
+    model.name = "mock"
+    model.sample_terminal_spot.side_effect = lambda S0, r, T, n: np.full(n, S0 * math.exp(r * T) * 1.01)
+    t = ob.MonteCarloTechnique(n_paths=1000, n_steps=4, seed=3)
+    opt = ob.Option(strike=100.0, maturity=1.0, option_type=ob.OptionType.CALL)
+    th = t.theta(opt, ob.Stock(spot=100.0), model, ob.Rate(rate=0.05))
+    assert model.sample_terminal_spot.call_count == 2              # T + h and T - h
+    assert sorted(c.args[2] for c in model.sample_terminal_spot.call_args_list) == pytest.approx(
+        [1.0 - 1e-5, 1.0 + 1e-5])
+    # deterministic terminal S0 e^{rT} 1.01: price = 1.01 S0 - K e^{-rT}, theta = -r K e^{-rT}
+    assert th == pytest.approx(-0.05 * 100.0 * math.exp(-0.05), rel=1e-5)
