@@ -176,7 +176,9 @@ __device__ __forceinline__ void simulate_draw(const EuroArgs &A, uint64_t id, S 
     constexpr bool MIRROR = DEFER && !TWO;
     // SABR kinds with the hand-written maths: log-vol form, one exponential per step
     // (BGEN: the host has seen that beta is neither 0 nor 1 -- no switch in the step)
-    constexpr int LOGV = (kind_sabr(KIND) && NIMPL == 1) ? (BGEN ? 2 : 1) : 0;
+    // (3: spot scenarios with a general beta -- power tables, see step_sabr)
+    constexpr int LOGV = (kind_sabr(KIND) && NIMPL == 1)
+                             ? (BGEN ? (scen_count<decltype(sa.x)>::value > 1 ? 3 : 2) : 1) : 0;
     init_state<KIND, DEFER, LOGV>(sa, c);
     init_state<KIND, DEFER, LOGV>(sb, c);
     sa.j = sb.j = 0.0;
@@ -591,8 +593,23 @@ template <int KIND, bool ANTI, int NS, bool SCHED = false, bool BGEN = false>
 __global__ void __launch_bounds__(scen_threads(SCHED), 1) k_european_scen(const EuroArgs A) {
     static_assert(kind_sabr(KIND), "spot scenarios share the vol path: SABR kinds");
     extern __shared__ __align__(16) unsigned char wide_smem[];
-    __shared__ double scratch[5 * 32];     // (the tables take 224 of the 227 KB a block can have)
-    const auto tv = fill_rng_tables<WideExpLayout, true>(wide_smem, A.c.m11, A.c.m12, A.c.m21, A.c.m22);
+    __shared__ double scratch[5 * 32];     // (the tables take 221 of the 227 KB a block can have)
+    auto tv = fill_rng_tables<ScenLayout, true>(wide_smem, A.c.m11, A.c.m12, A.c.m21, A.c.m22);
+    if constexpr (BGEN) {
+        // power tables behind the generator's: c_i^beta for the 512 nodes of the log table (its
+        // entries hold -2 / c_i), two copies, and 2^(e beta) for the exponents -64 .. 63
+        double *pc = reinterpret_cast<double *>(wide_smem + ScenLayout::bytes(true));
+        double *pe = reinterpret_cast<double *>(wide_smem + ScenLayout::bytes(true) + POW_C_BYTES);
+        for (int i = threadIdx.x; i < 512; i += blockDim.x) {
+            const double v = pow(-2.0 / g_rng_base.logt[i].x, A.c.beta);
+            pc[2 * i] = v;
+            pc[2 * i + 1] = v;
+        }
+        for (int i = threadIdx.x; i < POW_E_N; i += blockDim.x)
+            pe[i] = exp2(A.c.beta * (double)(i - POW_E_BIAS));
+        tv.pw_c = keep_u32(tv.base + ScenLayout::bytes(true) + (tv.l2 >> 1));
+        tv.pw_e = keep_u32(tv.base + ScenLayout::bytes(true) + POW_C_BYTES);
+    }
     __syncthreads();
     double acc[5 * NS];
 #pragma unroll

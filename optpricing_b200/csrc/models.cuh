@@ -38,6 +38,7 @@ struct Consts {
     double alpha, beta;
     double neg_half_alpha2_dt;
     double log_v0;            // ln v0 (SABR kinds, log-vol form; -600 stands for v0 <= 0)
+    double pw[4];             // (1 + rho)^beta = 1 + r' (pw0 + r' (pw1 + r' (pw2 + r' pw3))), r' = -2 rho
     // correlation of the kernel itself (mc_kernels.py:59,67)
     double rho, rho_bar;
     // Philox mode: (z1, cz) = M (a, b) for iid N(0,1) a, b; sqrt(dt) and, for
@@ -236,11 +237,42 @@ __device__ __forceinline__ void sabr_spot_update(double &x, double v, double z1,
     }
 }
 
+// s^beta for a positive normal s from the tables of the scenario kernel: with s = 2^e m,
+// m = c_i (1 + rho) for the log table's node c_i (|rho| <= 2^-10),
+//   s^beta = 2^(e beta) c_i^beta (1 + rho)^beta,
+// two 8-byte lookups (beta is known at launch; the host expands the binomial series in
+// r' = -2 rho to degree 4: the next term is below 1e-17) and 7 fp64-pipe instructions, where
+// exp(beta ln s) costs 17.  Exponents outside -64 .. 63 are clamped (s is floored at 1e-8).
+template <class V>
+__device__ __forceinline__ double pow_beta(double s_pos, const Consts &c, V t) {
+    const int hi = __double2hiint(s_pos);
+    const double m = __hiloint2double(mantissa_hi(hi, t.k3ff), __double2loint(s_pos));
+    const double2 tb = lds_f64x2(t.log_at((uint32_t)hi));
+    const double r = fma(m, tb.x, 2.0);
+    double p = fma(r, c.pw[3], c.pw[2]);
+    p = fma(p, r, c.pw[1]);
+    p = fma(p, r, c.pw[0]);
+    p = fma(p, r, 1.0);
+    const double tc = lds_f64(t.pw_c + (((uint32_t)hi >> 7) & (511u << 4)));
+    const int e = min(max((hi >> 20) - (1023 - POW_E_BIAS), 0), POW_E_N - 1);
+    const double te = lds_f64(t.pw_e + (uint32_t)e * 8u);
+    return (te * tc) * p;
+}
+
 template <int LOGV, class S, class V>
 __device__ __forceinline__ void step_sabr(S &s, double z1, double cz, const Consts &c, V t) {
     constexpr int NS = scen_count<decltype(s.x)>::value;
     if constexpr (NS == 1) {
         sabr_spot_update<LOGV>(s.x, s.v, z1, c, t);
+    } else if constexpr (LOGV == 3) {
+        // spot scenarios, beta neither 0 nor 1: ONE exponential for the vol state they share,
+        // s^beta per spot from the beta-specific tables (pow_beta)
+        const double vz = fast_exp(floor_neg650(s.v), t) * z1;
+#pragma unroll
+        for (int k = 0; k < NS; ++k) {
+            const double s_pos = floor_1e8(s.x.a[k]);
+            s.x.a[k] += fma(vz, pow_beta(s_pos, c, t), c.rqc_dt * s_pos);
+        }
     } else {
 #pragma unroll
         for (int k = 0; k < NS; ++k) sabr_spot_update<LOGV>(s.x.a[k], s.v, z1, c, t);

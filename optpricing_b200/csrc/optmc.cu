@@ -269,6 +269,13 @@ static int make_consts(optmc_ctx *ctx, const optmc_model *m, double x0, double d
     c.neg_half_alpha2_dt = -0.5 * m->alpha * m->alpha * dt;
     c.log_v0 = m->v0 > 0.0 ? std::max(std::log(m->v0), -600.0) : -600.0;
     c.beta_mode = m->beta == 1.0 ? 1 : m->beta == 0.0 ? 2 : m->beta == 0.5 ? 3 : 0;
+    {   // binomial series of (1 + rho)^beta in r' = -2 rho (models.cuh: pow_beta)
+        const double b = m->beta;
+        c.pw[0] = -b / 2.0;
+        c.pw[1] = b * (b - 1.0) / 8.0;
+        c.pw[2] = -b * (b - 1.0) * (b - 2.0) / 48.0;
+        c.pw[3] = b * (b - 1.0) * (b - 2.0) * (b - 3.0) / 384.0;
+    }
     c.rho = m->rho;
     c.rho_bar = std::sqrt(1 - m->rho * m->rho);                                      // :59
     const double sd = c.sqrt_dt, rho = c.rho, rb = c.rho_bar;
@@ -614,7 +621,7 @@ extern "C" int optmc_european_aux_async(optmc_ctx *ctx, const optmc_model *model
 template <int KIND, bool ANTI, int NS, bool SCHED, bool BGEN>
 static int launch_scen_t(optmc_ctx *ctx, EuroArgs &A, cudaStream_t st, int *grid_out) {
     auto kern = k_european_scen<KIND, ANTI, NS, SCHED, BGEN>;
-    const int smem = (int)WideExpLayout::bytes(true);
+    const int smem = (int)(ScenLayout::bytes(true) + POW_C_BYTES + POW_E_BYTES);
     static bool attr_set[64] = {};
     if (!attr_set[ctx->device & 63]) {
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));

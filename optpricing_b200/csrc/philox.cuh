@@ -247,6 +247,9 @@ struct RngViewT {
     uint32_t l8, l4, l2;    // 16 (l mod 8), 16 (l mod 4), 16 (l mod 2): OR-ed into entry offsets
     uint32_t le;            // 8 (l mod EXP_COPIES)
     uint32_t k3ff;          // 0x3FF00000 held in a register (mantissa_hi)
+    // beta-specific power tables of the SABR scenario kernel (models.cuh: pow_beta), else unused:
+    // per-lane base of c_i^beta (two copies, 8-byte entries) and base of 2^(e beta)
+    uint32_t pw_c = 0, pw_e = 0;
     template <int COPIES>
     __device__ __forceinline__ uint32_t lane16() const {
         static_assert(COPIES == 1 || COPIES == 2 || COPIES == 4 || COPIES == 8, "copies");
@@ -278,6 +281,10 @@ struct RngViewT {
 using CompactLayout = TableLayout<1, 1, 1, 1>;
 using WideLayout = TableLayout<8, 0, 8, 4>;      // Heston, Bates, one-factor models: 160 / 224 KB
 using WideExpLayout = TableLayout<8, 4, 8, 2>;   // SABR kinds (exp table in the step): 224 KB
+using ScenLayout = TableLayout<8, 1, 8, 2>;      // SABR spot scenarios: one exp per vol state and step
+                                                 // only (212 KB) + 9 KB of power tables behind it
+constexpr int POW_E_N = 128, POW_E_BIAS = 64;    // 2^(e beta) for the binary exponents -64 .. 63
+constexpr uint32_t POW_C_BYTES = 512u * 2u * 8u, POW_E_BYTES = (uint32_t)POW_E_N * 8u;
 using RngView = RngViewT<CompactLayout>;
 using RngViewW = RngViewT<WideLayout>;
 using RngViewS = RngViewT<WideExpLayout>;
