@@ -452,7 +452,7 @@ __host__ __device__ constexpr int euro_min_blocks(int kind, int nimpl, bool sche
     return OPTMC_EURO_MIN_BLOCKS_ALL;
 #else
     // (the library-maths variants and the SABR-jump kernels -- inlined jump code; the scheduled
-    // one keeps eight jump factors in its jump groups -- spill at 64 registers)
+    // one keeps its jump schedule and pending jump in registers -- spill at 64 registers)
     return (kind == OPTMC_HESTON || kind == OPTMC_BATES || kind == OPTMC_DUPIRE || nimpl == 0 ||
             kind == OPTMC_SABR_JUMP)
                ? OPTMC_EURO_MIN_BLOCKS : 4;
