@@ -490,3 +490,41 @@ def test_theta_from_one_simulation_guards():
         [1.0 - 1e-5, 1.0 + 1e-5])
     # deterministic terminal S0 e^{rT} 1.01: price = 1.01 S0 - K e^{-rT}, theta = -r K e^{-rT}
     assert th == pytest.approx(-0.05 * 100.0 * math.exp(-0.05), rel=1e-5)
+
+
+def test_pow_beta_table_scheme_is_accurate_by_emulation():
+    """pow_beta (csrc/models.cuh; the SABR scenario kernel): s^beta = 2^(e beta) c_i^beta (1 + rho)^beta
+    with the log table's nodes c_i, the binomial series to degree 4 in r' = -2 rho with the host's
+    coefficients (optmc.cu) and fused multiply-adds.  Emulated with exact rational FMAs over spots
+    from 1e-8 (the floor) to 1e12 and several beta: relative error below 3e-15 (a few ulp: three roundings
+    of the product, one of each table entry) -- the scenario
+    prices then equal bumped re-pricings far inside the 1e-9 the GPU test asserts."""
+    from fractions import Fraction as F
+
+    def fma(a, b, c):
+        return float(F(a) * F(b) + F(c))
+
+    rng = np.random.default_rng(8)
+    spots = np.concatenate([10.0 ** rng.uniform(-8, 12, 300), [1e-8, 1.0, 100.0, 2.0 - 2.0 ** -52,
+                                                              1.0 + 2.0 ** -52, 65536.0]])
+    for beta in (0.8, 0.5, 0.3, 0.999, 0.05):
+        pw = [-beta / 2.0, beta * (beta - 1.0) / 8.0, -beta * (beta - 1.0) * (beta - 2.0) / 48.0,
+              beta * (beta - 1.0) * (beta - 2.0) * (beta - 3.0) / 384.0]
+        worst = 0.0
+        for s in spots:
+            m, e = math.frexp(float(s))            # s = m 2^e, m in [0.5, 1)
+            m, e = 2.0 * m, e - 1                  # m in [1, 2): the mantissa the kernel rebuilds
+            i = int((m - 1.0) * 512)
+            c = 1.0 + (i + 0.5) / 512
+            tx = -2.0 / c                          # optmc.cu: RngBase.logt[i].x
+            r = fma(m, tx, 2.0)
+            p = fma(r, pw[3], pw[2])
+            p = fma(p, r, pw[1])
+            p = fma(p, r, pw[0])
+            p = fma(p, r, 1.0)
+            tc = (-2.0 / tx) ** beta               # european.cuh: pow(-2 / logt[i].x, beta)
+            te = 2.0 ** (beta * e)                 # exp2(beta (k - 64)), k = e + 64 in 0 .. 127
+            assert 0 <= e + 64 <= 127
+            got = (te * tc) * p
+            worst = max(worst, abs(got / float(s) ** beta - 1.0))
+        assert worst < 3e-15, (beta, worst)
